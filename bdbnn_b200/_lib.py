@@ -1,0 +1,85 @@
+"""ctypes binding of libbdbnn_b200.so (the C ABI in include/bdbnn.h).
+
+There is NO CPU fallback and no PyTorch-eager fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbdbnn_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_void_p, c_int, c_int64, c_size_t = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+
+
+class ConvShape(ctypes.Structure):
+    """Mirror of `bdbnn_conv_shape` (include/bdbnn.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "Ho", "Wo")]
+
+
+_P = c_void_p
+_SH = ctypes.POINTER(ConvShape)
+# name -> (restype, argtypes); MUST list every symbol include/bdbnn.h declares (tests check this).
+SIGNATURES = {
+    "bdbnn_version": (c_int, []),
+    "bdbnn_last_error_string": (ctypes.c_char_p, []),
+    "bdbnn_tc_supported": (c_int, [_SH]),
+    "bdbnn_act_pack": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P]),
+    "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bdbnn_binconv_fwd_xnor": (c_int, [_P, _P, _P, _P, _SH, _P]),
+    "bdbnn_binconv_fwd_tc": (c_int, [_P, _P, _P, _P, _SH, _P]),
+    "bdbnn_binconv_dgrad": (c_int, [_P, _P, _P, _P, _P, _SH, _P]),
+    "bdbnn_binconv_wgrad": (c_int, [_P, _P, _P, _P, _SH, _P]),
+    "bdbnn_grad_pack": (c_int, [_P, _P, c_int64, c_int, _P, _P]),
+    "bdbnn_binconv_dgrad_tc": (c_int, [_P, _P, _P, _P, _SH, _P]),
+    "bdbnn_wgrad_tc_workspace_bytes": (c_size_t, [_SH]),
+    "bdbnn_binconv_wgrad_tc": (c_int, [_P, _P, _P, _P, _P, _SH, _P, c_size_t, _P]),
+    "bdbnn_kurtosis_multi_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P]),
+    "bdbnn_kurtosis_multi_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P]),
+    "bdbnn_kd_logits_fwd_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
+    "bdbnn_kd_layer_multi_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P]),
+    "bdbnn_kd_layer_multi_bwd": (c_int, [_P, _P, c_int, _P, _P, c_int, _P]),
+}
+
+
+def lib():
+    """Load (once) and return the ctypes handle. Raises RuntimeError if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"bdbnn_b200: {LIB_PATH} not found. Build it with `python -m bdbnn_b200.build` "
+                "(nvcc, sm_100a). There is no CPU / eager fallback.")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().bdbnn_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"bdbnn_b200: {what} failed with code {rc}: {msg}")
+
+
+def launch_count():
+    """Number of kernels this process launched through the C ABI (bench.py reports it)."""
+    return _launches[0]
+
+
+_launches = [0]
+
+
+def count(n=1):
+    _launches[0] += n

@@ -1,0 +1,217 @@
+// Sign / bit-pack kernels (HBM-streaming).  See include/bdbnn.h for the contracts.
+//
+//   act_pack    : fp32 NHWC activations -> sign bits + STE mask bits (+ optional +-1 bf16 copy)
+//   weight_pack : fp32 OIHW weights     -> alpha, sign bits [o][tap][cw], STE mask bits, bf16 operands
+//   grad_pack   : fp32 NHWC grad        -> bf16(gy * gscale[o])
+//
+// Spec: sign(x) := (x >= 0) ? +1 : -1 ; STE mask := |x| <= 1.
+#include "common.cuh"
+
+namespace bdbnn {
+
+constexpr int kPackUnroll = 8;
+
+// One warp produces kPackUnroll words per iteration: lane j of the warp owns channel 32k+j of the
+// word; __ballot_sync assembles the word.  Loads are issued kPackUnroll-deep before any ballot so
+// each thread keeps 8 independent 4-byte requests in flight (enough bytes in flight to stream HBM at
+// full occupancy; every warp-load is one 128-byte line).
+__global__ void __launch_bounds__(256)
+act_pack_kernel(const float* __restrict__ x, int64_t n_words, int32_t C, int32_t Cw,
+                uint32_t* __restrict__ sign_bits, uint32_t* __restrict__ mask_bits,
+                uint16_t* __restrict__ xb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const bool flat = (C & 31) == 0;
+
+  for (int64_t w0 = warp_global * kPackUnroll; w0 < n_words; w0 += n_warps * kPackUnroll) {
+    float v[kPackUnroll];
+    int64_t idx[kPackUnroll];
+    bool ok[kPackUnroll];
+#pragma unroll
+    for (int j = 0; j < kPackUnroll; ++j) {
+      const int64_t wi = w0 + j;
+      if (flat) {
+        idx[j] = wi * 32 + lane;
+        ok[j] = wi < n_words;
+      } else {
+        const int64_t p = wi / Cw;
+        const int k = int(wi - p * Cw);
+        const int c = k * 32 + lane;
+        idx[j] = p * C + c;
+        ok[j] = (wi < n_words) && (c < C);
+      }
+      v[j] = ok[j] ? __ldcs(x + idx[j]) : __int_as_float(0x7fc00000);  // NaN -> both bits 0
+    }
+    uint32_t my_sign = 0, my_mask = 0;
+#pragma unroll
+    for (int j = 0; j < kPackUnroll; ++j) {
+      const uint32_t sb = __ballot_sync(0xffffffffu, v[j] >= 0.0f);
+      const uint32_t mb = __ballot_sync(0xffffffffu, fabsf(v[j]) <= 1.0f);
+      if (lane == j) { my_sign = sb; my_mask = mb; }
+      if (xb != nullptr && ok[j]) xb[idx[j]] = (v[j] >= 0.0f) ? uint16_t(0x3F80) : uint16_t(0xBF80);
+    }
+    if (lane < kPackUnroll && (w0 + lane) < n_words) {
+      sign_bits[w0 + lane] = my_sign;
+      mask_bits[w0 + lane] = my_mask;
+    }
+  }
+}
+
+// One block per output channel.
+__global__ void __launch_bounds__(256)
+weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32_t T, int32_t Cw,
+                   float* __restrict__ alpha, uint32_t* __restrict__ wsign,
+                   uint16_t* __restrict__ wf, uint16_t* __restrict__ wt,
+                   float* __restrict__ gscale, float* __restrict__ inv_gscale) {
+  const int o = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int per = Cin * T;
+  const float* Wo = W + int64_t(o) * per;
+
+  __shared__ float red[32];
+  __shared__ float s_alpha;
+  float a = 0.f;
+  for (int i = tid; i < per; i += blockDim.x) a += fabsf(Wo[i]);
+  a = warp_sum(a);
+  if (lane == 0) red[warp] = a;
+  __syncthreads();
+  if (warp == 0) {
+    float t = (lane < nwarps) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) {
+      const float al = t / float(per);
+      s_alpha = al;
+      alpha[o] = al;
+      const float g = (al > 0.f) ? al : 1.f;
+      if (gscale) gscale[o] = g;
+      if (inv_gscale) inv_gscale[o] = 1.0f / g;
+    }
+  }
+  __syncthreads();
+  const bool live = s_alpha > 0.f;
+
+  // sign words [o][t][k]
+  for (int w = warp; w < T * Cw; w += nwarps) {
+    const int t = w / Cw, k = w - t * Cw;
+    const int c = k * 32 + lane;
+    const bool ok = c < Cin;
+    const float v = ok ? Wo[c * T + t] : -1.0f;
+    const uint32_t sb = __ballot_sync(0xffffffffu, ok && (v >= 0.0f));
+    if (lane == 0) wsign[(int64_t(o) * T + t) * Cw + k] = sb;
+  }
+  // bf16 operands for the tensor-core path
+  if (wf != nullptr || wt != nullptr) {
+    for (int i = tid; i < per; i += blockDim.x) {
+      const int t = i / Cin, c = i - t * Cin;  // (t, c) with c fastest: coalesced wf writes
+      const float v = Wo[c * T + t];
+      const uint16_t sg = (v >= 0.0f) ? uint16_t(0x3F80) : uint16_t(0xBF80);
+      if (wf) wf[(int64_t(o) * T + t) * Cin + c] = sg;
+      if (wt) wt[(int64_t(c) * T + (T - 1 - t)) * Cout + o] = live ? sg : uint16_t(0);
+    }
+  }
+}
+
+// |W| <= 1 bits over the flat OIHW tensor.
+__global__ void __launch_bounds__(256)
+flat_mask_kernel(const float* __restrict__ W, int64_t n, uint32_t* __restrict__ mask_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int64_t n_words = (n + 31) / 32;
+  for (int64_t wi = warp_global; wi < n_words; wi += n_warps) {
+    const int64_t e = wi * 32 + lane;
+    const bool ok = e < n;
+    const float v = ok ? W[e] : 2.0f;
+    const uint32_t mb = __ballot_sync(0xffffffffu, ok && fabsf(v) <= 1.0f);
+    if (lane == 0) mask_bits[wi] = mb;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// gys[i] = bf16_rn(gy[i] * gscale[i % Cout]); Cout % 4 == 0 fast path, scalar tail otherwise.
+__global__ void __launch_bounds__(256)
+grad_pack_kernel(const float* __restrict__ gy, const float* __restrict__ gscale, int64_t n,
+                 int32_t Cout, uint16_t* __restrict__ out) {
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  if ((Cout & 3) == 0) {
+    const int64_t n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(gy);
+    uint2* o2 = reinterpret_cast<uint2*>(out);
+    for (int64_t i = tid; i < n4; i += nthreads) {
+      const float4 v = __ldcs(g4 + i);
+      const int o = int((i * 4) % Cout);
+      const float4 s = *reinterpret_cast<const float4*>(gscale + o);
+      uint2 r;
+      r.x = pack_bf16x2(v.x * s.x, v.y * s.y);
+      r.y = pack_bf16x2(v.z * s.z, v.w * s.w);
+      o2[i] = r;
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) {
+      const float v = gy[i] * gscale[i % Cout];
+      out[i] = uint16_t(pack_bf16x2(v, 0.f) & 0xffffu);
+    }
+  }
+}
+
+}  // namespace bdbnn
+
+using namespace bdbnn;
+
+extern "C" int bdbnn_act_pack(const float* x, int64_t n_pix, int32_t C, uint32_t* sign_bits,
+                              uint32_t* mask_bits, uint16_t* xb_bf16, void* stream) {
+  BDBNN_REQUIRE(n_pix >= 0 && C > 0, "act_pack: bad n_pix/C");
+  if (n_pix == 0) return BDBNN_OK;
+  BDBNN_REQUIRE(x && sign_bits && mask_bits, "act_pack: NULL pointer");
+  const int32_t Cw = (C + 31) / 32;
+  const int64_t n_words = n_pix * Cw;
+  const int threads = 256;
+  const int64_t warps_needed = (n_words + kPackUnroll - 1) / kPackUnroll;
+  int64_t blocks = (warps_needed * 32 + threads - 1) / threads;
+  const int64_t cap = int64_t(num_sms()) * 8 * 4;  // a few waves of full-occupancy blocks
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  act_pack_kernel<<<unsigned(blocks), threads, 0, cudaStream_t(stream)>>>(
+      x, n_words, C, Cw, sign_bits, mask_bits, xb_bf16);
+  return check_launch("act_pack_kernel");
+}
+
+extern "C" int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
+                                 float* alpha, uint32_t* wsign_bits, uint32_t* wmask_bits,
+                                 uint16_t* wf_bf16, uint16_t* wt_bf16, float* gscale,
+                                 float* inv_gscale, void* stream) {
+  BDBNN_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "weight_pack: bad dims");
+  BDBNN_REQUIRE(W && alpha && wsign_bits && wmask_bits, "weight_pack: NULL pointer");
+  const int32_t T = kh * kw, Cw = (Cin + 31) / 32;
+  weight_pack_kernel<<<Cout, 256, 0, cudaStream_t(stream)>>>(W, Cout, Cin, T, Cw, alpha, wsign_bits,
+                                                            wf_bf16, wt_bf16, gscale, inv_gscale);
+  int rc = check_launch("weight_pack_kernel");
+  if (rc) return rc;
+  const int64_t n = int64_t(Cout) * Cin * T;
+  const int64_t n_words = (n + 31) / 32;
+  int64_t blocks = (n_words * 32 + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  flat_mask_kernel<<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(W, n, wmask_bits);
+  return check_launch("flat_mask_kernel");
+}
+
+extern "C" int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_pix, int32_t Cout,
+                               uint16_t* gys_bf16, void* stream) {
+  BDBNN_REQUIRE(n_pix >= 0 && Cout > 0, "grad_pack: bad dims");
+  if (n_pix == 0) return BDBNN_OK;
+  BDBNN_REQUIRE(gy && gscale && gys_bf16, "grad_pack: NULL pointer");
+  const int64_t n = n_pix * Cout;
+  int64_t blocks = ((n >> 2) + 255) / 256;
+  const int64_t cap = int64_t(num_sms()) * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  grad_pack_kernel<<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(gy, gscale, n, Cout, gys_bf16);
+  return check_launch("grad_pack_kernel");
+}

@@ -1,0 +1,295 @@
+"""torch.autograd.Function wrappers over the C ABI (include/bdbnn.h).
+
+PyTorch supplies device memory, streams and autograd bookkeeping only; every arithmetic step of the
+hot path is a kernel in libbdbnn_b200.so.  CUDA tensors are mandatory: CPU tensors raise."""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+from ._lib import ConvShape
+
+_IMPL_ENV = "BDBNN_IMPL"          # auto | xnor | tc
+_VALID_IMPL = ("auto", "xnor", "tc")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"bdbnn_b200.{what}: expected a CUDA tensor, got device={t.device}. "
+                           "The B200 path has no CPU fallback (use oracle/ for CPU checking).")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"bdbnn_b200.{what}: expected float32, got {t.dtype}")
+
+
+def _nhwc(t):
+    """Return t with NHWC physical layout (no copy if it already is channels_last)."""
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def conv_shape(x_shape, w_shape, stride, padding):
+    n, cin, h, w = x_shape
+    cout, cin_w, kh, kw = w_shape
+    if cin != cin_w:
+        raise RuntimeError(f"bdbnn_b200.binconv2d: input has {cin} channels, weight expects {cin_w}")
+    ho = (h + 2 * padding - kh) // stride + 1
+    wo = (w + 2 * padding - kw) // stride + 1
+    if ho <= 0 or wo <= 0:
+        raise RuntimeError("bdbnn_b200.binconv2d: empty output")
+    return ConvShape(n, h, w, cin, cout, kh, kw, stride, padding, ho, wo)
+
+
+def resolve_impl(impl, shape):
+    impl = impl or os.environ.get(_IMPL_ENV, "auto")
+    if impl not in _VALID_IMPL:
+        raise ValueError(f"impl must be one of {_VALID_IMPL}, got {impl!r}")
+    tc_ok = bool(_lib.lib().bdbnn_tc_supported(ctypes.byref(shape)))
+    if impl == "tc" and not tc_ok:
+        raise RuntimeError("bdbnn_b200: impl='tc' requested but the tcgen05 path does not support this shape")
+    return "tc" if (impl in ("auto", "tc") and tc_ok) else "xnor"
+
+
+class _BinConv2d(torch.autograd.Function):
+    """y = alpha[o] * conv2d(sign(x), sign(W)) with STE backward (spec: DESIGN.md §2).
+
+    forward  : act_pack (sign+mask bits [+bf16 copy]) -> weight_pack -> binconv_fwd_{xnor|tc}
+    backward : [grad_pack ->] dgrad (mask fused) , wgrad (mask fused)
+    Saved for backward: bits only (plus the bf16 +-1 copy on the tensor-core path) — never fp32 x."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding, impl):
+        _require_cuda(x, "binconv2d(x)")
+        _require_cuda(weight, "binconv2d(weight)")
+        L = _lib.lib()
+        sh = conv_shape(x.shape, weight.shape, stride, padding)
+        use = resolve_impl(impl, sh)
+        dev = x.device
+        xc = _nhwc(x.detach())
+        w = weight.detach().contiguous()
+        n, cin, h, wd = x.shape
+        cout, _, kh, kw = weight.shape
+        cw = (cin + 31) // 32
+        T = kh * kw
+        st = _stream()
+        i32 = dict(dtype=torch.int32, device=dev)
+        sign_bits = torch.empty((n, h, wd, cw), **i32)
+        mask_bits = torch.empty((n, h, wd, cw), **i32)
+        tc = use == "tc"
+        xb = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=dev) if tc else None
+        _lib.check(L.bdbnn_act_pack(_p(xc), n * h * wd, cin, _p(sign_bits), _p(mask_bits), _p(xb), st),
+                   "act_pack")
+        alpha = torch.empty((cout,), dtype=torch.float32, device=dev)
+        wsign = torch.empty((cout, T, cw), **i32)
+        wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
+        wf = wt = gscale = inv_gscale = None
+        if tc:
+            wf = torch.empty((cout, T, cin), dtype=torch.bfloat16, device=dev)
+            wt = torch.empty((cin, T, cout), dtype=torch.bfloat16, device=dev)
+            gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
+            inv_gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
+        _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask),
+                                       _p(wf), _p(wt), _p(gscale), _p(inv_gscale), st), "weight_pack")
+        y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
+                        memory_format=torch.channels_last)
+        if tc:
+            _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), ctypes.byref(sh), st),
+                       "binconv_fwd_tc")
+        else:
+            _lib.check(L.bdbnn_binconv_fwd_xnor(_p(sign_bits), _p(wsign), _p(alpha), _p(y),
+                                                ctypes.byref(sh), st), "binconv_fwd_xnor")
+        _lib.count(4)
+        ctx.sh = sh
+        ctx.use = use
+        ctx.x_shape = tuple(x.shape)
+        ctx.w_shape = tuple(weight.shape)
+        if tc:
+            ctx.save_for_backward(sign_bits, mask_bits, wsign, wmask, alpha, xb, wt, gscale, inv_gscale)
+        else:
+            ctx.save_for_backward(sign_bits, mask_bits, wsign, wmask, alpha)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.lib()
+        sh = ctx.sh
+        st = _stream()
+        dev = gy.device
+        g = _nhwc(gy)
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx = gw = None
+        saved = ctx.saved_tensors
+        sign_bits, mask_bits, wsign, wmask, alpha = saved[:5]
+        if ctx.use == "tc":
+            xb, wt, gscale, inv_gscale = saved[5:]
+            n_pix_out = sh.N * sh.Ho * sh.Wo
+            gys = torch.empty((sh.N, sh.Ho, sh.Wo, sh.Cout), dtype=torch.bfloat16, device=dev)
+            _lib.check(L.bdbnn_grad_pack(_p(g), _p(gscale), n_pix_out, sh.Cout, _p(gys), st), "grad_pack")
+            _lib.count(1)
+            if need_x:
+                gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev,
+                                 memory_format=torch.channels_last)
+                _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), _p(wt), _p(mask_bits), _p(gx),
+                                                    ctypes.byref(sh), st), "binconv_dgrad_tc")
+                _lib.count(1)
+            if need_w:
+                gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
+                nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
+                ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+                _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
+                                                    ctypes.byref(sh), _p(ws), nbytes, st), "binconv_wgrad_tc")
+                _lib.count(2)
+        else:
+            if need_x:
+                gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev,
+                                 memory_format=torch.channels_last)
+                _lib.check(L.bdbnn_binconv_dgrad(_p(g), _p(wsign), _p(alpha), _p(mask_bits), _p(gx),
+                                                 ctypes.byref(sh), st), "binconv_dgrad")
+                _lib.count(1)
+            if need_w:
+                gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
+                _lib.check(L.bdbnn_binconv_wgrad(_p(g), _p(sign_bits), _p(wmask), _p(gw),
+                                                 ctypes.byref(sh), st), "binconv_wgrad")
+                _lib.count(1)
+        return gx, gw, None, None, None
+
+
+def binconv2d(x, weight, stride=1, padding=1, impl=None):
+    """1W/1A binarised conv2d. x [N,Cin,H,W] fp32 CUDA (any strides; NHWC is copy-free),
+    weight [Cout,Cin,kh,kw] fp32. Returns [N,Cout,Ho,Wo] fp32 (channels_last strides)."""
+    return _BinConv2d.apply(x, weight, int(stride), int(padding), impl)
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _KurtosisMulti(torch.autograd.Function):
+    """All hooked layers' kurtosis losses in two launches (fwd) + one (bwd).
+    Replaces 19x KurtosisWeight.kurtosis_calc (kurtosis.py:23-39)."""
+
+    @staticmethod
+    def forward(ctx, targets, *weights):
+        L = _lib.lib()
+        n = len(weights)
+        if n == 0 or n > 64:
+            raise RuntimeError(f"kurtosis_multi: need 1..64 tensors, got {n}")
+        ws = []
+        for w in weights:
+            _require_cuda(w, "kurtosis_multi")
+            ws.append(w.detach().contiguous())
+        dev = ws[0].device
+        numel = (ctypes.c_int64 * n)(*[w.numel() for w in ws])
+        tg = (ctypes.c_float * n)(*[float(t) for t in targets])
+        moments = torch.empty((n * 8,), dtype=torch.float64, device=dev)
+        kurt = torch.empty((n,), dtype=torch.float32, device=dev)
+        loss = torch.empty((n,), dtype=torch.float32, device=dev)
+        _lib.check(L.bdbnn_kurtosis_multi_fwd(_ptr_array(ws), numel, tg, n, _p(moments), _p(kurt),
+                                              _p(loss), _stream()), "kurtosis_multi_fwd")
+        _lib.count(2)
+        ctx.targets = tuple(float(t) for t in targets)
+        ctx.save_for_backward(moments, *ws)
+        ctx.mark_non_differentiable(kurt)
+        return loss, kurt
+
+    @staticmethod
+    def backward(ctx, gloss, _gkurt):
+        L = _lib.lib()
+        moments, *ws = ctx.saved_tensors
+        n = len(ws)
+        grads = [torch.empty_like(w) for w in ws]
+        numel = (ctypes.c_int64 * n)(*[w.numel() for w in ws])
+        tg = (ctypes.c_float * n)(*ctx.targets)
+        gout = gloss.contiguous()
+        _lib.check(L.bdbnn_kurtosis_multi_bwd(_ptr_array(ws), numel, tg, n, _p(moments), _p(gout),
+                                              _ptr_array(grads), 0, _stream()), "kurtosis_multi_bwd")
+        _lib.count(1)
+        return (None, *grads)
+
+
+def kurtosis_multi(weights, targets):
+    """Returns (loss[L], kurtosis[L]) for weight tensors `weights` and python-float `targets`."""
+    return _KurtosisMulti.apply(tuple(targets), *weights)
+
+
+class _KDLogits(torch.autograd.Function):
+    """DistributionLoss.forward (utils/KD_loss.py:16-43): loss and d loss/d s in one pass."""
+
+    @staticmethod
+    def forward(ctx, s, t):
+        _require_cuda(s, "kd_logits(stud)")
+        _require_cuda(t, "kd_logits(teacher)")
+        if s.dim() != 2 or s.shape != t.shape:
+            raise RuntimeError(f"kd_logits: expected matching [N,C] tensors, got {tuple(s.shape)} {tuple(t.shape)}")
+        L = _lib.lib()
+        sc, tc = s.detach().contiguous(), t.detach().contiguous()
+        n, c = sc.shape
+        row = torch.empty((n,), dtype=torch.float32, device=s.device)
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        grad = torch.empty_like(sc) if ctx.needs_input_grad[0] else None
+        _lib.check(L.bdbnn_kd_logits_fwd_bwd(_p(sc), _p(tc), n, c, _p(row), _p(loss), _p(grad), _stream()),
+                   "kd_logits_fwd_bwd")
+        _lib.count(2)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return (grad * gout if grad is not None else None), None
+
+
+def kd_logits_loss(stud_logits, teacher_logits):
+    return _KDLogits.apply(stud_logits, teacher_logits)
+
+
+class _KDLayerMulti(torch.autograd.Function):
+    """sum_l KLDivLoss(log_target=True)(Ws_l, Wt_l) (utils/KD_loss.py:52-67) in two launches."""
+
+    @staticmethod
+    def forward(ctx, n_pairs, *tensors):
+        L = _lib.lib()
+        ws = [t.detach().contiguous() for t in tensors[:n_pairs]]
+        wt = [t.detach().contiguous() for t in tensors[n_pairs:]]
+        if len(wt) != n_pairs or n_pairs == 0 or n_pairs > 64:
+            raise RuntimeError("kd_layer_multi: need 1..64 (student, teacher) pairs")
+        for a, b in zip(ws, wt):
+            _require_cuda(a, "kd_layer_multi")
+            _require_cuda(b, "kd_layer_multi")
+            if a.shape != b.shape:
+                raise RuntimeError(f"kd_layer_multi: shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+        dev = ws[0].device
+        numel = (ctypes.c_int64 * n_pairs)(*[w.numel() for w in ws])
+        partial = torch.empty((n_pairs,), dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(L.bdbnn_kd_layer_multi_fwd(_ptr_array(ws), _ptr_array(wt), numel, n_pairs, _p(partial),
+                                              _p(loss), _stream()), "kd_layer_multi_fwd")
+        _lib.count(2)
+        ctx.n_pairs = n_pairs
+        ctx.save_for_backward(*wt)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        L = _lib.lib()
+        wt = list(ctx.saved_tensors)
+        n = ctx.n_pairs
+        grads = [torch.empty_like(w) for w in wt]
+        numel = (ctypes.c_int64 * n)(*[w.numel() for w in wt])
+        g = gout.contiguous().reshape(1)
+        _lib.check(L.bdbnn_kd_layer_multi_bwd(_ptr_array(wt), numel, n, _p(g), _ptr_array(grads), 0,
+                                              _stream()), "kd_layer_multi_bwd")
+        _lib.count(1)
+        return (None, *grads, *([None] * n))
+
+
+def kd_layer_loss(student_weights, teacher_weights):
+    """Student/teacher weight lists of equal length and matching shapes -> 0-d loss."""
+    return _KDLayerMulti.apply(len(student_weights), *student_weights, *teacher_weights)

@@ -1,0 +1,131 @@
+"""Network shells the binary convs sit in ("needed shell", stock topology).
+
+torchvision-style naming is part of the contract: `conv1` is the fp32 stem the kurtosis hooks skip
+(train.py:393 drops all_convs[0]), shortcuts are called `downsample` (utils/KD_loss.py:64), and an
+ImageNet ResNet-18 exposes exactly 19 hookable convs after the stem (16 binary 3x3 + 3 fp32 1x1;
+train.py:467-470 lists 19 targets).  Blocks follow Bi-Real-Net: one shortcut per binary conv, no
+non-linearity other than the sign inside the conv.
+
+The builders take `conv_cls` so the CPU oracle (oracle/models_ref.py) can instantiate the same
+topology around its pure-PyTorch conv."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .modules import HardBinaryConv, HardBinaryConv_cifar
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, conv_cls=HardBinaryConv):
+        super().__init__()
+        self.conv1 = conv_cls(inplanes, planes, 3, stride, 1)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = conv_cls(planes, planes, 3, 1, 1)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+
+    def forward(self, x):
+        residual = x if self.downsample is None else self.downsample(x)
+        out = self.bn1(self.conv1(x)) + residual
+        return self.bn2(self.conv2(out)) + out
+
+
+class ResNetImageNet(nn.Module):
+    """ResNet-18/34 for 224x224 inputs; binary 3x3 convs, fp32 stem / 1x1 shortcuts / classifier."""
+
+    def __init__(self, layers, num_classes=1000, conv_cls=HardBinaryConv):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = self._make_layer(64, layers[0], 1, conv_cls)
+        self.layer2 = self._make_layer(128, layers[1], 2, conv_cls)
+        self.layer3 = self._make_layer(256, layers[2], 2, conv_cls)
+        self.layer4 = self._make_layer(512, layers[3], 2, conv_cls)
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(512, num_classes)
+
+    def _make_layer(self, planes, blocks, stride, conv_cls):
+        downsample = None
+        if stride != 1 or self.inplanes != planes:
+            downsample = nn.Sequential(
+                nn.Conv2d(self.inplanes, planes, kernel_size=1, stride=stride, bias=False),
+                nn.BatchNorm2d(planes))
+        layers = [BasicBlock(self.inplanes, planes, stride, downsample, conv_cls)]
+        self.inplanes = planes
+        for _ in range(1, blocks):
+            layers.append(BasicBlock(planes, planes, conv_cls=conv_cls))
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.maxpool(self.bn1(self.conv1(x)))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+class _PadShortcut(nn.Module):
+    """Parameter-free CIFAR shortcut (option A): stride-2 subsample + zero-pad channels."""
+
+    def __init__(self, planes):
+        super().__init__()
+        self.pad = planes // 4
+
+    def forward(self, x):
+        return F.pad(x[:, :, ::2, ::2], (0, 0, 0, 0, self.pad, self.pad), "constant", 0.0)
+
+
+class BasicBlockCifar(nn.Module):
+    def __init__(self, inplanes, planes, stride=1, conv_cls=HardBinaryConv_cifar):
+        super().__init__()
+        self.conv1 = conv_cls(inplanes, planes, 3, stride, 1)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = conv_cls(planes, planes, 3, 1, 1)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.shortcut = _PadShortcut(planes) if (stride != 1 or inplanes != planes) else None
+
+    def forward(self, x):
+        residual = x if self.shortcut is None else self.shortcut(x)
+        out = self.bn1(self.conv1(x)) + residual
+        return self.bn2(self.conv2(out)) + out
+
+
+class ResNetCifar(nn.Module):
+    """ResNet-20-style CIFAR net: fp32 3x3 stem + 3 stages x n blocks (18 binary convs for n=3)."""
+
+    def __init__(self, n_blocks=3, num_classes=10, conv_cls=HardBinaryConv_cifar):
+        super().__init__()
+        self.inplanes = 16
+        self.conv1 = nn.Conv2d(3, 16, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(16)
+        self.layer1 = self._make_layer(16, n_blocks, 1, conv_cls)
+        self.layer2 = self._make_layer(32, n_blocks, 2, conv_cls)
+        self.layer3 = self._make_layer(64, n_blocks, 2, conv_cls)
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(64, num_classes)
+
+    def _make_layer(self, planes, blocks, stride, conv_cls):
+        layers = [BasicBlockCifar(self.inplanes, planes, stride, conv_cls)]
+        self.inplanes = planes
+        for _ in range(1, blocks):
+            layers.append(BasicBlockCifar(planes, planes, 1, conv_cls))
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.bn1(self.conv1(x))
+        x = self.layer3(self.layer2(self.layer1(x)))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+def resnet18(pretrained=False, conv_cls=HardBinaryConv, **kw):
+    return ResNetImageNet([2, 2, 2, 2], conv_cls=conv_cls, **kw)
+
+
+def resnet34(pretrained=False, conv_cls=HardBinaryConv, **kw):
+    return ResNetImageNet([3, 4, 6, 3], conv_cls=conv_cls, **kw)
+
+
+def resnet20(conv_cls=HardBinaryConv_cifar, **kw):
+    return ResNetCifar(3, conv_cls=conv_cls, **kw)

@@ -1,0 +1,171 @@
+"""Training-step driver: the per-batch bodies of the reference, restated.
+
+    plain step             train.py:457-529   (`train`)
+    teacher-student step   train.py:573-651   (`train_teacher_student`)
+
+The reference's train.py cannot run as shipped (missing `models/`, undefined args w_l2_reg /
+w_wr_reg / w_lambda_ce, per-iteration re-wrapping of w_kurtosis_target, unconditional .cuda();
+SURVEY.md §0.3), so its step semantics live here with those defects resolved the way the code
+evidently intends: w_l2_reg = w_wr_reg = False, w_lambda_ce = 1.0 unless --react, scalar kurtosis
+target broadcast once over the hooked layers.
+
+`ops` abstracts the three loss terms so that the CPU oracle (oracle/step_ref.py) drives the very same
+step body with pure-PyTorch loss code; the product default is the fused CUDA kernels.
+Nothing here calls .item(): the five host syncs per step of train.py:519-524 are left to the caller.
+"""
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import losses as _losses
+from .modules import HardBinaryConv, HardBinaryConv_cifar, HardBinaryConv_react
+
+IMAGENET_DIFFKURT = [1.8, 1.4, 1.4, 1.4, 1.4, 1.2, 1.4, 1.2, 1.2, 1.4,
+                     1.4, 1.4, 1.2, 1.2, 1.2, 1.2, 1.4, 1, 1]                      # train.py:467-470
+CIFAR_DIFFKURT = [1.4] * 14 + [1.8, 1.8, 1.8, 1.8, 2.2]                            # train.py:472-475
+TS_DIFFKURT = [1.8, 1.8, 1.8, 1.8, 1.8, 1.8, 1.4, 1.8, 1.8, 1.8,
+               1.4, 1.4, 1.4, 1.4, 1.8, 1.2, 1.4, 1.2, 1.2]                        # train.py:586-589
+
+
+@dataclass
+class StepConfig:
+    """The hot-path flags of train.py:64-171 (defaults are the reference's)."""
+    w_kurtosis: bool = False
+    w_kurtosis_target: Union[float, Sequence[float]] = 1.8      # train.py:127
+    w_lambda_kurtosis: float = 1.0                               # train.py:129
+    kurtosis_mode: str = 'avg'                                   # train.py:137
+    kurtepoch: int = 0
+    weight_name: Sequence[str] = ('all',)
+    remove_weight_name: Optional[Sequence[str]] = None
+    teacher_student: bool = False                                # --imagenet_setting_step_2_ts
+    react: bool = False
+    alpha: float = 0.9                                           # train.py:168
+    beta: float = 200.0                                          # train.py:169
+    temperature: float = 4.0                                     # train.py:170 (unused by the layer loss)
+    w_lambda_ce: float = 1.0                                     # undefined upstream unless --react (B2)
+
+
+def select_hooked_weights(model, cfg: StepConfig):
+    """train.py:388-406: names of every Conv2d / HardBinaryConv* weight, first one dropped."""
+    if not cfg.w_kurtosis:
+        return {}
+    if cfg.weight_name[0] == 'all':
+        all_convs = [n + '.weight' for n, m in model.named_modules()
+                     if isinstance(m, (nn.Conv2d, HardBinaryConv_react, HardBinaryConv, HardBinaryConv_cifar))]
+        weight_name = all_convs[1:]
+        if cfg.remove_weight_name:
+            for name in weight_name:            # (sic) removing while iterating, as train.py:395-397
+                if cfg.remove_weight_name[0] in name:
+                    weight_name.remove(name)
+    else:
+        weight_name = list(cfg.weight_name)
+    params = dict(model.named_parameters())
+    hooked = {}
+    for name in weight_name:
+        p = params.get(name)
+        if p is None:
+            name = name.replace("weight", 'float_weight')
+            p = params.get(name)
+        hooked[name] = p
+    return hooked
+
+
+def accuracy(output, target, topk=(1,)):
+    """utils/utils.py:72-85 (device tensors, no sync)."""
+    with torch.no_grad():
+        maxk = max(topk)
+        batch_size = target.size(0)
+        _, pred = output.topk(maxk, 1, True, True)
+        pred = pred.t()
+        correct = pred.eq(target.view(1, -1).expand_as(pred))
+        return [correct[:k].reshape(-1).float().sum(0, keepdim=True).mul_(100.0 / batch_size) for k in topk]
+
+
+class FusedOps:
+    """Loss terms on the fused CUDA kernels (product path)."""
+
+    @staticmethod
+    def kurtosis(weights, targets, mode, n_hooks, lam):
+        reg, _, _ = _losses.kurtosis_regularization(weights, targets, mode, n_hooks, lam)
+        return reg
+
+    kd_logits = staticmethod(lambda s, t: _losses.DistributionLoss()(s, t))
+
+    @staticmethod
+    def kd_layer(out_s, out_t, model_s, model_t, T):
+        return _losses.DistributionLoss_layer()(out_s, out_t, model_s, model_t, T)
+
+
+class TrainStep:
+    """One optimisation step. `grad_sync` (optional) is called between backward and optimizer.step()
+    — the data-parallel gradient all-reduce (bdbnn_b200.ddp.GradAllReduce)."""
+
+    def __init__(self, model, optimizer, cfg: StepConfig = None, teacher=None, ops=FusedOps,
+                 grad_sync=None, criterion=None):
+        self.model, self.optimizer, self.cfg = model, optimizer, cfg or StepConfig()
+        self.teacher, self.ops, self.grad_sync = teacher, ops, grad_sync
+        self.criterion = criterion or nn.CrossEntropyLoss()
+        self.hooked = select_hooked_weights(model, self.cfg)
+        if self.cfg.teacher_student and teacher is None:
+            raise ValueError("teacher_student step needs a teacher model")
+        if self.cfg.w_kurtosis:
+            tgt = self.cfg.w_kurtosis_target
+            self.targets = list(tgt) if isinstance(tgt, (list, tuple)) else [tgt] * len(self.hooked)
+            if len(self.targets) < len(self.hooked):
+                raise ValueError("fewer kurtosis targets than hooked layers")
+
+    def __call__(self, images, target, epoch=0):
+        cfg = self.cfg
+        output = self.model(images)                                               # train.py:492 / 602
+        loss_kl = loss_kl_c = 0
+        if cfg.teacher_student:
+            with torch.no_grad():
+                output_teacher = self.teacher(images)                             # train.py:603
+            alpha, beta, lam_ce = cfg.alpha, cfg.beta, cfg.w_lambda_ce
+            if cfg.react:                                                         # train.py:605-609
+                beta, lam_ce = 0, 0
+            else:
+                loss_kl = self.ops.kd_layer(output, output_teacher, self.model, self.teacher,
+                                            cfg.temperature) * beta               # train.py:611
+            loss_kl_c = self.ops.kd_logits(output, output_teacher) * alpha        # train.py:612
+            orig_loss = self.criterion(output, target) * lam_ce                   # train.py:614
+        else:
+            orig_loss = self.criterion(output, target)                            # train.py:493
+        kurt_reg = 0
+        if cfg.w_kurtosis and cfg.kurtepoch <= epoch and self.hooked:             # train.py:498-513
+            kurt_reg = self.ops.kurtosis(list(self.hooked.values()), self.targets[:len(self.hooked)],
+                                         cfg.kurtosis_mode, len(self.hooked), cfg.w_lambda_kurtosis)
+        loss = loss_kl + loss_kl_c + orig_loss + kurt_reg                         # train.py:515 / 636
+        acc1, acc5 = accuracy(output, target, topk=(1, min(5, output.shape[1])))  # train.py:518
+        self.optimizer.zero_grad()                                                # train.py:527
+        loss.backward()                                                           # train.py:528
+        if self.grad_sync is not None:
+            self.grad_sync()
+        self.optimizer.step()                                                     # train.py:529
+        det = lambda v: v.detach() if torch.is_tensor(v) else v
+        return {"loss": loss.detach(), "ce": orig_loss.detach(), "kurt": det(kurt_reg), "kl": det(loss_kl),
+                "kl_c": det(loss_kl_c), "acc1": acc1, "acc5": acc5, "output": output.detach()}
+
+
+def make_optimizer(model, dataset='imagenet', lr=None, momentum=0.9, weight_decay=None, fused=None):
+    """train.py:319-336. CIFAR: SGD(lr .1, m .9, wd 1e-4). ImageNet: Adam, weight decay only on
+    4-D / 'conv' parameters (train.py:323-330)."""
+    if dataset in ('cifar10', 'cifar100'):
+        return torch.optim.SGD(model.parameters(), lr if lr is not None else 0.1, momentum=momentum,
+                               weight_decay=1e-4 if weight_decay is None else weight_decay)
+    all_parameters = list(model.parameters())
+    weight_parameters = [p for n, p in model.named_parameters() if p.ndimension() == 4 or 'conv' in n]
+    ids = {id(p) for p in weight_parameters}
+    other_parameters = [p for p in all_parameters if id(p) not in ids]
+    kw = {}
+    if fused is None:
+        fused = all(p.is_cuda for p in all_parameters)
+    if fused:
+        kw["fused"] = True
+    return torch.optim.Adam(
+        [{'params': other_parameters},
+         {'params': weight_parameters, 'weight_decay': 1e-4 if weight_decay is None else weight_decay}],
+        lr=lr if lr is not None else 1e-3, **kw)

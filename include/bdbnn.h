@@ -1,0 +1,163 @@
+/*
+ * bdbnn.h — C ABI of libbdbnn_b200.so (sm_100a).
+ *
+ * The reference (BlueAnon/BD-BNN) ships no native code: its hot path is Python calling
+ * ATen/cuDNN.  Each entry point below therefore replaces a *Python* call site of the reference
+ * (cited per function, paths relative to the reference root).  The binding a maintainer adds on the
+ * reference side is a ctypes stub; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - activations are NHWC ("channels_last"): element (n,h,w,c) at ((n*H+h)*W+w)*C+c;
+ *   - conv weights are OIHW fp32 exactly as torch stores nn.Conv2d.weight;
+ *   - bit tensors are uint32 words; bit j of word k covers channel 32*k+j (LSB first);
+ *     bit value 1 encodes +1 (x >= 0), bit value 0 encodes -1 (x < 0); channel padding bits are 0;
+ *   - stream is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - the library never allocates device memory: the caller owns every buffer incl. workspaces;
+ *   - return value 0 = ok, negative = error (bdbnn_last_error_string() describes the last one on
+ *     the calling thread).  Nothing throws across the ABI.
+ */
+#ifndef BDBNN_H_
+#define BDBNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BDBNN_API __attribute__((visibility("default")))
+#else
+#define BDBNN_API
+#endif
+
+#define BDBNN_OK 0
+#define BDBNN_ERR_INVALID_ARG (-1)
+#define BDBNN_ERR_CUDA (-2)
+#define BDBNN_ERR_UNSUPPORTED (-3)
+#define BDBNN_ERR_WORKSPACE (-4)
+
+/* Geometry of one conv2d call (square or rectangular kernels, symmetric zero padding). */
+typedef struct bdbnn_conv_shape {
+  int32_t N, H, W, Cin;     /* input  [N,H,W,Cin]  */
+  int32_t Cout, kh, kw;     /* weight [Cout,Cin,kh,kw] */
+  int32_t stride, pad;      /* same in h and w */
+  int32_t Ho, Wo;           /* output [N,Ho,Wo,Cout]; must equal (H+2*pad-kh)/stride+1 etc. */
+} bdbnn_conv_shape;
+
+/* Library ABI version (major*1000 + minor). */
+BDBNN_API int bdbnn_version(void);
+/* Thread-local description of the last error returned on this thread ("" if none). */
+BDBNN_API const char* bdbnn_last_error_string(void);
+/* 1 if the tcgen05/TMA implicit-GEMM kernels can serve this shape, else 0 (generic kernels do). */
+BDBNN_API int bdbnn_tc_supported(const bdbnn_conv_shape* s);
+
+/* ---- activation sign/pack ---------------------------------------------------------------------
+ * Replaces the activation binarisation inside the (absent) HardBinaryConv*.forward invoked at
+ * train.py:492 / train.py:602 (spec in DESIGN.md §2).
+ *   sign_bits[p*Cw+k] bit j = (x[p*C+32k+j] >= 0)           (forward operand, bit-exact)
+ *   mask_bits[p*Cw+k] bit j = (|x[p*C+32k+j]| <= 1)         (STE mask saved for backward)
+ *   xb_bf16 [p*C+c]        = +1.0/-1.0 as bf16 (0x3F80/0xBF80); may be NULL (tensor-core operand)
+ * n_pix = N*H*W, Cw = ceil(C/32).  NaN inputs: sign bit 0 (-1), mask bit 0. */
+BDBNN_API int bdbnn_act_pack(const float* x, int64_t n_pix, int32_t C, uint32_t* sign_bits,
+                   uint32_t* mask_bits, uint16_t* xb_bf16, void* stream);
+
+/* ---- weight sign/pack -------------------------------------------------------------------------
+ * Replaces the weight binarisation of HardBinaryConv*.forward (same call sites).
+ *   alpha[o]                 = mean_{c,r,s} |W[o,c,r,s]|                       (fp32)
+ *   wsign_bits[(o*T+t)*Cw+k] bit j = (W[o,32k+j,t] >= 0),  T = kh*kw, t = r*kw+s
+ *   wmask_bits[e/32] bit e%32      = (|W.flat[e]| <= 1)   in OIHW flat order  (STE mask)
+ *   wf_bf16[(o*T+t)*Cin+c]   = sign(W[o,c,t]) as bf16              (fwd  B operand; may be NULL)
+ *   wt_bf16[(c*T+t)*Cout+o]  = alpha[o]>0 ? sign(W[o,c,T-1-t]) : 0 (dgrad B operand; may be NULL)
+ *   gscale[o] = alpha[o] > 0 ? alpha[o] : 1 ;  inv_gscale[o] = 1/gscale[o]   (may be NULL) */
+BDBNN_API int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
+                      float* alpha, uint32_t* wsign_bits, uint32_t* wmask_bits,
+                      uint16_t* wf_bf16, uint16_t* wt_bf16, float* gscale, float* inv_gscale,
+                      void* stream);
+
+/* ---- binary conv forward, XNOR-popcount (bit-serial, CUDA cores) -------------------------------
+ * y[n,ho,wo,o] = alpha[o] * sum_{valid taps} (Cin - 2*popc(xbits ^ wbits)); zero padding
+ * contributes 0.  Replaces F.conv2d on +-1 fp32 tensors inside HardBinaryConv*.forward
+ * (train.py:492,602).  Integer part exact. */
+BDBNN_API int bdbnn_binconv_fwd_xnor(const uint32_t* sign_bits, const uint32_t* wsign_bits,
+                           const float* alpha, float* y, const bdbnn_conv_shape* s, void* stream);
+
+/* ---- binary conv forward, tcgen05 implicit GEMM on +-1 bf16 operands (exact, fp32 accumulate) --
+ * Same result as bdbnn_binconv_fwd_xnor.  Requires bdbnn_tc_supported(s). */
+BDBNN_API int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, const float* alpha,
+                         float* y, const bdbnn_conv_shape* s, void* stream);
+
+/* ---- backward: data gradient -------------------------------------------------------------------
+ * gx[n,h,w,c] = mask(n,h,w,c) * sum_{t,o} gy[n,ho,wo,o] * alpha[o] * sign(W[o,c,t])
+ * Replaces cuDNN dgrad + the STE mask multiply that autograd runs under loss.backward()
+ * (train.py:528, train.py:650).  Generic kernel: fp32 CUDA cores, any shape. */
+BDBNN_API int bdbnn_binconv_dgrad(const float* gy, const uint32_t* wsign_bits, const float* alpha,
+                        const uint32_t* mask_bits, float* gx, const bdbnn_conv_shape* s,
+                        void* stream);
+
+/* ---- backward: weight gradient -----------------------------------------------------------------
+ * gW[o,c,r,s] = wmask(o,c,r,s) * sum_{n,ho,wo} gy[n,ho,wo,o] * sign(x)[n,ho*st+r-p,wo*st+s-p,c]
+ * (Bi-Real STE: gradient w.r.t. the scaled binary weight passed straight through where |W|<=1.)
+ * gW is OVERWRITTEN, OIHW fp32.  Generic kernel: fp32 CUDA cores + atomics, any shape. */
+BDBNN_API int bdbnn_binconv_wgrad(const float* gy, const uint32_t* sign_bits, const uint32_t* wmask_bits,
+                        float* gW, const bdbnn_conv_shape* s, void* stream);
+
+/* ---- backward on tensor cores (tcgen05, bf16 operands, fp32 accumulate) ------------------------
+ * grad_pack: gys_bf16[p*Cout+o] = bf16_rn(gy[p*Cout+o] * gscale[o])   (shared by dgrad_tc/wgrad_tc)
+ * dgrad_tc : gx = mask * conv_transpose(gys, wt_bf16)                  (sign-only weights, exact)
+ * wgrad_tc : gW = wmask * inv_gscale[o] * sum_pix gys[pix,o]*xb[pix',c]
+ * wgrad_tc needs a workspace of bdbnn_wgrad_tc_workspace_bytes(s) bytes (split-K partials). */
+BDBNN_API int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_pix, int32_t Cout,
+                    uint16_t* gys_bf16, void* stream);
+BDBNN_API int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, const uint16_t* wt_bf16,
+                           const uint32_t* mask_bits, float* gx, const bdbnn_conv_shape* s,
+                           void* stream);
+BDBNN_API size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s);
+BDBNN_API int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, const uint16_t* xb_bf16,
+                           const uint32_t* wmask_bits, const float* inv_gscale, float* gW,
+                           const bdbnn_conv_shape* s, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ---- kurtosis regulariser, multi-tensor --------------------------------------------------------
+ * Replaces KurtosisWeight.kurtosis_calc (kurtosis.py:23-39) called per hooked layer at
+ * train.py:501-504 / 622-625, and the scalar reduction at train.py:505-512.
+ * For each tensor l<L (L <= BDBNN_MAX_TENSORS): mu=mean(w), s=std(w) UNBIASED (n-1),
+ * K=mean(((w-mu)/s)^4), loss=(K-target)^2.
+ *   w_ptrs_host / numel_host / targets_host : HOST arrays of length L
+ *   moments  : device double[L*8] scratch that the backward reads (mu, s, K, mean z^3, ...)
+ *   kurt_out, loss_out : device float[L]
+ * bwd: grad_l[j] (+)= gout[l] * 2(K-T) * 4/(n s) * (z^3 - mean(z^3) - z K n/(n-1));
+ *      gout is a DEVICE float[L]; accumulate!=0 adds into grad, else overwrites. */
+#define BDBNN_MAX_TENSORS 64
+BDBNN_API int bdbnn_kurtosis_multi_fwd(const float* const* w_ptrs_host, const int64_t* numel_host,
+                             const float* targets_host, int32_t L, double* moments,
+                             float* kurt_out, float* loss_out, void* stream);
+BDBNN_API int bdbnn_kurtosis_multi_bwd(const float* const* w_ptrs_host, const int64_t* numel_host,
+                             const float* targets_host, int32_t L, const double* moments,
+                             const float* gout, float* const* grad_ptrs_host, int32_t accumulate,
+                             void* stream);
+
+/* ---- KD logits loss (DistributionLoss.forward, utils/KD_loss.py:16-43; train.py:612) -----------
+ * loss = -(1/N) sum_n sum_c softmax(t)[n,c] * log_softmax(s)[n,c]
+ * grad_s[n,c] = (softmax(s) - softmax(t))[n,c] / N          (written when grad_s != NULL)
+ * row_ws: device float[N] scratch.  s,t row-major [N,C] fp32. */
+BDBNN_API int bdbnn_kd_logits_fwd_bwd(const float* s, const float* t, int32_t N, int32_t C, float* row_ws,
+                            float* loss_out, float* grad_s, void* stream);
+
+/* ---- KD per-layer weight loss (DistributionLoss_layer.forward, utils/KD_loss.py:52-67) ---------
+ * loss = sum_l mean_l( exp(Wt_l) * (Wt_l - Ws_l) )   == sum_l KLDivLoss(log_target=True)(Ws,Wt)
+ * bwd : gWs_l[j] (+)= -gout[0] * exp(Wt_l[j]) / numel_l
+ * partial: device double[L] scratch. */
+BDBNN_API int bdbnn_kd_layer_multi_fwd(const float* const* ws_ptrs_host, const float* const* wt_ptrs_host,
+                             const int64_t* numel_host, int32_t L, double* partial,
+                             float* loss_out, void* stream);
+BDBNN_API int bdbnn_kd_layer_multi_bwd(const float* const* wt_ptrs_host, const int64_t* numel_host,
+                             int32_t L, const float* gout, float* const* grad_ptrs_host,
+                             int32_t accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDBNN_H_ */

@@ -1,0 +1,156 @@
+"""CPU: host-side logic, import surface, C-ABI export list, no-fallback guarantees."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_import_paths():
+    from models import cifar10 as cifar_models, imagenet as imagenet_models              # train.py:27-28
+    from models.imagenet.resnet_bi_imagenet_set_2 import HardBinaryConv_react           # train.py:30
+    from models.imagenet.resnet_bi_imagenet_set_2_2 import HardBinaryConv               # train.py:31
+    from models.bin_module.binarized_modules import HardBinaryConv_cifar, BinarizeConv2d  # train.py:32
+    from kurtosis import KurtosisWeight                                                  # train.py:29
+    from utils.KD_loss import DistributionLoss, DistributionLoss_layer                   # train.py:34
+    names = sorted(n for n in imagenet_models.__dict__
+                   if n.islower() and not n.startswith("__") and callable(imagenet_models.__dict__[n]))
+    assert "resnet18" in names and "resnet34" in names                                   # train.py:53-56
+    assert callable(cifar_models.__dict__["resnet20"])
+    for cls in (HardBinaryConv, HardBinaryConv_react, HardBinaryConv_cifar):
+        assert issubclass(cls, BinarizeConv2d) and issubclass(cls, nn.Conv2d)
+    assert KurtosisWeight and DistributionLoss and DistributionLoss_layer
+
+
+def test_module_contract_and_hook_selection():
+    import models
+    from bdbnn_b200.step import StepConfig, select_hooked_weights
+    m = models.imagenet.resnet18(False)
+    hooked = select_hooked_weights(m, StepConfig(w_kurtosis=True))
+    assert len(hooked) == 19                                          # train.py:467-470
+    assert "conv1.weight" not in hooked and "layer2.0.downsample.0.weight" in hooked
+    for n, p in hooked.items():
+        assert p.ndim == 4 and p.requires_grad and n.endswith(".weight")
+    assert sum(p.numel() for p in m.parameters()) == 11689512
+    sd = m.state_dict()
+    assert "layer1.0.conv1.weight" in sd and not any(k.endswith(".k") or k.endswith(".t") for k in sd)
+    m2 = models.cifar10.resnet20()
+    assert len(select_hooked_weights(m2, StepConfig(w_kurtosis=True))) == 18
+    conv = m2.layer1[0].conv1
+    conv.k, conv.t = torch.tensor([3.0]), torch.tensor([0.3])          # EDE assignment, train.py:414-415
+    hooked = select_hooked_weights(m, StepConfig(w_kurtosis=True, remove_weight_name=["downsample"]))
+    assert 16 <= len(hooked) < 19                                     # buggy in-loop remove kept (train.py:395)
+
+
+def test_cpu_tensors_are_rejected_no_fallback():
+    from bdbnn_b200 import BinarizeConv2d, KurtosisWeight, DistributionLoss
+    conv = BinarizeConv2d(4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        conv(torch.randn(1, 4, 5, 5))
+    kw = KurtosisWeight(torch.randn(4, 4, 3, 3), "w", 1.8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        kw.fn_regularization()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DistributionLoss()(torch.randn(2, 3), torch.randn(2, 3))
+    with pytest.raises(ValueError, match="should not require gradients"):
+        DistributionLoss()(torch.randn(2, 3), torch.randn(2, 3, requires_grad=True))
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    prod = [os.path.join(ROOT, "kurtosis.py")]
+    for d in ("bdbnn_b200", "models", "utils"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, d)):
+            prod += [os.path.join(dp, f) for f in fs if f.endswith(".py")]
+    for f in prod:
+        src = open(f).read()
+        if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or re.search(r"from\s+\.+\s*import\s+oracle", src):
+            bad.append(f)
+    assert not bad, bad
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "bdbnn.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(bdbnn_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_capi_library_exports_every_declared_symbol():
+    from bdbnn_b200 import build, _lib
+    path = build.build()
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES out of sync with include/bdbnn.h"
+    h = ctypes.CDLL(path)
+    for s in syms:
+        assert hasattr(h, s), f"{s} not exported"
+    h.bdbnn_version.restype = ctypes.c_int
+    assert h.bdbnn_version() >= 1000
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\sT\s+(bdbnn_\w+)", out))
+    assert exported == set(syms), exported ^ set(syms)
+
+
+def test_library_is_sm100a():
+    from bdbnn_b200 import build
+    path = build.build()
+    out = subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out[:400]
+
+
+def test_cpu_oracle_step_runs_and_learns():
+    """Config 1 shape (ResNet-20 CIFAR) on the shared step driver with the oracle ops."""
+    from bdbnn_b200.step import StepConfig, TrainStep, make_optimizer
+    from oracle.models_ref import RefOps, resnet20_ref
+    torch.manual_seed(0)
+    m = resnet20_ref()
+    step = TrainStep(m, make_optimizer(m, "cifar10", lr=0.05), StepConfig(w_kurtosis=True), ops=RefOps)
+    x, y = torch.randn(16, 3, 32, 32), torch.randint(0, 10, (16,))
+    l0 = float(step(x, y)["loss"])
+    for _ in range(5):
+        out = step(x, y)
+    assert float(out["loss"]) < l0
+    assert all(p.grad is not None for p in m.parameters())          # DDP needs every param to get a grad
+
+
+def _ddp_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bdbnn_b200.ddp import FlatGradOptimizerShim, GradAllReduce
+    from bdbnn_b200.step import StepConfig, TrainStep, make_optimizer
+    from oracle.models_ref import RefOps, resnet20_ref
+    torch.manual_seed(100 + rank)                     # different init per rank: broadcast must fix it
+    m = resnet20_ref()
+    red = GradAllReduce(m)
+    opt = FlatGradOptimizerShim(make_optimizer(m, "cifar10", lr=0.1), red)
+    step = TrainStep(m, opt, StepConfig(w_kurtosis=True), ops=RefOps, grad_sync=red)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(8, 3, 32, 32, generator=g)
+    y = torch.randint(0, 10, (8,), generator=g)
+    xs, ys = x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4]
+    step(xs, ys)
+    torch.save((red.flat.clone(), torch.cat([p.detach().reshape(-1) for p in m.parameters()])),
+               os.path.join(outdir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gradient_allreduce(tmp_path):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    (g0, p0), (g1, p1) = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2)]
+    assert torch.equal(g0, g1) and torch.equal(p0, p1)     # averaged grads and updated params identical
+    assert g0.abs().sum() > 0
