@@ -18,6 +18,70 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelTimer:
+    """Opt-in CUDA-event timing of individual kernels on the stream they are launched on
+    (bench.py uses it inside the timed region for the roofline figure). Disabled -> zero overhead."""
+    enabled = False
+    records = []          # (family, key, start_event, end_event, algorithmic_bytes)
+
+    @classmethod
+    def start(cls):
+        cls.records = []
+        cls.enabled = True
+
+    @classmethod
+    def stop(cls):
+        cls.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for fam, key, e0, e1, nbytes in cls.records:
+            d = out.setdefault((fam, key), {"ms": 0.0, "launches": 0, "bytes": nbytes})
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+        cls.records = []
+        return out
+
+
+class _timed:
+    def __init__(self, family, key, nbytes):
+        self.args = (family, key, nbytes)
+
+    def __enter__(self):
+        if KernelTimer.enabled:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if KernelTimer.enabled:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            fam, key, nbytes = self.args
+            KernelTimer.records.append((fam, key, self.e0, e1, nbytes))
+        return False
+
+
+def _shape_key(sh):
+    return f"N{sh.N}_{sh.H}x{sh.W}_c{sh.Cin}-{sh.Cout}_k{sh.kh}s{sh.stride}"
+
+
+def algorithmic_bytes(kernel, sh):
+    """Per-launch algorithmic bytes of each kernel: compulsory HBM reads + writes."""
+    n_in = sh.N * sh.H * sh.W * sh.Cin
+    n_out = sh.N * sh.Ho * sh.Wo * sh.Cout
+    n_w = sh.Cout * sh.Cin * sh.kh * sh.kw
+    return {
+        "act_pack": 4 * n_in + 2 * n_in // 8,                 # read fp32 x, write sign+mask bits
+        "act_pack_tc": 4 * n_in + 2 * n_in // 8 + 2 * n_in,   # + bf16 copy
+        "fwd_xnor": n_in // 8 + n_w // 8 + 4 * n_out,         # read bits, write fp32 y
+        "fwd_tc": 2 * n_in + 2 * n_w + 4 * n_out,             # read bf16 +-1, write fp32 y
+        "dgrad": 4 * n_out + n_w // 8 + n_in // 8 + 4 * n_in,  # read gy, bits; write gx
+        "wgrad": 4 * n_out + n_in // 8 + n_w // 8 + 4 * n_w,
+        "grad_pack": 4 * n_out + 2 * n_out,
+        "dgrad_tc": 2 * n_out + 2 * n_w + n_in // 8 + 4 * n_in,
+        "wgrad_tc": 2 * n_out + 2 * n_in + n_w // 8 + 4 * n_w,
+    }[kernel]
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -84,8 +148,10 @@ class _BinConv2d(torch.autograd.Function):
         mask_bits = torch.empty((n, h, wd, cw), **i32)
         tc = use == "tc"
         xb = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=dev) if tc else None
-        _lib.check(L.bdbnn_act_pack(_p(xc), n * h * wd, cin, _p(sign_bits), _p(mask_bits), _p(xb), st),
-                   "act_pack")
+        key = _shape_key(sh)
+        with _timed("act_pack", key, algorithmic_bytes("act_pack_tc" if tc else "act_pack", sh)):
+            _lib.check(L.bdbnn_act_pack(_p(xc), n * h * wd, cin, _p(sign_bits), _p(mask_bits), _p(xb), st),
+                       "act_pack")
         alpha = torch.empty((cout,), dtype=torch.float32, device=dev)
         wsign = torch.empty((cout, T, cw), **i32)
         wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
@@ -100,11 +166,13 @@ class _BinConv2d(torch.autograd.Function):
         y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
                         memory_format=torch.channels_last)
         if tc:
-            _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), ctypes.byref(sh), st),
-                       "binconv_fwd_tc")
+            with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
+                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), ctypes.byref(sh), st),
+                           "binconv_fwd_tc")
         else:
-            _lib.check(L.bdbnn_binconv_fwd_xnor(_p(sign_bits), _p(wsign), _p(alpha), _p(y),
-                                                ctypes.byref(sh), st), "binconv_fwd_xnor")
+            with _timed("binconv_fwd_xnor", key, algorithmic_bytes("fwd_xnor", sh)):
+                _lib.check(L.bdbnn_binconv_fwd_xnor(_p(sign_bits), _p(wsign), _p(alpha), _p(y),
+                                                    ctypes.byref(sh), st), "binconv_fwd_xnor")
         _lib.count(4)
         ctx.sh = sh
         ctx.use = use
@@ -127,36 +195,43 @@ class _BinConv2d(torch.autograd.Function):
         gx = gw = None
         saved = ctx.saved_tensors
         sign_bits, mask_bits, wsign, wmask, alpha = saved[:5]
+        key = _shape_key(sh)
         if ctx.use == "tc":
             xb, wt, gscale, inv_gscale = saved[5:]
             n_pix_out = sh.N * sh.Ho * sh.Wo
             gys = torch.empty((sh.N, sh.Ho, sh.Wo, sh.Cout), dtype=torch.bfloat16, device=dev)
-            _lib.check(L.bdbnn_grad_pack(_p(g), _p(gscale), n_pix_out, sh.Cout, _p(gys), st), "grad_pack")
+            with _timed("grad_pack", key, algorithmic_bytes("grad_pack", sh)):
+                _lib.check(L.bdbnn_grad_pack(_p(g), _p(gscale), n_pix_out, sh.Cout, _p(gys), st), "grad_pack")
             _lib.count(1)
             if need_x:
                 gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev,
                                  memory_format=torch.channels_last)
-                _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), _p(wt), _p(mask_bits), _p(gx),
-                                                    ctypes.byref(sh), st), "binconv_dgrad_tc")
+                with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh)):
+                    _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), _p(wt), _p(mask_bits), _p(gx),
+                                                        ctypes.byref(sh), st), "binconv_dgrad_tc")
                 _lib.count(1)
             if need_w:
                 gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
                 nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
                 ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
-                _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
-                                                    ctypes.byref(sh), _p(ws), nbytes, st), "binconv_wgrad_tc")
+                with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh)):
+                    _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
+                                                        ctypes.byref(sh), _p(ws), nbytes, st),
+                               "binconv_wgrad_tc")
                 _lib.count(2)
         else:
             if need_x:
                 gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev,
                                  memory_format=torch.channels_last)
-                _lib.check(L.bdbnn_binconv_dgrad(_p(g), _p(wsign), _p(alpha), _p(mask_bits), _p(gx),
-                                                 ctypes.byref(sh), st), "binconv_dgrad")
+                with _timed("binconv_dgrad_generic", key, algorithmic_bytes("dgrad", sh)):
+                    _lib.check(L.bdbnn_binconv_dgrad(_p(g), _p(wsign), _p(alpha), _p(mask_bits), _p(gx),
+                                                     ctypes.byref(sh), st), "binconv_dgrad")
                 _lib.count(1)
             if need_w:
                 gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
-                _lib.check(L.bdbnn_binconv_wgrad(_p(g), _p(sign_bits), _p(wmask), _p(gw),
-                                                 ctypes.byref(sh), st), "binconv_wgrad")
+                with _timed("binconv_wgrad_generic", key, algorithmic_bytes("wgrad", sh)):
+                    _lib.check(L.bdbnn_binconv_wgrad(_p(g), _p(sign_bits), _p(wmask), _p(gw),
+                                                     ctypes.byref(sh), st), "binconv_wgrad")
                 _lib.count(1)
         return gx, gw, None, None, None
 

@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — ResNet-18 1W/1A training throughput (images/sec) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this repo (CUDA kernels)
+    torchrun ... bench.py --gpus N --steps K --warmup W       # one rank per GPU, NCCL
+    python bench.py --impl reference ...                      # reference arm: the CPU oracle step
+
+A "step" = one full optimisation step of the restated train.py body (bdbnn_b200.step.TrainStep:
+forward, losses, backward, gradient all-reduce, optimizer) on one synthetic batch.  Workload at N=1 is
+BASELINE.json configs[1]: ResNet-18 1W/1A, synthetic 224x224, batch 256 per GPU.
+
+Prints ONE JSON line (rank 0).  `value` = images/sec with inputs resident in HBM; `e2e` = the same
+step fed from pinned host memory (H2D copy of every batch + D2H read of the loss inside the timed
+region); `roofline` = achieved algorithmic GB/s of the dominant CUDA kernel family measured with CUDA
+events on the launching stream inside the timed region; `cpu_baseline` = the CPU oracle step timed on
+this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="resnet18", choices=["resnet18", "resnet34", "resnet20"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 256; 128 for resnet20)")
+    ap.add_argument("--workload", default="ce", choices=["ce", "kurt_kd"],
+                    help="ce = BASELINE configs[1]; kurt_kd = configs[2] (kurtosis + KD, fp32 teacher)")
+    ap.add_argument("--conv-impl", default=None, choices=[None, "auto", "xnor", "tc"])
+    ap.add_argument("--cpu-batch", type=int, default=32, help="bounded CPU sample: images per CPU step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu: 1 warm-up step, no e2e / cpu legs (numbers printed are not bench values)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(name, conv_impl=None, ref=False):
+    if ref:
+        from oracle import models_ref
+        return {"resnet18": models_ref.resnet18_ref, "resnet34": models_ref.resnet34_ref,
+                "resnet20": models_ref.resnet20_ref}[name]()
+    from bdbnn_b200 import resnet
+    from bdbnn_b200.modules import BinarizeConv2d
+    m = {"resnet18": resnet.resnet18, "resnet34": resnet.resnet34, "resnet20": resnet.resnet20}[name]()
+    for mod in m.modules():
+        if isinstance(mod, BinarizeConv2d):
+            mod.impl = conv_impl
+    return m
+
+
+def build_teacher(name):
+    """fp32 teacher, random init (no checkpoints offline), eval, no grads (train.py:250-277)."""
+    import torchvision
+    if name == "resnet20":
+        from oracle import models_ref  # noqa: F401  (not used on the GPU arm)
+        raise SystemExit("kurt_kd workload is defined for the ImageNet models")
+    t = {"resnet18": torchvision.models.resnet18, "resnet34": torchvision.models.resnet34}[name]()
+    t.eval()
+    for p in t.parameters():
+        p.requires_grad = False
+    return t
+
+
+def shapes(model_name, batch):
+    if model_name == "resnet20":
+        return (batch, 3, 32, 32), 10, "cifar10"
+    return (batch, 3, 224, 224), 1000, "imagenet"
+
+
+def step_config(workload):
+    from bdbnn_b200.step import StepConfig
+    if workload == "kurt_kd":
+        return StepConfig(w_kurtosis=True, teacher_student=True, alpha=0.9, beta=200.0, w_lambda_ce=1.0)
+    return StepConfig()
+
+
+def cpu_reference_run(args, steps, warmup, batch):
+    """The reference arm / cpu_baseline: restated train.py step on the pure-PyTorch oracle modules,
+    all host threads."""
+    from bdbnn_b200.step import TrainStep, make_optimizer
+    from oracle.models_ref import RefOps
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    ishape, ncls, dataset = shapes(args.model, batch)
+    model = build_model(args.model, ref=True)
+    teacher = None
+    cfg = step_config(args.workload)
+    if cfg.teacher_student:
+        teacher = build_teacher(args.model)
+    step = TrainStep(model, make_optimizer(model, dataset, fused=False), cfg, teacher=teacher, ops=RefOps)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(ishape, generator=g)
+    y = torch.randint(0, ncls, (batch,), generator=g)
+    for _ in range(warmup):
+        step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = step(x, y)
+        float(out["loss"])
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    batch = args.batch or (128 if args.model == "resnet20" else 256)
+    workload = (f"{args.model} 1W/1A synthetic {'32x32' if args.model == 'resnet20' else '224x224'} "
+                f"batch {batch}/GPU, {'CE' if args.workload == 'ce' else 'CE+kurtosis+KD(fp32 teacher)'}"
+                f" full train step")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = min(args.cpu_batch, batch)
+        v, ms, cores = cpu_reference_run(args, max(1, args.steps), max(0, args.warmup), cb)
+        line = {"impl": "reference", "metric": "images/sec", "value": round(v, 3), "unit": "images/sec",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": workload, "parallelism": "cpu"},
+                "cpu_baseline": {"value": round(v, 3), "unit": "images/sec", "cores": cores, "kind": "port",
+                                 "sample": f"{args.steps} steps of a {cb}-image slice of the {batch}-image batch "
+                                           "(pure-PyTorch oracle of the restated train.py step; the reference's "
+                                           "own train.py cannot run, SURVEY.md §0.3)"},
+                "e2e": {"value": round(v, 3), "unit": "images/sec", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    import torch.distributed as dist
+    from bdbnn_b200 import _lib
+    from bdbnn_b200.ddp import FlatGradOptimizerShim, GradAllReduce
+    from bdbnn_b200.functional import KernelTimer
+    from bdbnn_b200.step import TrainStep, make_optimizer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True            # train.py:368
+    torch.manual_seed(0)
+    ishape, ncls, dataset = shapes(args.model, batch)
+    model = build_model(args.model, args.conv_impl).to(dev).to(memory_format=torch.channels_last)
+    cfg = step_config(args.workload)
+    teacher = None
+    if cfg.teacher_student:
+        teacher = build_teacher(args.model).to(dev).to(memory_format=torch.channels_last)
+    opt = make_optimizer(model, dataset)
+    reducer = None
+    if world > 1:
+        reducer = GradAllReduce(model)
+        opt = FlatGradOptimizerShim(opt, reducer)
+    step = TrainStep(model, opt, cfg, teacher=teacher, grad_sync=reducer)
+
+    g = torch.Generator().manual_seed(rank)
+    x_host = torch.randn(ishape, generator=g).contiguous(memory_format=torch.channels_last).pin_memory()
+    y_host = torch.randint(0, ncls, (batch,), generator=g).pin_memory()
+    x_dev = x_host.to(dev, non_blocking=True)
+    y_dev = y_host.to(dev, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident timing (value) -----------------------------------------------------------
+    if args.profile_mode:
+        args.no_e2e = args.no_cpu_baseline = True
+    n_warm = 1 if args.profile_mode else max(3, args.warmup)
+    for _ in range(n_warm):
+        step(x_dev, y_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    KernelTimer.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev, y_dev)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - n0
+    kern = KernelTimer.stop()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = batch * world * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end: pinned host batch -> H2D (prefetched on a copy stream) -> step -> D2H loss -----
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        bufs = [(torch.empty_like(x_dev), torch.empty_like(y_dev)) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prefetch(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])
+                bufs[b][0].copy_(x_host, non_blocking=True)
+                bufs[b][1].copy_(y_host, non_blocking=True)
+                ready[b].record(copy_stream)
+
+        def e2e_loop(n):
+            for b in range(2):
+                consumed[b].record()
+            prefetch(0)
+            last = None
+            for i in range(n):
+                b = i % 2
+                if i + 1 < n:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[b])
+                out = step(bufs[b][0], bufs[b][1])
+                consumed[b].record()
+                last = float(out["loss"])       # D2H read of the step's result (train.py:519)
+            return last
+
+        e2e_loop(2)
+        barrier()
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": round(batch * world * args.steps / (ms_e2e / 1e3), 2), "unit": "images/sec",
+               "ms_per_step": round(ms_e2e / args.steps, 3),
+               "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
+               "d2h_bytes_per_step": 4,
+               "note": "pinned fp32 batch, H2D double-buffered on a copy stream, loss read back every step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family ---------------------------------------------------
+    peak, peak_src = peaks()
+    fam = {}
+    for (family, key), d in kern.items():
+        f = fam.setdefault(family, {"ms": 0.0, "launches": 0, "bytes": 0})
+        f["ms"] += d["ms"]; f["launches"] += d["launches"]; f["bytes"] += d["bytes"] * d["launches"]
+    kernels = []
+    for family, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        kernels.append({"kernel": family, "ms_per_step": round(f["ms"] / args.steps, 4),
+                        "launches_per_step": f["launches"] // args.steps,
+                        "achieved_gbs": round(f["bytes"] / 1e9 / (f["ms"] / 1e3), 1) if f["ms"] > 0 else None,
+                        "share_of_step": round(f["ms"] / ms_total, 4)})
+    roofline = None
+    if kernels:
+        top = kernels[0]
+        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": round(top["achieved_gbs"] / peak, 4), "traffic": None,
+                    "peak_source": peak_src,
+                    "how": "sum of per-launch algorithmic bytes (DESIGN.md §4) / sum of CUDA-event durations "
+                           "of that kernel family over the timed region"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = min(args.cpu_batch, batch)
+        v, ms, cores = cpu_reference_run(args, 2, 1, cb)
+        cpu = {"value": round(v, 3), "unit": "images/sec", "cores": cores, "kind": "port",
+               "sample": f"2 timed steps (1 warm-up) of a {cb}-image slice of the {batch}-image batch, "
+                         f"{ms:.0f} ms/step, oracle CPU step"}
+
+    line = {"metric": "images/sec", "value": round(value, 2), "unit": "images/sec", "n_gpus": world,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16/f32",
+            "data": "synthetic",
+            "config": {"workload": workload, "global_batch": batch * world,
+                       "parallelism": f"dp{world}", "optimizer": "Adam (train.py:323-336)" if dataset == "imagenet"
+                       else "SGD (train.py:319-321)", "conv_impl": args.conv_impl or "auto",
+                       "l2_policy": "per-step working set (>3 GB of activations) exceeds the 126 MB L2; no flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "kernels": kernels, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

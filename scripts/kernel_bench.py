@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Per-layer kernel micro-benchmark (ResNet-18 N=256 binary-conv shapes):
+CUDA-event time, algorithmic GB/s and fraction of the measured HBM peak for every kernel of the path.
+L2 is flushed (256 MB write) between timed launches.   python scripts/kernel_bench.py [--impl xnor|tc]"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from bdbnn_b200 import _lib  # noqa: E402
+from bdbnn_b200.functional import _p, _stream, algorithmic_bytes, conv_shape  # noqa: E402
+
+R18 = [("layer1", 64, 56, 64, 1), ("layer2.0.conv1", 64, 56, 128, 2), ("layer2", 128, 28, 128, 1),
+       ("layer3.0.conv1", 128, 28, 256, 2), ("layer3", 256, 14, 256, 1),
+       ("layer4.0.conv1", 256, 14, 512, 2), ("layer4", 512, 7, 512, 1)]
+
+
+def timeit(fn, flush, iters=5):
+    ts = []
+    for _ in range(iters + 1):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts = sorted(ts[1:])
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--impl", default="xnor")
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    L = _lib.lib()
+    peak = 6575.1
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk))["hbm_gbs"]
+    flush = torch.empty(64 * 1024 * 1024, device="cuda")
+    rows = []
+    for name, cin, hw, cout, stride in R18:
+        n = a.batch
+        sh = conv_shape((n, cin, hw, hw), (cout, cin, 3, 3), stride, 1)
+        cw = (cin + 31) // 32
+        x = torch.randn(n, hw, hw, cin, device="cuda")
+        w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
+        sb = torch.empty((n, hw, hw, cw), dtype=torch.int32, device="cuda")
+        mb = torch.empty_like(sb)
+        xb = torch.empty((n, hw, hw, cin), dtype=torch.bfloat16, device="cuda")
+        alpha = torch.empty(cout, device="cuda")
+        ws = torch.empty((cout, 9, cw), dtype=torch.int32, device="cuda")
+        wm = torch.empty(((w.numel() + 31) // 32,), dtype=torch.int32, device="cuda")
+        wf = torch.empty((cout, 9, cin), dtype=torch.bfloat16, device="cuda")
+        wt = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device="cuda")
+        gs, igs = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
+        y = torch.empty((n, sh.Ho, sh.Wo, cout), device="cuda")
+        gy = torch.randn_like(y)
+        gys = torch.empty(y.shape, dtype=torch.bfloat16, device="cuda")
+        gx = torch.empty_like(x)
+        gw = torch.empty_like(w)
+        st = _stream()
+        shp = ctypes.byref(sh)
+        tc = a.impl == "tc" and L.bdbnn_tc_supported(shp)
+        ck = _lib.check
+        kernels = {
+            "act_pack" + ("_tc" if tc else ""): lambda: ck(L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb if tc else None), st), "p"),
+            "weight_pack": lambda: ck(L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(gs), _p(igs), st), "w"),
+        }
+        if tc:
+            nb = int(L.bdbnn_wgrad_tc_workspace_bytes(shp))
+            wsb = torch.empty(max(nb, 4) // 4, device="cuda")
+            kernels.update({
+                "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), shp, st), "f"),
+                "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, _p(gys), st), "g"),
+                "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), _p(wt), _p(mb), _p(gx), shp, st), "d"),
+                "wgrad_tc": lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w"),
+            })
+        else:
+            kernels.update({
+                "fwd_xnor": lambda: ck(L.bdbnn_binconv_fwd_xnor(_p(sb), _p(ws), _p(alpha), _p(y), shp, st), "f"),
+                "dgrad": lambda: ck(L.bdbnn_binconv_dgrad(_p(gy), _p(ws), _p(alpha), _p(mb), _p(gx), shp, st), "d"),
+                "wgrad": lambda: ck(L.bdbnn_binconv_wgrad(_p(gy), _p(sb), _p(wm), _p(gw), shp, st), "w"),
+            })
+        for kname, fn in kernels.items():
+            fn()
+            torch.cuda.synchronize()
+            ms = timeit(fn, flush, iters=3 if kname in ("dgrad", "wgrad") else 7)
+            nbytes = algorithmic_bytes(kname, sh) if kname != "weight_pack" else 4 * w.numel()
+            gbs = nbytes / 1e9 / (ms / 1e3)
+            macs = 2.0 * n * sh.Ho * sh.Wo * cout * cin * 9
+            rows.append({"layer": name, "kernel": kname, "ms": round(ms, 4), "alg_MB": round(nbytes / 1e6, 2),
+                         "GBs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4),
+                         "TFLOPs": round(macs / 1e12 / (ms / 1e3), 1) if "pack" not in kname else None})
+            print(rows[-1], flush=True)
+        del x, y, gy, gx, xb, gys
+        torch.cuda.empty_cache()
+    if a.out:
+        json.dump(rows, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""GPU: whole training step (BASELINE.json config 1 shape, reduced batch) vs the CPU oracle step,
+and the kernel-launch counter bench.py reports."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads(m):
+    return {n: p.grad.detach().cpu().clone() for n, p in m.named_parameters()}
+
+
+@pytest.mark.parametrize("ts", [False, True])
+def test_resnet20_step_matches_cpu_oracle(ts):
+    import torchvision
+    from bdbnn_b200 import _lib
+    from bdbnn_b200.resnet import resnet20
+    from bdbnn_b200.step import StepConfig, TrainStep, make_optimizer
+    from oracle.models_ref import RefOps, resnet20_ref
+    torch.manual_seed(0)
+    ref = resnet20_ref()
+    gpu = resnet20()
+    gpu.load_state_dict(ref.state_dict())
+    gpu = gpu.cuda().to(memory_format=torch.channels_last)
+    teacher_ref = teacher_gpu = None
+    if ts:
+        torch.manual_seed(1)
+        teacher_ref = resnet20_ref().eval()           # same names/shapes as the student (KD_loss.py:63)
+        for p in teacher_ref.parameters():
+            p.requires_grad = False                   # train.py:275-276
+        teacher_gpu = resnet20()
+        teacher_gpu.load_state_dict(teacher_ref.state_dict())
+        teacher_gpu = teacher_gpu.cuda().to(memory_format=torch.channels_last).eval()
+        for p in teacher_gpu.parameters():
+            p.requires_grad = False
+    cfg = StepConfig(w_kurtosis=True, teacher_student=ts, beta=200.0, alpha=0.9)
+    # lr=0: compare gradients of one step without the update moving the weights
+    s_ref = TrainStep(ref, make_optimizer(ref, "cifar10", lr=0.0), cfg, teacher=teacher_ref, ops=RefOps)
+    s_gpu = TrainStep(gpu, make_optimizer(gpu, "cifar10", lr=0.0), cfg, teacher=teacher_gpu)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(16, 3, 32, 32, generator=g)
+    y = torch.randint(0, 10, (16,), generator=g)
+    n0 = _lib.launch_count()
+    o_ref = s_ref(x, y)
+    o_gpu = s_gpu(x.cuda().contiguous(memory_format=torch.channels_last), y.cuda())
+    assert _lib.launch_count() - n0 >= 18 * 6      # 18 binary convs x (pack, wpack x2, fwd, dgrad, wgrad)
+    for k in ("loss", "ce", "kurt") + (("kl", "kl_c") if ts else ()):
+        torch.testing.assert_close(o_gpu[k].cpu(), o_ref[k], rtol=2e-4, atol=1e-5)
+    torch.testing.assert_close(o_gpu["output"].cpu(), o_ref["output"], rtol=1e-3, atol=1e-4)
+    gr, gg = _grads(ref), _grads(gpu)
+    assert gr.keys() == gg.keys()
+    for n in gr:
+        scale = gr[n].abs().max().item() + 1e-12
+        err = (gg[n] - gr[n]).abs().max().item()
+        assert err <= 2e-3 * scale, (n, err, scale)
