@@ -1,25 +1,434 @@
-// tcgen05 / TMA implicit-GEMM kernels (placeholder until the tensor-core path lands: every entry
-// point reports BDBNN_ERR_UNSUPPORTED and bdbnn_tc_supported() answers 0, so callers take the
-// CUDA-core kernels in binconv.cu).
+// tcgen05 / TMA implicit-GEMM kernels for the binary convolution (sm_100a only).
+//
+//   tc_conv_kernel  : D[pix, n] = sum_{tap t} sum_{k} A[pix shifted by t, k] * B[n, t*Kc + k]
+//                     forward : A = sign(x)  (+-1 bf16, NHWC), B = sign(W)  [Cout][T][Cin]; epilogue * alpha[n]
+//                     dgrad   : A = gy*gscale (bf16,  NHWC), B = sign(W)^T [Cin][T'][Cout]; epilogue * STE mask bit
+//
+// Dataflow per CTA (one 128-row output tile, one N tile):
+//   warp 4 lane 0 : TMA producer. For every (tap, K-block) loads the activation box
+//                   [BNI images][BH rows][BW=OW cols][KB channels] at coordinates shifted by the tap —
+//                   TMA zero-fills out-of-image coordinates, which IS the conv's zero padding — and the
+//                   matching [BN x KB] weight box, into a `stages`-deep ring of 128B-swizzled K-major tiles.
+//   warp 5 lane 0 : issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), M=128, N=BN, K=16 per
+//                   instruction; tcgen05.commit releases ring slots / signals the epilogue.
+//   warps 0..3    : epilogue. tcgen05.ld the accumulator (warp w owns TMEM lanes 32w..32w+31 = tile rows),
+//                   apply alpha / STE mask, store fp32 NHWC rows (each thread writes whole 64-byte runs).
+// +-1 operands and fp32 accumulation make the forward integer-exact (|sum| <= 9*512 < 2^24).
+#include <cuda.h>
+
 #include "common.cuh"
+
+namespace bdbnn {
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+      "%13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >>4
+// in [0,14), LBO>>4 in [16,30), SBO>>4 in [32,46), version=1 in [46,48), layout type in [61,64).
+// For swizzled K-major tiles LBO is unused; SBO = bytes between 8-row groups = 8 * row_bytes.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);  // SW128 / SW64 / SW32
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFFu) >> 4);
+  d |= uint64_t(1) << 16;                          // LBO (ignored for swizzled K-major)
+  d |= uint64_t((8u * row_bytes) >> 4) << 32;      // SBO
+  d |= uint64_t(1) << 46;                          // descriptor version (Blackwell)
+  d |= uint64_t(layout) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// K-major A and B (0) @15/@16, N>>3 @17, M>>4 @24.
+__host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;
+
+struct TcConvParams {
+  int32_t OW, OH, NIMG;      // output pixel grid (one GEMM row per output pixel)
+  int32_t BW, BH, BNI;       // tile = BNI images x BH rows x BW(=OW) cols  (<= 128 pixels)
+  int32_t tiles_h;           // tiles per image group along h
+  int32_t Kc, KB, n_kb;      // contraction channels, K-block elements (16/32/64), Kc/KB
+  int32_t kh, kw, padA;      // taps; tap (r,s) reads input pixel (oh + r - padA, ow + s - padA)
+  int32_t Nout, BN;          // GEMM N total / per CTA
+  int32_t stages;
+  int32_t row_bytes;         // KB * 2 = swizzle span (32/64/128)
+  const float* alpha;        // MODE 0: per-output-channel scale
+  const uint32_t* mask;      // MODE 1: STE mask words [pix][Nout/32 (ceil)]
+  float* out;                // [pix][Nout] fp32
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = kTileM * p.row_bytes;          // ring slot: A tile then B tile
+  const uint32_t b_bytes = p.BN * p.row_bytes;
+  const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
+  const uint32_t tmem_cols = p.BN < 32 ? 32u : uint32_t(p.BN);   // power of two >= 32
+
+  const int tile_n = blockIdx.x / p.tiles_h, tile_h = blockIdx.x - tile_n * p.tiles_h;
+  const int n0 = tile_n * p.BNI, h0 = tile_h * p.BH;
+  const int nn0 = blockIdx.y * p.BN;
+  const int n_iters = p.kh * p.kw * p.n_kb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&accum_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 5) tmem_alloc(smem_u32(&tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t tx = uint32_t(p.BNI * p.BH * p.BW + p.BN) * uint32_t(p.row_bytes);
+      int it = 0;
+      for (int r = 0; r < p.kh; ++r) {
+        for (int s = 0; s < p.kw; ++s) {
+          const int t = r * p.kw + s;
+          for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+            const int stage = it % p.stages;
+            const uint32_t phase = uint32_t(it / p.stages) & 1u;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, tx);
+            const uint32_t a_dst = tiles_base + stage * stage_bytes;
+            tma_load_4d(a_dst, &tmA, fb, kb * p.KB, s - p.padA, h0 + r - p.padA, n0);
+            tma_load_2d(a_dst + a_bytes, &tmB, fb, t * p.Kc + kb * p.KB, nn0);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN));
+      const int k_steps = p.KB / 16;                  // UMMA K = 16 bf16 = 32 bytes
+      for (int it = 0; it < n_iters; ++it) {
+        const int stage = it % p.stages;
+        const uint32_t phase = uint32_t(it / p.stages) & 1u;
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t a_src = tiles_base + stage * stage_bytes;
+        for (int k = 0; k < k_steps; ++k) {
+          const uint64_t ad = make_kmajor_desc(a_src + k * 32, p.row_bytes);
+          const uint64_t bd = make_kmajor_desc(a_src + a_bytes + k * 32, p.row_bytes);
+          umma_bf16(tmem_d, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));     // slot reusable once these MMAs retire
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+  } else {
+    // ---- epilogue: warp w <-> TMEM lanes [32w, 32w+32) <-> tile rows ----
+    const int m = warp * 32 + lane;
+    const int wi = m % p.BW;
+    const int q = m / p.BW;
+    const int hi = q % p.BH, ni = q / p.BH;
+    const bool valid = (ni < p.BNI) && (h0 + hi < p.OH) && (n0 + ni < p.NIMG);
+    const int64_t pix = (int64_t(n0 + ni) * p.OH + (h0 + hi)) * p.OW + wi;
+    float* orow = p.out + pix * p.Nout + nn0;
+    const int mask_words = (p.Nout + 31) >> 5;
+
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_d + (uint32_t(warp * 32) << 16);
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(lane_base + uint32_t(c0), v);
+      tmem_ld_wait();
+      if (valid) {
+        float f[16];
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * __ldg(p.alpha + nn0 + c0 + j);
+        } else {
+          const int col = nn0 + c0;
+          const uint32_t word = __ldg(p.mask + pix * mask_words + (col >> 5)) >> (col & 31);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = ((word >> j) & 1u) ? __uint_as_float(v[j]) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side: tensor-map construction and launch
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// bf16 NHWC activation tensor [N][H][W][C] -> 4-D map, box [BNI][BH][BW][KB].
+static int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int KB, int BW,
+                        int BH, int BNI) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return BDBNN_ERR_CUDA; }
+  cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
+  cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+  cuuint32_t box[4] = {cuuint32_t(KB), cuuint32_t(BW), cuuint32_t(BH), cuuint32_t(BNI)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KB * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act) failed: %d", int(r)); return BDBNN_ERR_CUDA; }
+  return BDBNN_OK;
+}
+
+// bf16 K-major weight matrix [rows][cols] -> 2-D map, box [BN rows][KB cols].
+static int make_weight_map(CUtensorMap* map, const void* base, int rows, int cols, int KB, int BN) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return BDBNN_ERR_CUDA; }
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(cols) * 2};
+  cuuint32_t box[2] = {cuuint32_t(KB), cuuint32_t(BN)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KB * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight) failed: %d", int(r)); return BDBNN_ERR_CUDA; }
+  return BDBNN_OK;
+}
+
+static bool chan_ok(int c) { return c == 16 || c == 32 || c == 64 || (c >= 128 && c % 128 == 0); }
+static int pick_bn(int n) { return n >= 128 ? 128 : n; }   // n in {16,32,64} or multiple of 64
+
+static bool tc_shape_ok(const bdbnn_conv_shape* s) {
+  if (!s || s->stride != 1) return false;
+  if (!chan_ok(s->Cin) || !chan_ok(s->Cout)) return false;   // K blocks of 16/32/64, N tiles <= 128
+  if (s->W > 128 || s->Wo > 128 || s->W < 1) return false;
+  if (s->kh != s->kw || s->kh > 7) return false;
+  if (s->pad > s->kh - 1 || s->pad > s->kw - 1) return false;           // dgrad pad' = k-1-p >= 0
+  return true;
+}
+
+// Launch D[OH x OW pixels of `NIMG` images, Nout] = conv(A[NIMG, IH, IW, Kc], B) (see kernel header).
+template <int MODE>
+static int launch_tc_conv(const uint16_t* A, int IH, int IW, int Kc, const uint16_t* B, int Nout, int kh,
+                          int kw, int padA, int NIMG, int OH, int OW, const float* alpha,
+                          const uint32_t* mask, float* out, cudaStream_t st) {
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.OW = OW; p.OH = OH; p.NIMG = NIMG;
+  p.BW = OW;
+  if (OH * OW <= kTileM) {
+    p.BH = OH;
+    p.BNI = kTileM / (OH * OW);
+    if (p.BNI > NIMG) p.BNI = NIMG;
+    if (p.BNI > 256) p.BNI = 256;
+  } else {
+    p.BH = kTileM / OW;
+    p.BNI = 1;
+  }
+  p.tiles_h = (OH + p.BH - 1) / p.BH;
+  const int tiles_n = (NIMG + p.BNI - 1) / p.BNI;
+  p.Kc = Kc;
+  p.KB = Kc >= 64 ? 64 : Kc;
+  p.n_kb = Kc / p.KB;
+  p.row_bytes = p.KB * 2;
+  p.kh = kh; p.kw = kw; p.padA = padA;
+  p.Nout = Nout;
+  p.BN = pick_bn(Nout);
+  p.alpha = alpha; p.mask = mask; p.out = out;
+  const uint32_t stage_bytes = (uint32_t(kTileM + p.BN) * p.row_bytes + 1023u) & ~1023u;
+  int stages = int((96u * 1024u) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > kh * kw * p.n_kb) stages = kh * kw * p.n_kb;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = size_t(stages) * stage_bytes + 1024;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_act_map(&tmA, A, NIMG, IH, IW, Kc, p.KB, p.BW, p.BH, p.BNI);
+  if (rc) return rc;
+  rc = make_weight_map(&tmB, B, Nout, kh * kw * Kc, p.KB, p.BN);
+  if (rc) return rc;
+  auto kern = tc_conv_kernel<MODE>;
+  BDBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  dim3 grid(unsigned(p.tiles_h * tiles_n), unsigned(Nout / p.BN));
+  kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+  return check_launch("tc_conv_kernel");
+}
+
+}  // namespace bdbnn
 
 using namespace bdbnn;
 
-extern "C" int bdbnn_tc_supported(const bdbnn_conv_shape*) { return 0; }
+extern "C" int bdbnn_tc_supported(const bdbnn_conv_shape* s) {
+  return tc_shape_ok(s) ? (BDBNN_TC_FWD | BDBNN_TC_DGRAD) : 0;
+}
 
-extern "C" int bdbnn_binconv_fwd_tc(const uint16_t*, const uint16_t*, const float*, float*,
-                                    const bdbnn_conv_shape*, void*) {
-  set_error("binconv_fwd_tc: not built");
-  return BDBNN_ERR_UNSUPPORTED;
+extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, const float* alpha,
+                                    float* y, const bdbnn_conv_shape* s, void* stream) {
+  int rc = validate_shape(s);
+  if (rc) return rc;
+  BDBNN_REQUIRE(xb_bf16 && wf_bf16 && alpha && y, "binconv_fwd_tc: NULL pointer");
+  if (!tc_shape_ok(s)) { set_error("binconv_fwd_tc: shape not supported by the tcgen05 path"); return BDBNN_ERR_UNSUPPORTED; }
+  return launch_tc_conv<0>(xb_bf16, s->H, s->W, s->Cin, wf_bf16, s->Cout, s->kh, s->kw, s->pad, s->N,
+                           s->Ho, s->Wo, alpha, nullptr, y, cudaStream_t(stream));
 }
-extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t*, const uint16_t*, const uint32_t*, float*,
-                                      const bdbnn_conv_shape*, void*) {
-  set_error("binconv_dgrad_tc: not built");
-  return BDBNN_ERR_UNSUPPORTED;
+
+extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, const uint16_t* wt_bf16,
+                                      const uint32_t* mask_bits, float* gx, const bdbnn_conv_shape* s,
+                                      void* stream) {
+  int rc = validate_shape(s);
+  if (rc) return rc;
+  BDBNN_REQUIRE(gys_bf16 && wt_bf16 && mask_bits && gx, "binconv_dgrad_tc: NULL pointer");
+  if (!tc_shape_ok(s)) { set_error("binconv_dgrad_tc: shape not supported by the tcgen05 path"); return BDBNN_ERR_UNSUPPORTED; }
+  // gx[h,w,c] = sum_{r',s',o} gys[h + r' - (kh-1-p), w + s' - (kw-1-p), o] * wt[c][(r',s')][o]
+  return launch_tc_conv<1>(gys_bf16, s->Ho, s->Wo, s->Cout, wt_bf16, s->Cin, s->kh, s->kw,
+                           s->kh - 1 - s->pad, s->N, s->H, s->W, nullptr, mask_bits, gx,
+                           cudaStream_t(stream));
 }
+
 extern "C" size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape*) { return 0; }
 extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t*, const uint16_t*, const uint32_t*, const float*,
                                       float*, const bdbnn_conv_shape*, void*, size_t, void*) {
-  set_error("binconv_wgrad_tc: not built");
+  set_error("binconv_wgrad_tc: not built yet");
   return BDBNN_ERR_UNSUPPORTED;
 }

@@ -115,10 +115,10 @@ def resolve_impl(impl, shape):
     impl = impl or os.environ.get(_IMPL_ENV, "auto")
     if impl not in _VALID_IMPL:
         raise ValueError(f"impl must be one of {_VALID_IMPL}, got {impl!r}")
-    tc_ok = bool(_lib.lib().bdbnn_tc_supported(ctypes.byref(shape)))
-    if impl == "tc" and not tc_ok:
+    caps = int(_lib.lib().bdbnn_tc_supported(ctypes.byref(shape)))
+    if impl == "tc" and not (caps & 1):
         raise RuntimeError("bdbnn_b200: impl='tc' requested but the tcgen05 path does not support this shape")
-    return "tc" if (impl in ("auto", "tc") and tc_ok) else "xnor"
+    return caps if (impl in ("auto", "tc") and (caps & 1)) else 0
 
 
 class _BinConv2d(torch.autograd.Function):
@@ -146,7 +146,7 @@ class _BinConv2d(torch.autograd.Function):
         i32 = dict(dtype=torch.int32, device=dev)
         sign_bits = torch.empty((n, h, wd, cw), **i32)
         mask_bits = torch.empty((n, h, wd, cw), **i32)
-        tc = use == "tc"
+        tc = bool(use & 1)
         xb = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=dev) if tc else None
         key = _shape_key(sh)
         with _timed("act_pack", key, algorithmic_bytes("act_pack_tc" if tc else "act_pack", sh)):
@@ -196,13 +196,15 @@ class _BinConv2d(torch.autograd.Function):
         saved = ctx.saved_tensors
         sign_bits, mask_bits, wsign, wmask, alpha = saved[:5]
         key = _shape_key(sh)
-        if ctx.use == "tc":
+        if ctx.use & 1:
             xb, wt, gscale, inv_gscale = saved[5:]
             n_pix_out = sh.N * sh.Ho * sh.Wo
             gys = torch.empty((sh.N, sh.Ho, sh.Wo, sh.Cout), dtype=torch.bfloat16, device=dev)
             with _timed("grad_pack", key, algorithmic_bytes("grad_pack", sh)):
                 _lib.check(L.bdbnn_grad_pack(_p(g), _p(gscale), n_pix_out, sh.Cout, _p(gys), st), "grad_pack")
             _lib.count(1)
+            if need_x and not (ctx.use & 2):
+                raise RuntimeError("bdbnn_b200: dgrad_tc unavailable for a shape fwd_tc accepted")
             if need_x:
                 gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev,
                                  memory_format=torch.channels_last)
@@ -210,7 +212,14 @@ class _BinConv2d(torch.autograd.Function):
                     _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), _p(wt), _p(mask_bits), _p(gx),
                                                         ctypes.byref(sh), st), "binconv_dgrad_tc")
                 _lib.count(1)
-            if need_w:
+            if need_w and not (ctx.use & 4):
+                # wgrad on CUDA cores from the saved sign bits (tcgen05 wgrad not available for this shape)
+                gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
+                with _timed("binconv_wgrad_generic", key, algorithmic_bytes("wgrad", sh)):
+                    _lib.check(L.bdbnn_binconv_wgrad(_p(g), _p(sign_bits), _p(wmask), _p(gw),
+                                                     ctypes.byref(sh), st), "binconv_wgrad")
+                _lib.count(1)
+            elif need_w:
                 gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
                 nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
                 ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)

@@ -51,7 +51,11 @@ typedef struct bdbnn_conv_shape {
 BDBNN_API int bdbnn_version(void);
 /* Thread-local description of the last error returned on this thread ("" if none). */
 BDBNN_API const char* bdbnn_last_error_string(void);
-/* 1 if the tcgen05/TMA implicit-GEMM kernels can serve this shape, else 0 (generic kernels do). */
+/* Which tcgen05/TMA implicit-GEMM kernels can serve this shape: bitmask
+ * BDBNN_TC_FWD | BDBNN_TC_DGRAD | BDBNN_TC_WGRAD (0 = none: the CUDA-core kernels do all three). */
+#define BDBNN_TC_FWD 1
+#define BDBNN_TC_DGRAD 2
+#define BDBNN_TC_WGRAD 4
 BDBNN_API int bdbnn_tc_supported(const bdbnn_conv_shape* s);
 
 /* ---- activation sign/pack ---------------------------------------------------------------------

@@ -69,7 +69,8 @@ def main():
         gw = torch.empty_like(w)
         st = _stream()
         shp = ctypes.byref(sh)
-        tc = a.impl == "tc" and L.bdbnn_tc_supported(shp)
+        caps = int(L.bdbnn_tc_supported(shp)) if a.impl == "tc" else 0
+        tc = bool(caps & 1)
         ck = _lib.check
         kernels = {
             "act_pack" + ("_tc" if tc else ""): lambda: ck(L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb if tc else None), st), "p"),
@@ -82,8 +83,11 @@ def main():
                 "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), shp, st), "f"),
                 "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, _p(gys), st), "g"),
                 "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), _p(wt), _p(mb), _p(gx), shp, st), "d"),
-                "wgrad_tc": lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w"),
             })
+            if caps & 4:
+                kernels["wgrad_tc"] = lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w")
+            else:
+                kernels["wgrad"] = lambda: ck(L.bdbnn_binconv_wgrad(_p(gy), _p(sb), _p(wm), _p(gw), shp, st), "w")
         else:
             kernels.update({
                 "fwd_xnor": lambda: ck(L.bdbnn_binconv_fwd_xnor(_p(sb), _p(ws), _p(alpha), _p(y), shp, st), "f"),

@@ -271,7 +271,7 @@ def test_kd_logits_matches_reference_golden():
 
 def test_kd_layer_matches_reference_golden():
     from bdbnn_b200 import DistributionLoss_layer
-    from tests.test_oracle_golden import _tiny
+    from helpers import tiny_net as _tiny
     for case in _golden("kd_layer_cases.pt"):
         stud, teach = _tiny(case["wrapped"]), _tiny(case["wrapped"])
         stud.load_state_dict(case["stud_state"])

@@ -1,0 +1,104 @@
+"""GPU: tcgen05/TMA implicit-GEMM kernels vs the CUDA-core kernels and the CPU oracle."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import binconv_ref as B  # noqa: E402
+
+TC_SHAPES = [  # n, cin, h, w, cout, k, stride, pad
+    (2, 64, 8, 8, 64, 3, 1, 1),        # 64-pixel images: 2 images per 128-row tile
+    (3, 64, 14, 14, 128, 3, 1, 1),     # partial h tiles (9+5 rows), odd image count
+    (2, 128, 28, 28, 128, 3, 1, 1),    # R18 layer2 geometry, two K blocks per tap
+    (1, 64, 56, 56, 64, 3, 1, 1),      # R18 layer1 geometry
+    (5, 256, 7, 7, 256, 3, 1, 1),      # 49-pixel images, 2 per tile, odd count -> OOB image
+    (2, 16, 32, 32, 16, 3, 1, 1),      # R20 stage1: 32-byte swizzle
+    (2, 32, 16, 16, 32, 3, 1, 1),      # R20 stage2: 64-byte swizzle
+    (2, 64, 9, 11, 64, 3, 1, 0),       # pad 0: output grid smaller than input
+    (1, 64, 6, 6, 64, 1, 1, 0),        # 1x1
+    (1, 64, 10, 10, 64, 5, 1, 2),      # 5x5
+    (1, 512, 7, 7, 512, 3, 1, 1),      # R18 layer4: 8 K blocks, 4 N tiles
+]
+
+
+def _caps(shape):
+    from bdbnn_b200 import _lib
+    from bdbnn_b200.functional import conv_shape
+    n, cin, h, w, cout, k, stride, pad = shape
+    sh = conv_shape((n, cin, h, w), (cout, cin, k, k), stride, pad)
+    return int(_lib.lib().bdbnn_tc_supported(ctypes.byref(sh)))
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_fwd_tc_equals_xnor_bit_exact_and_oracle(shape):
+    from bdbnn_b200.functional import binconv2d
+    assert _caps(shape) & 1
+    n, cin, h, w, cout, k, stride, pad = shape
+    g = torch.Generator().manual_seed(17 + sum(shape))
+    x = torch.randn(n, cin, h, w, generator=g)
+    x.view(-1)[0] = 0.0
+    wt = torch.randn(cout, cin, k, k, generator=g) * 0.1
+    xd = x.cuda().contiguous(memory_format=torch.channels_last)
+    wd = wt.cuda()
+    y_tc = binconv2d(xd, wd, stride, pad, "tc")
+    y_x = binconv2d(xd, wd, stride, pad, "xnor")
+    assert torch.equal(y_tc, y_x)                       # both: alpha[o] * exact integer, same fp32 multiply
+    ref = B.binconv_forward(x.double(), wt.double(), stride, pad).float()
+    torch.testing.assert_close(y_tc.cpu(), ref, rtol=3e-6, atol=0)
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_backward_tc_vs_oracle(shape):
+    """bf16 rounding of gy*gscale (rel 2^-9 per element, random sign) bounds the error; weights +-1 and
+    the fp32 accumulation are exact.  Tolerance: 1e-2 of max|ref| (observed ~2e-3)."""
+    from bdbnn_b200.functional import binconv2d
+    caps = _caps(shape)
+    assert caps & 2
+    n, cin, h, w, cout, k, stride, pad = shape
+    g = torch.Generator().manual_seed(23 + sum(shape))
+    x = torch.randn(n, cin, h, w, generator=g) * 1.2
+    wt = torch.randn(cout, cin, k, k, generator=g) * 0.8
+    if cout > 2:
+        wt[1].zero_()                                    # alpha == 0 filter
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wd = wt.cuda().requires_grad_(True)
+    y = binconv2d(xd, wd, stride, pad, "tc")
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy.cuda())
+    gx_ref, gw_ref = B.binconv_backward(x.double(), wt.double(), gy.double(), stride, pad)
+    for name, got, ref in (("gx", xd.grad.cpu(), gx_ref), ("gw", wd.grad.cpu(), gw_ref)):
+        scale = ref.abs().max().item() + 1e-30
+        err = (got.double() - ref).abs().max().item()
+        assert err <= 1e-2 * scale, (name, err, scale)
+    assert (xd.grad.cpu()[x.abs() > 1] == 0).all()
+    assert (wd.grad.cpu()[wt.abs() > 1] == 0).all()
+    # exactness check of the data path: gy representable in bf16 and alpha a power of two -> exact dgrad
+    wt2 = B.sign_pm1(torch.randn(cout, cin, k, k, generator=g)) * 0.5
+    gy2 = torch.randint(-8, 9, y.shape, generator=g).float()
+    xd2 = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y2 = binconv2d(xd2, wt2.cuda(), stride, pad, "tc")
+    y2.backward(gy2.cuda())
+    gx2, _ = B.binconv_backward(x.double(), wt2.double(), gy2.double(), stride, pad)
+    assert torch.equal(xd2.grad.cpu().double(), gx2)
+
+
+def test_tc_supported_rejects_unsupported_shapes():
+    assert _caps((1, 40, 8, 8, 64, 3, 1, 1)) == 0       # Cin not 16/32/64/128k
+    assert _caps((1, 64, 8, 8, 64, 3, 2, 1)) == 0       # stride 2 (CUDA-core kernels for now)
+    assert _caps((1, 64, 8, 200, 64, 3, 1, 1)) == 0     # row wider than one tile
+    from bdbnn_b200.functional import binconv2d
+    with pytest.raises(RuntimeError, match="tcgen05"):
+        binconv2d(torch.randn(1, 40, 8, 8, device="cuda"), torch.randn(64, 40, 3, 3, device="cuda"), 1, 1, "tc")
+
+
+def test_fwd_tc_full_size_layers_equal_xnor():
+    """BASELINE.json config-2 sizes (ResNet-18, N=256): the two independent forward kernels agree
+    bit-for-bit on every stride-1 3x3 layer geometry."""
+    from bdbnn_b200.functional import binconv2d
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for cin, hw in ((64, 56), (128, 28), (256, 14), (512, 7)):
+        x = torch.randn(256, cin, hw, hw, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+        w = torch.randn(cin, cin, 3, 3, device="cuda", generator=g) * 0.05
+        assert torch.equal(binconv2d(x, w, 1, 1, "tc"), binconv2d(x, w, 1, 1, "xnor"))

@@ -39,21 +39,7 @@ def test_kd_logits_oracle_matches_reference(golden_dir):
                                    rtol=1e-5, atol=1e-8)
 
 
-def _tiny(wrapped):
-    import torch.nn as nn
-    net = nn.Module()
-    net.conv1 = nn.Conv2d(3, 8, 3, bias=False)
-    blk = nn.Module()
-    blk.conv1 = nn.Conv2d(8, 8, 3, bias=False)
-    blk.conv2 = nn.Conv2d(8, 16, 3, bias=False)
-    blk.downsample = nn.Sequential(nn.Conv2d(8, 16, 1, bias=False))
-    net.layer1 = nn.Sequential(blk)
-    net.fc = nn.Linear(16, 4)
-    if wrapped:
-        outer = nn.Module()
-        outer.module = net
-        return outer
-    return net
+from helpers import tiny_net as _tiny  # noqa: E402
 
 
 def test_kd_layer_pairing_and_value_match_reference(golden_dir):
