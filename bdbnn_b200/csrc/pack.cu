@@ -134,7 +134,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// gys[i] = bf16_rn(gy[i] * gscale[i % Cout]); Cout % 4 == 0 fast path, scalar tail otherwise.
+// v = gy[i] * gscale[i % Cout]; halves==1: out[i] = bf16_rn(v);
+// halves==2: out[pix*2*Cout + o] = hi = bf16_rn(v), out[pix*2*Cout + Cout + o] = bf16_rn(v - hi).
+__device__ __forceinline__ float bf16_round(float v) {
+  return __uint_as_float(pack_bf16x2(0.f, v) & 0xffff0000u);
+}
+template <int HALVES>
 __global__ void __launch_bounds__(256)
 grad_pack_kernel(const float* __restrict__ gy, const float* __restrict__ gscale, int64_t n,
                  int32_t Cout, uint16_t* __restrict__ out) {
@@ -143,20 +148,33 @@ grad_pack_kernel(const float* __restrict__ gy, const float* __restrict__ gscale,
   if ((Cout & 3) == 0) {
     const int64_t n4 = n >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(gy);
-    uint2* o2 = reinterpret_cast<uint2*>(out);
     for (int64_t i = tid; i < n4; i += nthreads) {
       const float4 v = __ldcs(g4 + i);
-      const int o = int((i * 4) % Cout);
+      const int64_t e = i * 4;
+      const int64_t pix = e / Cout;
+      const int o = int(e - pix * Cout);
       const float4 s = *reinterpret_cast<const float4*>(gscale + o);
+      const float a0 = v.x * s.x, a1 = v.y * s.y, a2 = v.z * s.z, a3 = v.w * s.w;
       uint2 r;
-      r.x = pack_bf16x2(v.x * s.x, v.y * s.y);
-      r.y = pack_bf16x2(v.z * s.z, v.w * s.w);
-      o2[i] = r;
+      r.x = pack_bf16x2(a0, a1);
+      r.y = pack_bf16x2(a2, a3);
+      uint16_t* dst = out + pix * (int64_t(HALVES) * Cout) + o;
+      *reinterpret_cast<uint2*>(dst) = r;
+      if (HALVES == 2) {
+        uint2 l;
+        l.x = pack_bf16x2(a0 - bf16_round(a0), a1 - bf16_round(a1));
+        l.y = pack_bf16x2(a2 - bf16_round(a2), a3 - bf16_round(a3));
+        *reinterpret_cast<uint2*>(dst + Cout) = l;
+      }
     }
   } else {
     for (int64_t i = tid; i < n; i += nthreads) {
-      const float v = gy[i] * gscale[i % Cout];
-      out[i] = uint16_t(pack_bf16x2(v, 0.f) & 0xffffu);
+      const int64_t pix = i / Cout;
+      const int o = int(i - pix * Cout);
+      const float v = gy[i] * gscale[o];
+      uint16_t* dst = out + pix * (int64_t(HALVES) * Cout) + o;
+      *dst = uint16_t(pack_bf16x2(v, 0.f) & 0xffffu);
+      if (HALVES == 2) dst[Cout] = uint16_t(pack_bf16x2(v - bf16_round(v), 0.f) & 0xffffu);
     }
   }
 }
@@ -203,8 +221,9 @@ extern "C" int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int3
 }
 
 extern "C" int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_pix, int32_t Cout,
-                               uint16_t* gys_bf16, void* stream) {
+                               int32_t halves, uint16_t* gys_bf16, void* stream) {
   BDBNN_REQUIRE(n_pix >= 0 && Cout > 0, "grad_pack: bad dims");
+  BDBNN_REQUIRE(halves == 1 || halves == 2, "grad_pack: halves must be 1 or 2");
   if (n_pix == 0) return BDBNN_OK;
   BDBNN_REQUIRE(gy && gscale && gys_bf16, "grad_pack: NULL pointer");
   const int64_t n = n_pix * Cout;
@@ -212,6 +231,9 @@ extern "C" int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_p
   const int64_t cap = int64_t(num_sms()) * 8 * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  grad_pack_kernel<<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(gy, gscale, n, Cout, gys_bf16);
+  if (halves == 2)
+    grad_pack_kernel<2><<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(gy, gscale, n, Cout, gys_bf16);
+  else
+    grad_pack_kernel<1><<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(gy, gscale, n, Cout, gys_bf16);
   return check_launch("grad_pack_kernel");
 }

@@ -139,13 +139,19 @@ __host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
 constexpr int kTcThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kTileM = 128;
+constexpr int kMaxTaps = 49;
 
 struct TcConvParams {
   int32_t OW, OH, NIMG;      // output pixel grid (one GEMM row per output pixel)
   int32_t BW, BH, BNI;       // tile = BNI images x BH rows x BW(=OW) cols  (<= 128 pixels)
   int32_t tiles_h;           // tiles per image group along h
   int32_t Kc, KB, n_kb;      // contraction channels, K-block elements (16/32/64), Kc/KB
-  int32_t kh, kw, padA;      // taps; tap (r,s) reads input pixel (oh + r - padA, ow + s - padA)
+  int32_t a_halves;          // 1: A has Kc channels; 2: A = [hi | lo] bf16 split, 2*Kc channels, B reused
+  int32_t in_step;           // input coordinate = out coordinate * in_step + tap offset (2 for stride-2 fwd)
+  int32_t n_taps;            // taps actually visited (subset for the stride-2 dgrad phases)
+  int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];   // input offset of tap i
+  uint8_t tap_b[kMaxTaps];   // K-block row of B for tap i (B column = tap_b * Kc + k)
+  int32_t out_step, out_off_h, out_off_w, OHf, OWf;  // out pixel = (oh*out_step+off_h, ow*out_step+off_w) in OHf x OWf
   int32_t Nout, BN;          // GEMM N total / per CTA
   int32_t stages;
   int32_t row_bytes;         // KB * 2 = swizzle span (32/64/128)
@@ -174,7 +180,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tile_n = blockIdx.x / p.tiles_h, tile_h = blockIdx.x - tile_n * p.tiles_h;
   const int n0 = tile_n * p.BNI, h0 = tile_h * p.BH;
   const int nn0 = blockIdx.y * p.BN;
-  const int n_iters = p.kh * p.kw * p.n_kb;
+  const int kb_total = p.n_kb * p.a_halves;
+  const int n_iters = p.n_taps * kb_total;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -198,19 +205,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t tx = uint32_t(p.BNI * p.BH * p.BW + p.BN) * uint32_t(p.row_bytes);
       int it = 0;
-      for (int r = 0; r < p.kh; ++r) {
-        for (int s = 0; s < p.kw; ++s) {
-          const int t = r * p.kw + s;
-          for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-            const int stage = it % p.stages;
-            const uint32_t phase = uint32_t(it / p.stages) & 1u;
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_expect_tx(fb, tx);
-            const uint32_t a_dst = tiles_base + stage * stage_bytes;
-            tma_load_4d(a_dst, &tmA, fb, kb * p.KB, s - p.padA, h0 + r - p.padA, n0);
-            tma_load_2d(a_dst + a_bytes, &tmB, fb, t * p.Kc + kb * p.KB, nn0);
-          }
+      for (int ti = 0; ti < p.n_taps; ++ti) {
+        const int dh = p.tap_dh[ti], dw = p.tap_dw[ti], tb = p.tap_b[ti];
+        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+          const int stage = it % p.stages;
+          const uint32_t phase = uint32_t(it / p.stages) & 1u;
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, tx);
+          const uint32_t a_dst = tiles_base + stage * stage_bytes;
+          const int kbb = kb >= p.n_kb ? kb - p.n_kb : kb;       // hi and lo halves share B
+          tma_load_4d(a_dst, &tmA, fb, kb * p.KB, dw, h0 * p.in_step + dh, n0);
+          tma_load_2d(a_dst + a_bytes, &tmB, fb, tb * p.Kc + kbb * p.KB, nn0);
         }
       }
     }
@@ -239,8 +245,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int wi = m % p.BW;
     const int q = m / p.BW;
     const int hi = q % p.BH, ni = q / p.BH;
-    const bool valid = (ni < p.BNI) && (h0 + hi < p.OH) && (n0 + ni < p.NIMG);
-    const int64_t pix = (int64_t(n0 + ni) * p.OH + (h0 + hi)) * p.OW + wi;
+    const int oh = (h0 + hi) * p.out_step + p.out_off_h, ow = wi * p.out_step + p.out_off_w;
+    const bool valid = (ni < p.BNI) && (h0 + hi < p.OH) && (n0 + ni < p.NIMG) && oh < p.OHf && ow < p.OWf;
+    const int64_t pix = (int64_t(n0 + ni) * p.OHf + oh) * p.OWf + ow;
     float* orow = p.out + pix * p.Nout + nn0;
     const int mask_words = (p.Nout + 31) >> 5;
 
@@ -306,13 +313,14 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
 
 // bf16 NHWC activation tensor [N][H][W][C] -> 4-D map, box [BNI][BH][BW][KB].
 static int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int KB, int BW,
-                        int BH, int BNI) {
+                        int BH, int BNI, int step = 1) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return BDBNN_ERR_CUDA; }
   cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
   cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
-  cuuint32_t box[4] = {cuuint32_t(KB), cuuint32_t(BW), cuuint32_t(BH), cuuint32_t(BNI)};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // element stride `step` in w/h: TMA loads ceil(box/step) elements, so box = loaded * step
+  cuuint32_t box[4] = {cuuint32_t(KB), cuuint32_t(BW * step), cuuint32_t(BH * step), cuuint32_t(BNI)};
+  cuuint32_t estr[4] = {1, cuuint32_t(step), cuuint32_t(step), 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KB * 2),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -336,61 +344,75 @@ static int make_weight_map(CUtensorMap* map, const void* base, int rows, int col
 }
 
 static bool chan_ok(int c) { return c == 16 || c == 32 || c == 64 || (c >= 128 && c % 128 == 0); }
-static int pick_bn(int n) { return n >= 128 ? 128 : n; }   // n in {16,32,64} or multiple of 64
+static int pick_bn(int n) { return n >= 128 ? 128 : n; }   // n in {16,32,64} or multiple of 128
 
 static bool tc_shape_ok(const bdbnn_conv_shape* s) {
-  if (!s || s->stride != 1) return false;
+  if (!s || (s->stride != 1 && s->stride != 2)) return false;
   if (!chan_ok(s->Cin) || !chan_ok(s->Cout)) return false;   // K blocks of 16/32/64, N tiles <= 128
-  if (s->W > 128 || s->Wo > 128 || s->W < 1) return false;
+  if (s->Wo > 128 || s->W > 128 * s->stride || s->W < 1) return false;
   if (s->kh != s->kw || s->kh > 7) return false;
-  if (s->pad > s->kh - 1 || s->pad > s->kw - 1) return false;           // dgrad pad' = k-1-p >= 0
+  if (s->pad > s->kh - 1) return false;
   return true;
 }
 
-// Launch D[OH x OW pixels of `NIMG` images, Nout] = conv(A[NIMG, IH, IW, Kc], B) (see kernel header).
+// One implicit-GEMM launch: D[NIMG x OH x OW pixels, Nout] = sum_taps A[pixel*in_step + tap offset] * B.
+struct TcConvLaunch {
+  const uint16_t* A; int IH, IW, Kc, a_halves, in_step;
+  const uint16_t* B; int b_taps, Nout;
+  int NIMG, OH, OW;
+  int n_taps; int8_t dh[kMaxTaps], dw[kMaxTaps]; uint8_t tb[kMaxTaps];
+  int out_step, off_h, off_w, OHf, OWf;
+  const float* alpha; const uint32_t* mask; float* out;
+};
+
 template <int MODE>
-static int launch_tc_conv(const uint16_t* A, int IH, int IW, int Kc, const uint16_t* B, int Nout, int kh,
-                          int kw, int padA, int NIMG, int OH, int OW, const float* alpha,
-                          const uint32_t* mask, float* out, cudaStream_t st) {
+static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   TcConvParams p;
   memset(&p, 0, sizeof(p));
-  p.OW = OW; p.OH = OH; p.NIMG = NIMG;
-  p.BW = OW;
-  if (OH * OW <= kTileM) {
-    p.BH = OH;
-    p.BNI = kTileM / (OH * OW);
-    if (p.BNI > NIMG) p.BNI = NIMG;
+  p.OW = L.OW; p.OH = L.OH; p.NIMG = L.NIMG;
+  p.BW = L.OW;
+  if (L.OH * L.OW <= kTileM) {
+    p.BH = L.OH;
+    p.BNI = kTileM / (L.OH * L.OW);
+    if (p.BNI > L.NIMG) p.BNI = L.NIMG;
     if (p.BNI > 256) p.BNI = 256;
   } else {
-    p.BH = kTileM / OW;
+    p.BH = kTileM / L.OW;
     p.BNI = 1;
   }
-  p.tiles_h = (OH + p.BH - 1) / p.BH;
-  const int tiles_n = (NIMG + p.BNI - 1) / p.BNI;
-  p.Kc = Kc;
-  p.KB = Kc >= 64 ? 64 : Kc;
-  p.n_kb = Kc / p.KB;
+  p.tiles_h = (L.OH + p.BH - 1) / p.BH;
+  const int tiles_n = (L.NIMG + p.BNI - 1) / p.BNI;
+  p.Kc = L.Kc;
+  p.KB = L.Kc >= 64 ? 64 : L.Kc;
+  p.n_kb = L.Kc / p.KB;
+  p.a_halves = L.a_halves;
+  p.in_step = L.in_step;
   p.row_bytes = p.KB * 2;
-  p.kh = kh; p.kw = kw; p.padA = padA;
-  p.Nout = Nout;
-  p.BN = pick_bn(Nout);
-  p.alpha = alpha; p.mask = mask; p.out = out;
+  p.n_taps = L.n_taps;
+  memcpy(p.tap_dh, L.dh, sizeof(p.tap_dh));
+  memcpy(p.tap_dw, L.dw, sizeof(p.tap_dw));
+  memcpy(p.tap_b, L.tb, sizeof(p.tap_b));
+  p.out_step = L.out_step; p.out_off_h = L.off_h; p.out_off_w = L.off_w; p.OHf = L.OHf; p.OWf = L.OWf;
+  p.Nout = L.Nout;
+  p.BN = pick_bn(L.Nout);
+  p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
   const uint32_t stage_bytes = (uint32_t(kTileM + p.BN) * p.row_bytes + 1023u) & ~1023u;
+  const int n_iters = p.n_taps * p.n_kb * p.a_halves;
   int stages = int((96u * 1024u) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > kh * kw * p.n_kb) stages = kh * kw * p.n_kb;
+  if (stages > n_iters) stages = n_iters;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = size_t(stages) * stage_bytes + 1024;
 
   CUtensorMap tmA, tmB;
-  int rc = make_act_map(&tmA, A, NIMG, IH, IW, Kc, p.KB, p.BW, p.BH, p.BNI);
+  int rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, p.KB, p.BW, p.BH, p.BNI, L.in_step);
   if (rc) return rc;
-  rc = make_weight_map(&tmB, B, Nout, kh * kw * Kc, p.KB, p.BN);
+  rc = make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, p.KB, p.BN);
   if (rc) return rc;
   auto kern = tc_conv_kernel<MODE>;
   BDBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  dim3 grid(unsigned(p.tiles_h * tiles_n), unsigned(Nout / p.BN));
+  dim3 grid(unsigned(p.tiles_h * tiles_n), unsigned(L.Nout / p.BN));
   kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   return check_launch("tc_conv_kernel");
 }
@@ -415,7 +437,8 @@ struct TcWgradParams {
   int32_t BW, BH, BNI, tiles_h;  // K box = BNI x BH x BW output pixels
   int32_t rows_box, k_stage;     // valid pixel rows per box, rounded up to 16
   int32_t n_kboxes, kboxes_per_cta;
-  int32_t Cin, Cout, kh, kw, pad;
+  int32_t Cin, Cout, kh, kw, pad, stride;
+  int32_t g_halves;              // 1: gys = bf16(g); 2: gys = [hi | lo] split, both accumulated
   int32_t chunks_per_tap;        // Cin / 64
   int32_t n_units, G;            // (tap, chunk) units; M tiles (accumulators) per CTA
   int32_t BN;                    // N tile (output channels per CTA)
@@ -448,7 +471,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int mt0 = blockIdx.y * p.G;                               // first M tile of this CTA
   const int n_mtiles = (p.n_units + 1) / 2;
   const int g_cta = min(p.G, n_mtiles - mt0);
-  const int nb_boxes = p.BN / 64;
+  const int nb_chunks = p.BN / 64;                                // 64-channel chunks of the N tile
+  const int nb_boxes = nb_chunks * p.g_halves;                    // hi (and lo) boxes of gys
   const uint32_t a_bytes = uint32_t(p.G) * 2u * box_bytes;
   const uint32_t stage_bytes = a_bytes + uint32_t(nb_boxes) * box_bytes;
   const int nn0 = blockIdx.z * p.BN;
@@ -508,10 +532,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           if (u >= p.n_units) u = p.n_units - 1;                  // odd unit count: duplicate, rows ignored
           const int t = u / p.chunks_per_tap, j = u - t * p.chunks_per_tap;
           const int r = t / p.kw, s = t - r * p.kw;
-          tma_load_4d(dst0 + i * box_bytes, &tmX, fb, j * 64, s - p.pad, h0 + r - p.pad, n0);
+          tma_load_4d(dst0 + i * box_bytes, &tmX, fb, j * 64, s - p.pad, h0 * p.stride + r - p.pad, n0);
         }
-        for (int jb = 0; jb < nb_boxes; ++jb)
-          tma_load_4d(dst0 + a_bytes + jb * box_bytes, &tmG, fb, nn0 + jb * 64, 0, h0, n0);
+        for (int hf = 0; hf < p.g_halves; ++hf)
+          for (int jb = 0; jb < nb_chunks; ++jb)
+            tma_load_4d(dst0 + a_bytes + (hf * nb_chunks + jb) * box_bytes, &tmG, fb,
+                        hf * p.Cout + nn0 + jb * 64, 0, h0, n0);
       }
     }
   } else if (warp == 5) {
@@ -528,10 +554,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t a0 = tiles_base + stage * stage_bytes;
         const uint32_t b0 = a0 + a_bytes;
         for (int g = 0; g < g_cta; ++g) {
-          for (int k = 0; k < k_steps; ++k) {
-            const uint64_t ad = make_mnmajor_desc(a0 + g * 2 * box_bytes + k * 2048, box_bytes);
-            const uint64_t bd = make_mnmajor_desc(b0 + k * 2048, box_bytes);
-            umma_bf16(tmem_d + uint32_t(g * p.BN), ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int hf = 0; hf < p.g_halves; ++hf) {
+            for (int k = 0; k < k_steps; ++k) {
+              const uint64_t ad = make_mnmajor_desc(a0 + g * 2 * box_bytes + k * 2048, box_bytes);
+              const uint64_t bd = make_mnmajor_desc(b0 + hf * nb_chunks * box_bytes + k * 2048, box_bytes);
+              umma_bf16(tmem_d + uint32_t(g * p.BN), ad, bd, idesc, (it > 0 || k > 0 || hf > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));
@@ -590,17 +618,18 @@ struct WgradPlan {
   bool ok;
 };
 
-static WgradPlan plan_wgrad(const bdbnn_conv_shape* s) {
+static WgradPlan plan_wgrad(const bdbnn_conv_shape* s, int halves = 2) {
   WgradPlan pl;
   memset(&pl, 0, sizeof(pl));
-  if (!s || s->stride != 1 || s->kh != s->kw || s->kh > 7 || s->pad > s->kh - 1) return pl;
+  if (!s || (s->stride != 1 && s->stride != 2) || s->kh != s->kw || s->kh > 7 || s->pad > s->kh - 1) return pl;
   if (s->Cin % 64 != 0 || s->Cout % 64 != 0) return pl;
   if (s->Cout > 128 && s->Cout % 256 != 0) return pl;
-  if (s->Wo > 128 || s->W > 256) return pl;
+  if (s->Wo > 128 || s->W > 128 * s->stride) return pl;
   TcWgradParams& p = pl.p;
   const int T = s->kh * s->kw;
   p.OW = s->Wo; p.OH = s->Ho; p.NIMG = s->N;
-  p.Cin = s->Cin; p.Cout = s->Cout; p.kh = s->kh; p.kw = s->kw; p.pad = s->pad;
+  p.Cin = s->Cin; p.Cout = s->Cout; p.kh = s->kh; p.kw = s->kw; p.pad = s->pad; p.stride = s->stride;
+  p.g_halves = halves;
   p.chunks_per_tap = s->Cin / 64;
   p.n_units = T * p.chunks_per_tap;
   const int n_mtiles = (p.n_units + 1) / 2;
@@ -610,7 +639,7 @@ static WgradPlan plan_wgrad(const bdbnn_conv_shape* s) {
   if (p.G > 5) p.G = 5;
   p.stages = 2;
   // choose the K box: largest pixel-row count whose ring fits ~200 KB, best utilisation first
-  const int row_bytes_all = p.G * 256 + p.BN * 2;               // smem bytes per pixel row per stage
+  const int row_bytes_all = p.G * 256 + p.BN * 2 * halves;      // smem bytes per pixel row per stage
   const int k_cap = int((200u * 1024u) / (unsigned(p.stages) * unsigned(row_bytes_all))) & ~15;
   if (k_cap < 16) return pl;
   const int kmax = k_cap > 128 ? 128 : k_cap;
@@ -654,7 +683,7 @@ using namespace bdbnn;
 
 extern "C" int bdbnn_tc_supported(const bdbnn_conv_shape* s) {
   if (!tc_shape_ok(s)) return 0;
-  return BDBNN_TC_FWD | BDBNN_TC_DGRAD | (plan_wgrad(s).ok ? BDBNN_TC_WGRAD : 0);
+  return BDBNN_TC_FWD | BDBNN_TC_DGRAD | (plan_wgrad(s, 2).ok ? BDBNN_TC_WGRAD : 0);
 }
 
 extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, const float* alpha,
@@ -663,29 +692,77 @@ extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_
   if (rc) return rc;
   BDBNN_REQUIRE(xb_bf16 && wf_bf16 && alpha && y, "binconv_fwd_tc: NULL pointer");
   if (!tc_shape_ok(s)) { set_error("binconv_fwd_tc: shape not supported by the tcgen05 path"); return BDBNN_ERR_UNSUPPORTED; }
-  return launch_tc_conv<0>(xb_bf16, s->H, s->W, s->Cin, wf_bf16, s->Cout, s->kh, s->kw, s->pad, s->N,
-                           s->Ho, s->Wo, alpha, nullptr, y, cudaStream_t(stream));
+  TcConvLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.A = xb_bf16; L.IH = s->H; L.IW = s->W; L.Kc = s->Cin; L.a_halves = 1; L.in_step = s->stride;
+  L.B = wf_bf16; L.b_taps = s->kh * s->kw; L.Nout = s->Cout;
+  L.NIMG = s->N; L.OH = s->Ho; L.OW = s->Wo;
+  for (int r = 0; r < s->kh; ++r)
+    for (int q = 0; q < s->kw; ++q) {
+      const int t = r * s->kw + q;
+      L.dh[t] = int8_t(r - s->pad); L.dw[t] = int8_t(q - s->pad); L.tb[t] = uint8_t(t);
+    }
+  L.n_taps = s->kh * s->kw;
+  L.out_step = 1; L.OHf = s->Ho; L.OWf = s->Wo;
+  L.alpha = alpha; L.out = y;
+  return launch_tc_conv<0>(L, cudaStream_t(stream));
 }
 
-extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, const uint16_t* wt_bf16,
-                                      const uint32_t* mask_bits, float* gx, const bdbnn_conv_shape* s,
-                                      void* stream) {
+extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_halves,
+                                      const uint16_t* wt_bf16, const uint32_t* mask_bits, float* gx,
+                                      const bdbnn_conv_shape* s, void* stream) {
   int rc = validate_shape(s);
   if (rc) return rc;
   BDBNN_REQUIRE(gys_bf16 && wt_bf16 && mask_bits && gx, "binconv_dgrad_tc: NULL pointer");
+  BDBNN_REQUIRE(grad_halves == 1 || grad_halves == 2, "binconv_dgrad_tc: grad_halves must be 1 or 2");
   if (!tc_shape_ok(s)) { set_error("binconv_dgrad_tc: shape not supported by the tcgen05 path"); return BDBNN_ERR_UNSUPPORTED; }
-  // gx[h,w,c] = sum_{r',s',o} gys[h + r' - (kh-1-p), w + s' - (kw-1-p), o] * wt[c][(r',s')][o]
-  return launch_tc_conv<1>(gys_bf16, s->Ho, s->Wo, s->Cout, wt_bf16, s->Cin, s->kh, s->kw,
-                           s->kh - 1 - s->pad, s->N, s->H, s->W, nullptr, mask_bits, gx,
-                           cudaStream_t(stream));
+  cudaStream_t st = cudaStream_t(stream);
+  const int T = s->kh * s->kw, sd = s->stride;
+  // gx[h,w,c] = sum over taps (r,q) with (h+p-r) % sd == 0 (same in w) of
+  //             gys[(h+p-r)/sd, (w+p-q)/sd, o] * wt[c][T-1-t][o]; one launch per (h%sd, w%sd) phase.
+  TcConvLaunch Ls[4];
+  int n_launch = 0;
+  bool empty_phase = false;
+  for (int a = 0; a < sd; ++a)
+    for (int b = 0; b < sd; ++b) {
+      TcConvLaunch& L = Ls[n_launch];
+      memset(&L, 0, sizeof(L));
+      for (int r = 0; r < s->kh; ++r) {
+        const int nh = a + s->pad - r;
+        if (nh % sd != 0) continue;
+        for (int q = 0; q < s->kw; ++q) {
+          const int nw = b + s->pad - q;
+          if (nw % sd != 0) continue;
+          L.dh[L.n_taps] = int8_t(nh / sd); L.dw[L.n_taps] = int8_t(nw / sd);
+          L.tb[L.n_taps] = uint8_t(T - 1 - (r * s->kw + q));
+          ++L.n_taps;
+        }
+      }
+      L.OH = (s->H - a + sd - 1) / sd; L.OW = (s->W - b + sd - 1) / sd;
+      if (L.OH <= 0 || L.OW <= 0) continue;
+      if (L.n_taps == 0) { empty_phase = true; continue; }
+      L.A = gys_bf16; L.IH = s->Ho; L.IW = s->Wo; L.Kc = s->Cout; L.a_halves = grad_halves; L.in_step = 1;
+      L.B = wt_bf16; L.b_taps = T; L.Nout = s->Cin;
+      L.NIMG = s->N;
+      L.out_step = sd; L.off_h = a; L.off_w = b; L.OHf = s->H; L.OWf = s->W;
+      L.mask = mask_bits; L.out = gx;
+      ++n_launch;
+    }
+  if (empty_phase)
+    BDBNN_CUDA(cudaMemsetAsync(gx, 0, size_t(s->N) * s->H * s->W * s->Cin * sizeof(float), st));
+  for (int i = 0; i < n_launch; ++i) {
+    rc = launch_tc_conv<1>(Ls[i], st);
+    if (rc) return rc;
+  }
+  return BDBNN_OK;
 }
 
 extern "C" size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s) {
-  if (!s || !plan_wgrad(s).ok) return 0;
+  if (!s || !plan_wgrad(s, 2).ok) return 0;
   return size_t(s->kh) * s->kw * s->Cin * s->Cout * sizeof(float);
 }
 
-extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, const uint16_t* xb_bf16,
+extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_halves, const uint16_t* xb_bf16,
                                       const uint32_t* wmask_bits, const float* inv_gscale, float* gW,
                                       const bdbnn_conv_shape* s, void* workspace, size_t workspace_bytes,
                                       void* stream) {
@@ -693,7 +770,8 @@ extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, const uint16_t* 
   if (rc) return rc;
   BDBNN_REQUIRE(gys_bf16 && xb_bf16 && wmask_bits && inv_gscale && gW && workspace,
                 "binconv_wgrad_tc: NULL pointer");
-  WgradPlan pl = plan_wgrad(s);
+  BDBNN_REQUIRE(grad_halves == 1 || grad_halves == 2, "binconv_wgrad_tc: grad_halves must be 1 or 2");
+  WgradPlan pl = plan_wgrad(s, grad_halves);
   if (!pl.ok) { set_error("binconv_wgrad_tc: shape not supported by the tcgen05 path"); return BDBNN_ERR_UNSUPPORTED; }
   const size_t need = bdbnn_wgrad_tc_workspace_bytes(s);
   if (workspace_bytes < need) {
@@ -704,9 +782,9 @@ extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, const uint16_t* 
   pl.p.ws = static_cast<float*>(workspace);
   BDBNN_CUDA(cudaMemsetAsync(workspace, 0, need, st));
   CUtensorMap tmX, tmG;
-  rc = make_act_map(&tmX, xb_bf16, s->N, s->H, s->W, s->Cin, 64, pl.p.BW, pl.p.BH, pl.p.BNI);
+  rc = make_act_map(&tmX, xb_bf16, s->N, s->H, s->W, s->Cin, 64, pl.p.BW, pl.p.BH, pl.p.BNI, s->stride);
   if (rc) return rc;
-  rc = make_act_map(&tmG, gys_bf16, s->N, s->Ho, s->Wo, s->Cout, 64, pl.p.BW, pl.p.BH, pl.p.BNI);
+  rc = make_act_map(&tmG, gys_bf16, s->N, s->Ho, s->Wo, s->Cout * grad_halves, 64, pl.p.BW, pl.p.BH, pl.p.BNI);
   if (rc) return rc;
   BDBNN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
   dim3 grid(unsigned(pl.ksplit), unsigned(pl.mgroups), unsigned(pl.ntiles));

@@ -11,6 +11,14 @@ from . import _lib
 from ._lib import ConvShape
 
 _IMPL_ENV = "BDBNN_IMPL"          # auto | xnor | tc
+_GRAD_ENV = "BDBNN_GRAD_HALVES"   # 2 (default): gy as bf16 hi+lo pair (fp32-class accuracy); 1: single bf16
+
+
+def grad_halves():
+    h = int(os.environ.get(_GRAD_ENV, "2"))
+    if h not in (1, 2):
+        raise ValueError(f"{_GRAD_ENV} must be 1 or 2")
+    return h
 _VALID_IMPL = ("auto", "xnor", "tc")
 
 
@@ -64,8 +72,9 @@ def _shape_key(sh):
     return f"N{sh.N}_{sh.H}x{sh.W}_c{sh.Cin}-{sh.Cout}_k{sh.kh}s{sh.stride}"
 
 
-def algorithmic_bytes(kernel, sh):
-    """Per-launch algorithmic bytes of each kernel: compulsory HBM reads + writes."""
+def algorithmic_bytes(kernel, sh, gh=1):
+    """Per-launch algorithmic bytes of each kernel: compulsory HBM reads + writes.
+    gh = bf16 halves of the packed gradient (1 or 2)."""
     n_in = sh.N * sh.H * sh.W * sh.Cin
     n_out = sh.N * sh.Ho * sh.Wo * sh.Cout
     n_w = sh.Cout * sh.Cin * sh.kh * sh.kw
@@ -76,9 +85,9 @@ def algorithmic_bytes(kernel, sh):
         "fwd_tc": 2 * n_in + 2 * n_w + 4 * n_out,             # read bf16 +-1, write fp32 y
         "dgrad": 4 * n_out + n_w // 8 + n_in // 8 + 4 * n_in,  # read gy, bits; write gx
         "wgrad": 4 * n_out + n_in // 8 + n_w // 8 + 4 * n_w,
-        "grad_pack": 4 * n_out + 2 * n_out,
-        "dgrad_tc": 2 * n_out + 2 * n_w + n_in // 8 + 4 * n_in,
-        "wgrad_tc": 2 * n_out + 2 * n_in + n_w // 8 + 4 * n_w,
+        "grad_pack": 4 * n_out + 2 * gh * n_out,
+        "dgrad_tc": 2 * gh * n_out + 2 * n_w + n_in // 8 + 4 * n_in,
+        "wgrad_tc": 2 * gh * n_out + 2 * n_in + n_w // 8 + 4 * n_w,
     }[kernel]
 
 
@@ -199,17 +208,18 @@ class _BinConv2d(torch.autograd.Function):
         if ctx.use & 1:
             xb, wt, gscale, inv_gscale = saved[5:]
             n_pix_out = sh.N * sh.Ho * sh.Wo
-            gys = torch.empty((sh.N, sh.Ho, sh.Wo, sh.Cout), dtype=torch.bfloat16, device=dev)
-            with _timed("grad_pack", key, algorithmic_bytes("grad_pack", sh)):
-                _lib.check(L.bdbnn_grad_pack(_p(g), _p(gscale), n_pix_out, sh.Cout, _p(gys), st), "grad_pack")
+            gh = grad_halves()
+            gys = torch.empty((sh.N, sh.Ho, sh.Wo, gh * sh.Cout), dtype=torch.bfloat16, device=dev)
+            with _timed("grad_pack", key, algorithmic_bytes("grad_pack", sh, gh)):
+                _lib.check(L.bdbnn_grad_pack(_p(g), _p(gscale), n_pix_out, sh.Cout, gh, _p(gys), st), "grad_pack")
             _lib.count(1)
             if need_x and not (ctx.use & 2):
                 raise RuntimeError("bdbnn_b200: dgrad_tc unavailable for a shape fwd_tc accepted")
             if need_x:
                 gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev,
                                  memory_format=torch.channels_last)
-                with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh)):
-                    _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), _p(wt), _p(mask_bits), _p(gx),
+                with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh)):
+                    _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gh, _p(wt), _p(mask_bits), _p(gx),
                                                         ctypes.byref(sh), st), "binconv_dgrad_tc")
                 _lib.count(1)
             if need_w and not (ctx.use & 4):
@@ -223,8 +233,8 @@ class _BinConv2d(torch.autograd.Function):
                 gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
                 nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
                 ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
-                with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh)):
-                    _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
+                with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh, gh)):
+                    _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gh, _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
                                                         ctypes.byref(sh), _p(ws), nbytes, st),
                                "binconv_wgrad_tc")
                 _lib.count(2)

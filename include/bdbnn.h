@@ -109,17 +109,20 @@ BDBNN_API int bdbnn_binconv_wgrad(const float* gy, const uint32_t* sign_bits, co
                         float* gW, const bdbnn_conv_shape* s, void* stream);
 
 /* ---- backward on tensor cores (tcgen05, bf16 operands, fp32 accumulate) ------------------------
- * grad_pack: gys_bf16[p*Cout+o] = bf16_rn(gy[p*Cout+o] * gscale[o])   (shared by dgrad_tc/wgrad_tc)
+ * grad_pack: v = gy[p*Cout+o] * gscale[o];  halves==1: gys[p*Cout+o] = bf16_rn(v)
+ *            halves==2: gys[p*2Cout+o] = hi = bf16_rn(v), gys[p*2Cout+Cout+o] = bf16_rn(v - hi)
+ *            (hi+lo carries 16 mantissa bits: backward then matches fp32 to ~1e-5 of max|grad|)
  * dgrad_tc : gx = mask * conv_transpose(gys, wt_bf16)                  (sign-only weights, exact)
  * wgrad_tc : gW = wmask * inv_gscale[o] * sum_pix gys[pix,o]*xb[pix',c]
- * wgrad_tc needs a workspace of bdbnn_wgrad_tc_workspace_bytes(s) bytes (split-K partials). */
+ * wgrad_tc needs a workspace of bdbnn_wgrad_tc_workspace_bytes(s) bytes (split-K partials).
+ * grad_halves must be the value grad_pack was called with. */
 BDBNN_API int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_pix, int32_t Cout,
-                    uint16_t* gys_bf16, void* stream);
-BDBNN_API int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, const uint16_t* wt_bf16,
+                    int32_t halves, uint16_t* gys_bf16, void* stream);
+BDBNN_API int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_halves, const uint16_t* wt_bf16,
                            const uint32_t* mask_bits, float* gx, const bdbnn_conv_shape* s,
                            void* stream);
 BDBNN_API size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s);
-BDBNN_API int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, const uint16_t* xb_bf16,
+BDBNN_API int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_halves, const uint16_t* xb_bf16,
                            const uint32_t* wmask_bits, const float* inv_gscale, float* gW,
                            const bdbnn_conv_shape* s, void* workspace, size_t workspace_bytes,
                            void* stream);

@@ -64,7 +64,8 @@ def main():
         gs, igs = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
         y = torch.empty((n, sh.Ho, sh.Wo, cout), device="cuda")
         gy = torch.randn_like(y)
-        gys = torch.empty(y.shape, dtype=torch.bfloat16, device="cuda")
+        GH = int(os.environ.get("BDBNN_GRAD_HALVES", "2"))
+        gys = torch.empty(y.shape[:3] + (GH * cout,), dtype=torch.bfloat16, device="cuda")
         gx = torch.empty_like(x)
         gw = torch.empty_like(w)
         st = _stream()
@@ -81,11 +82,11 @@ def main():
             wsb = torch.empty(max(nb, 4) // 4, device="cuda")
             kernels.update({
                 "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), shp, st), "f"),
-                "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, _p(gys), st), "g"),
-                "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), _p(wt), _p(mb), _p(gx), shp, st), "d"),
+                "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, GH, _p(gys), st), "g"),
+                "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), GH, _p(wt), _p(mb), _p(gx), shp, st), "d"),
             })
             if caps & 4:
-                kernels["wgrad_tc"] = lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w")
+                kernels["wgrad_tc"] = lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), GH, _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w")
             else:
                 kernels["wgrad"] = lambda: ck(L.bdbnn_binconv_wgrad(_p(gy), _p(sb), _p(wm), _p(gw), shp, st), "w")
         else:
@@ -98,7 +99,7 @@ def main():
             fn()
             torch.cuda.synchronize()
             ms = timeit(fn, flush, iters=3 if kname in ("dgrad", "wgrad") else 7)
-            nbytes = algorithmic_bytes(kname, sh) if kname != "weight_pack" else 4 * w.numel()
+            nbytes = algorithmic_bytes(kname, sh, GH) if kname != "weight_pack" else 4 * w.numel()
             gbs = nbytes / 1e9 / (ms / 1e3)
             macs = 2.0 * n * sh.Ho * sh.Wo * cout * cin * 9
             rows.append({"layer": name, "kernel": kname, "ms": round(ms, 4), "alg_MB": round(nbytes / 1e6, 2),

@@ -54,4 +54,4 @@ def test_resnet20_step_matches_cpu_oracle(ts):
     for n in gr:
         scale = gr[n].abs().max().item() + 1e-12
         err = (gg[n] - gr[n]).abs().max().item()
-        assert err <= 2e-3 * scale, (n, err, scale)
+        assert err <= 2e-3 * scale, (n, err, scale)   # fp32 sums in different order + a few sign flips near 0
