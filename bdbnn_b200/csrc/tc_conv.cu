@@ -15,6 +15,7 @@
 //                   apply alpha / STE mask, store fp32 NHWC rows (each thread writes whole 64-byte runs).
 // +-1 operands and fp32 accumulation make the forward integer-exact (|sum| <= 9*512 < 2^24).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -120,6 +121,9 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >>4
 // in [0,14), LBO>>4 in [16,30), SBO>>4 in [32,46), version=1 in [46,48), layout type in [61,64).
 // For swizzled K-major tiles LBO is unused; SBO = bytes between 8-row groups = 8 * row_bytes.
+// NOTE (measured on B200): a start address that is a whole number of 128-byte rows into a
+// 1024B-aligned SWIZZLE_128B tile needs base_offset = 0 — the hardware applies the swizzle XOR to the
+// absolute shared-memory address bits, so row-shifted views of one TMA-written tile are valid operands.
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
   const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);  // SW128 / SW64 / SW32
   uint64_t d = 0;
@@ -153,6 +157,9 @@ struct TcConvParams {
   uint8_t tap_b[kMaxTaps];   // K-block row of B for tap i (B column = tap_b * Kc + k)
   int32_t out_step, out_off_h, out_off_w, OHf, OWf;  // out pixel = (oh*out_step+off_h, ow*out_step+off_w) in OHf x OWf
   int32_t Nout, BN;          // GEMM N total / per CTA
+  // halo mode: ONE activation patch [PH][PW][64ch] per K block serves all taps; tap (dh,dw) is the same
+  // swizzled patch read from row offset (dh-dh_min)*PW + (dw-dw_min) (descriptor start + 128*shift)
+  int32_t halo, PW, PH, dh_min, dw_min, patch_bytes;
   int32_t stages;
   int32_t row_bytes;         // KB * 2 = swizzle span (32/64/128)
   const float* alpha;        // MODE 0: per-output-channel scale
@@ -168,11 +175,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t pfull_bar[2], pempty_bar[2];   // halo patch ring
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = kTileM * p.row_bytes;          // ring slot: A tile then B tile
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t tiles_base = smem_base + (p.halo ? 2u * uint32_t(p.patch_bytes) : 0u);
+  const uint32_t a_bytes = p.halo ? 0u : kTileM * p.row_bytes;   // ring slot: [A tile] then B tile
   const uint32_t b_bytes = p.BN * p.row_bytes;
   const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
   const uint32_t tmem_cols = p.BN < 32 ? 32u : uint32_t(p.BN);   // power of two >= 32
@@ -189,6 +198,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(&accum_bar), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&pfull_bar[s]), 1);
+      mbar_init(smem_u32(&pempty_bar[s]), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 4 && lane == 0) {
@@ -201,7 +214,56 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp == 4) {
+  if (p.halo) {
+    if (warp == 4) {
+      if (lane == 0) {
+        int it = 0;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          const int pa = kb & 1;
+          mbar_wait(smem_u32(&pempty_bar[pa]), (uint32_t(kb >> 1) & 1u) ^ 1u);
+          const uint32_t pb = smem_u32(&pfull_bar[pa]);
+          mbar_expect_tx(pb, uint32_t(p.PW * p.PH) * 128u);
+          tma_load_4d(smem_base + pa * p.patch_bytes, &tmA, pb, kb * p.KB, p.dw_min, h0 + p.dh_min, n0);
+          const int kbb = kb >= p.n_kb ? kb - p.n_kb : kb;
+          for (int ti = 0; ti < p.n_taps; ++ti, ++it) {
+            const int stage = it % p.stages;
+            const uint32_t phase = uint32_t(it / p.stages) & 1u;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, uint32_t(p.BN) * 128u);
+            tma_load_2d(tiles_base + stage * stage_bytes, &tmB, fb, p.tap_b[ti] * p.Kc + kbb * p.KB, nn0);
+          }
+        }
+      }
+    } else if (warp == 5) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN));
+        int it = 0;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          const int pa = kb & 1;
+          mbar_wait(smem_u32(&pfull_bar[pa]), uint32_t(kb >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t patch = smem_base + pa * p.patch_bytes;
+          for (int ti = 0; ti < p.n_taps; ++ti, ++it) {
+            const int stage = it % p.stages;
+            const uint32_t phase = uint32_t(it / p.stages) & 1u;
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t shift = uint32_t((p.tap_dh[ti] - p.dh_min) * p.PW + (p.tap_dw[ti] - p.dw_min));
+            const uint32_t b_src = tiles_base + stage * stage_bytes;
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_kmajor_desc(patch + shift * 128u + k * 32, 128);
+              const uint64_t bd = make_kmajor_desc(b_src + k * 32, 128);
+              umma_bf16(tmem_d, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&empty_bar[stage]));
+          }
+          umma_commit(smem_u32(&pempty_bar[pa]));
+        }
+        umma_commit(smem_u32(&accum_bar));
+      }
+    }
+  } else if (warp == 4) {
     if (lane == 0) {
       const uint32_t tx = uint32_t(p.BNI * p.BH * p.BW + p.BN) * uint32_t(p.row_bytes);
       int it = 0;
@@ -239,12 +301,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       umma_commit(smem_u32(&accum_bar));
     }
-  } else {
+  }
+  if (warp < 4) {
     // ---- epilogue: warp w <-> TMEM lanes [32w, 32w+32) <-> tile rows ----
     const int m = warp * 32 + lane;
-    const int wi = m % p.BW;
-    const int q = m / p.BW;
-    const int hi = q % p.BH, ni = q / p.BH;
+    const int rw = p.halo ? p.PW : p.BW;               // halo tiles live in padded-width pixel space
+    const int wi = m % rw;
+    const int q = m / rw;
+    const int hi = q % p.BH, ni = (p.halo && wi >= p.BW) ? p.BNI : q / p.BH;
     const int oh = (h0 + hi) * p.out_step + p.out_off_h, ow = wi * p.out_step + p.out_off_w;
     const bool valid = (ni < p.BNI) && (h0 + hi < p.OH) && (n0 + ni < p.NIMG) && oh < p.OHf && ow < p.OWf;
     const int64_t pix = (int64_t(n0 + ni) * p.OHf + oh) * p.OWf + ow;
@@ -396,23 +460,48 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   p.Nout = L.Nout;
   p.BN = pick_bn(L.Nout);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
-  const uint32_t stage_bytes = (uint32_t(kTileM + p.BN) * p.row_bytes + 1023u) & ~1023u;
+  // Halo mode (stride-1 launches with >128-pixel images and 64-channel K blocks): see TcConvParams.
+  static const int halo_env = [] { const char* e = getenv("BDBNN_TC_HALO"); return e ? atoi(e) : 1; }();
+  if (halo_env > 0 && L.in_step == 1 && p.KB == 64 && L.OH * L.OW > kTileM && p.n_taps > 0) {
+    int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
+    for (int i = 0; i < p.n_taps; ++i) {
+      dh0 = min(dh0, int(p.tap_dh[i])); dh1 = max(dh1, int(p.tap_dh[i]));
+      dw0 = min(dw0, int(p.tap_dw[i])); dw1 = max(dw1, int(p.tap_dw[i]));
+    }
+    const int PW = L.OW + (dw1 - dw0);
+    if (PW <= kTileM) {
+      p.halo = 1;
+      p.PW = PW; p.dh_min = dh0; p.dw_min = dw0;
+      p.BNI = 1;
+      p.BH = kTileM / PW;
+      p.PH = p.BH + (dh1 - dh0);
+      p.tiles_h = (L.OH + p.BH - 1) / p.BH;
+      const int rows = kTileM + (dh1 - dh0) * PW + (dw1 - dw0);
+      p.patch_bytes = int((uint32_t(rows) * 128u + 1023u) & ~1023u);
+    }
+  }
+  const int tiles_n_eff = (L.NIMG + p.BNI - 1) / p.BNI;
+  const uint32_t stage_bytes = p.halo ? ((uint32_t(p.BN) * 128u + 1023u) & ~1023u)
+                                      : ((uint32_t(kTileM + p.BN) * p.row_bytes + 1023u) & ~1023u);
   const int n_iters = p.n_taps * p.n_kb * p.a_halves;
-  int stages = int((96u * 1024u) / stage_bytes);
+  const uint32_t ring_budget = 96u * 1024u - (p.halo ? 2u * uint32_t(p.patch_bytes) : 0u);
+  int stages = int(ring_budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > n_iters) stages = n_iters;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = size_t(stages) * stage_bytes + 1024;
+  const size_t smem = size_t(stages) * stage_bytes + (p.halo ? 2u * size_t(p.patch_bytes) : 0u) + 1024;
 
   CUtensorMap tmA, tmB;
-  int rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, p.KB, p.BW, p.BH, p.BNI, L.in_step);
+  int rc = p.halo ? make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.PW, p.PH, 1, 1)
+                  : make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, p.KB, p.BW, p.BH, p.BNI,
+                                 L.in_step);
   if (rc) return rc;
   rc = make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, p.KB, p.BN);
   if (rc) return rc;
   auto kern = tc_conv_kernel<MODE>;
   BDBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  dim3 grid(unsigned(p.tiles_h * tiles_n), unsigned(L.Nout / p.BN));
+  dim3 grid(unsigned(p.tiles_h * tiles_n_eff), unsigned(L.Nout / p.BN));
   kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   return check_launch("tc_conv_kernel");
 }
