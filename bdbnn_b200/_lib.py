@@ -28,6 +28,7 @@ SIGNATURES = {
     "bdbnn_version": (c_int, []),
     "bdbnn_last_error_string": (ctypes.c_char_p, []),
     "bdbnn_tc_supported": (c_int, [_SH]),
+    "bdbnn_debug_trace": (c_int, [_P]),
     "bdbnn_act_pack": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P]),
     "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bdbnn_binconv_fwd_xnor": (c_int, [_P, _P, _P, _P, _SH, _P]),

@@ -1,0 +1,265 @@
+// Shared tcgen05 / TMA / mbarrier PTX wrappers and tensor-map helpers (sm_100a).
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace bdbnn {
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+      "%13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >>4
+// in [0,14), LBO>>4 in [16,30), SBO>>4 in [32,46), version=1 in [46,48), layout type in [61,64).
+// For swizzled K-major tiles LBO is unused; SBO = bytes between 8-row groups = 8 * row_bytes.
+// NOTE (measured on B200): a start address that is a whole number of 128-byte rows into a
+// 1024B-aligned SWIZZLE_128B tile needs base_offset = 0 — the hardware applies the swizzle XOR to the
+// absolute shared-memory address bits, so row-shifted views of one TMA-written tile are valid operands.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);  // SW128 / SW64 / SW32
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFFu) >> 4);
+  d |= uint64_t(1) << 16;                          // LBO (ignored for swizzled K-major)
+  d |= uint64_t((8u * row_bytes) >> 4) << 32;      // SBO
+  d |= uint64_t(1) << 46;                          // descriptor version (Blackwell)
+  d |= uint64_t(layout) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// K-major A and B (0) @15/@16, N>>3 @17, M>>4 @24.
+__host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;
+constexpr int kMaxTaps = 49;
+
+// Four K=16 steps of one 64-element (128-byte, SWIZZLE_128B K-major) K block in a single asm block:
+// the MMA-issuing thread is a lone scalar thread, so per-MMA instruction count is what bounds the
+// issue rate (a generic descriptor rebuild per MMA costs ~80 clk, more than a 128x64x16 MMA takes).
+// a_lo/b_lo are the low descriptor words (address>>4 | LBO), desc_hi the shared high word.
+__device__ __forceinline__ void umma_bf16_k4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "add.u32 al, %1, 2;\n\t"
+      "add.u32 bl, %2, 2;\n\t"
+      "mov.b64 da, {al, %3};\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, q;\n\t"
+      "add.u32 al, %1, 4;\n\t"
+      "add.u32 bl, %2, 4;\n\t"
+      "mov.b64 da, {al, %3};\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, q;\n\t"
+      "add.u32 al, %1, 6;\n\t"
+      "add.u32 bl, %2, 6;\n\t"
+      "mov.b64 da, {al, %3};\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, q;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+// Low / high words of a SWIZZLE_128B K-major descriptor (see make_kmajor_desc).
+__device__ __forceinline__ uint32_t kmajor128_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t kmajor128_hi() { return (1024u >> 4) | (1u << 14) | (2u << 29); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side: tensor-map construction and launch
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+inline CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// bf16 NHWC activation tensor [N][H][W][C] -> 4-D map, box [BNI][BH][BW][KB].
+inline int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int KB, int BW,
+                        int BH, int BNI, int step = 1) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return BDBNN_ERR_CUDA; }
+  cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
+  cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+  // element stride `step` in w/h: TMA loads ceil(box/step) elements, so box = loaded * step
+  cuuint32_t box[4] = {cuuint32_t(KB), cuuint32_t(BW * step), cuuint32_t(BH * step), cuuint32_t(BNI)};
+  cuuint32_t estr[4] = {1, cuuint32_t(step), cuuint32_t(step), 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KB * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act) failed: %d", int(r)); return BDBNN_ERR_CUDA; }
+  return BDBNN_OK;
+}
+
+// bf16 K-major weight matrix [rows][cols] -> 2-D map, box [BN rows][KB cols].
+inline int make_weight_map(CUtensorMap* map, const void* base, int rows, int cols, int KB, int BN) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return BDBNN_ERR_CUDA; }
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(cols) * 2};
+  cuuint32_t box[2] = {cuuint32_t(KB), cuuint32_t(BN)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KB * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight) failed: %d", int(r)); return BDBNN_ERR_CUDA; }
+  return BDBNN_OK;
+}
+
+
+// One implicit-GEMM launch: D[NIMG x OH x OW pixels, Nout] = sum_taps A[pixel*in_step + tap offset] * B.
+struct TcConvLaunch {
+  const uint16_t* A; int IH, IW, Kc, a_halves, in_step;
+  const uint16_t* B; int b_taps, Nout;
+  int NIMG, OH, OW;
+  int n_taps; int8_t dh[kMaxTaps], dw[kMaxTaps]; uint8_t tb[kMaxTaps];
+  int out_step, off_h, off_w, OHf, OWf;
+  const float* alpha; const uint32_t* mask; float* out;
+};
+
+// Persistent multi-accumulator kernel (tc_conv2.cu). Returns BDBNN_ERR_UNSUPPORTED if the geometry
+// does not qualify (caller falls back to the one-tile-per-CTA kernel in tc_conv.cu).
+int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st);
+void set_tc_trace(long long* buf);
+
+}  // namespace bdbnn

@@ -1,0 +1,428 @@
+// Persistent, warp-specialised tcgen05 implicit-GEMM conv (forward and dgrad), version 2.
+//
+// Why (measured on B200, profiles/r1_*): the one-tile-per-CTA kernel in tc_conv.cu is bound by
+// L2->SM traffic and per-CTA latency, not by HBM or the tensor pipe: every 128-pixel tile re-reads
+// the whole [BN x 9*C] weight slab and nine shifted activation boxes from L2 (1.0-1.4 GB per layer).
+// Here one CTA per SM stays resident and each work item is a SUPER TILE of up to four 128-row M tiles
+// (four TMEM accumulators) that
+//   * share every weight stage  -> weight traffic / 4
+//   * (halo mode) share ONE activation patch per 64-channel K block: the patch holds the super
+//     tile's pixels in padded-width raster order plus the halo rows; tap (dh,dw) of M tile j is the
+//     same swizzled patch viewed from row j*128 + (dh-dh_min)*PW + (dw-dw_min) — the UMMA descriptor
+//     start address simply moves by whole 128-byte rows (absolute-address swizzle, base_offset 0).
+//     Activation traffic drops from 9 boxes per tile to ~1.2 patches per 4 tiles.
+//   * overlap roles across work items: warp 4 = TMA producer, warp 5 = MMA issuer, warps 0-3 =
+//     epilogue; with BN <= 64 the eight accumulators form two buffers so the epilogue of item i
+//     overlaps the MMAs of item i+1.
+// Non-halo mode (small images, stride-2 forward) keeps per-tap boxes but still shares weight stages.
+#include "tc_common.cuh"
+
+namespace bdbnn {
+
+constexpr int kTS = 4;  // M tiles (accumulators) per super tile
+
+struct TcConv2Params {
+  int32_t OW, OH, NIMG;
+  int32_t halo;
+  // non-halo tile box: BNI images x BH rows x BW(=OW) cols per M tile
+  int32_t BW, BH, BNI, tiles_h, n_mtiles;
+  // halo geometry: super tile = HBNI image blocks of IB padded rows (IB = (rows + dh_span) * PW when
+  // HBNI > 1) or SH image rows of one image; patch box = [HBNI][PH][PW][64]
+  int32_t PW, PH, SH, IB, HBNI, dh_min, dw_min, supers_per_img;
+  uint32_t patch_bytes;
+  int32_t n_supers, n_ntiles;
+  int32_t Kc, n_kb, a_halves, in_step;
+  int32_t n_taps;
+  int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
+  uint8_t tap_b[kMaxTaps];
+  int32_t out_step, out_off_h, out_off_w, OHf, OWf;
+  int32_t Nout, BN, NB;
+  int32_t stages;
+  int32_t dbg;               // BDBNN_TC_DBG experiment bits: 1 = no global stores, 2 = no TMEM loads, 4 = no MMAs
+  uint32_t stage_bytes, b_bytes;
+  const float* alpha;
+  const uint32_t* mask;
+  float* out;
+  long long* trace;          // optional clock64 trace of CTA 0 (bdbnn_debug_trace), else NULL
+};
+
+// role r (0 producer, 1 mma, 2 epilogue) appends (event id, clock) pairs to its 2048-entry lane.
+#define BDBNN_TR(r, ev)                                                           \
+  do {                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0 && tr_n < 1023) {                   \
+      p.trace[(r) * 2048 + 2 * tr_n] = (ev);                                      \
+      p.trace[(r) * 2048 + 2 * tr_n + 1] = clock64();                             \
+      ++tr_n;                                                                     \
+    }                                                                             \
+  } while (0)
+
+struct SuperGeom {
+  int n0, h0, ntl;  // first image, first output row, M tiles in use
+};
+
+__device__ __forceinline__ SuperGeom super_geom(const TcConv2Params& p, int sup) {
+  SuperGeom g;
+  if (p.halo) {
+    if (p.HBNI > 1 || p.supers_per_img == 1) {
+      g.n0 = sup * p.HBNI;
+      g.h0 = 0;
+      const int imgs = min(p.HBNI, p.NIMG - g.n0);
+      g.ntl = (imgs * p.IB + kTileM - 1) / kTileM;
+    } else {
+      g.n0 = sup / p.supers_per_img;
+      g.h0 = (sup - g.n0 * p.supers_per_img) * p.SH;
+      const int rows = min(p.SH, p.OH - g.h0);
+      g.ntl = (rows * p.PW + kTileM - 1) / kTileM;
+    }
+  } else {
+    const int t0 = sup * kTS;
+    g.n0 = 0; g.h0 = 0;
+    g.ntl = min(kTS, p.n_mtiles - t0);
+  }
+  if (g.ntl > kTS) g.ntl = kTS;
+  return g;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const TcConv2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t pfull_bar[2], pempty_bar[2];
+  __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t tap_shift_rows[kMaxTaps];   // halo: row offset of tap i inside the patch
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < p.n_taps)
+    tap_shift_rows[threadIdx.x] = uint32_t((p.tap_dh[threadIdx.x] - p.dh_min) * p.PW +
+                                           (p.tap_dw[threadIdx.x] - p.dw_min));
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring_base = smem_base + (p.halo ? 2u * p.patch_bytes : 0u);
+  const int kb_total = p.n_kb * p.a_halves;
+  const int n_work = p.n_supers * p.n_ntiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&pfull_bar[s]), 1);
+      mbar_init(smem_u32(&pempty_bar[s]), 1);
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 5) tmem_alloc(smem_u32(&tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 4) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t it = 0, pcount = 0;
+      int tr_n = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int sup = w / p.n_ntiles, nt = w - sup * p.n_ntiles;
+        const SuperGeom g = super_geom(p, sup);
+        const int nn0 = nt * p.BN;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          const int kbb = kb >= p.n_kb ? kb - p.n_kb : kb;
+          if (p.halo) {
+            const uint32_t pa = pcount & 1u;
+            BDBNN_TR(0, 0);
+            mbar_wait(smem_u32(&pempty_bar[pa]), ((pcount >> 1) & 1u) ^ 1u);
+            BDBNN_TR(0, 1);
+            const uint32_t pb = smem_u32(&pfull_bar[pa]);
+            mbar_expect_tx(pb, uint32_t(p.PW * p.PH * p.HBNI) * 128u);
+            tma_load_4d(smem_base + pa * p.patch_bytes, &tmA, pb, kb * 64, p.dw_min, g.h0 + p.dh_min, g.n0);
+            ++pcount;
+          }
+          for (int ti = 0; ti < p.n_taps; ++ti, ++it) {
+            const uint32_t stage = it % uint32_t(p.stages);
+            const uint32_t phase = (it / uint32_t(p.stages)) & 1u;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            const uint32_t dst = ring_base + stage * p.stage_bytes;
+            if (p.halo) {
+              mbar_expect_tx(fb, p.b_bytes);
+            } else {
+              mbar_expect_tx(fb, p.b_bytes + uint32_t(g.ntl * p.BNI * p.BH * p.BW) * 128u);
+              for (int j = 0; j < g.ntl; ++j) {
+                const int t = sup * kTS + j;
+                const int tile_n = t / p.tiles_h, tile_h = t - tile_n * p.tiles_h;
+                tma_load_4d(dst + p.b_bytes + uint32_t(j) * (kTileM * 128u), &tmA, fb, kb * 64, p.tap_dw[ti],
+                            tile_h * p.BH * p.in_step + p.tap_dh[ti], tile_n * p.BNI);
+              }
+            }
+            tma_load_2d(dst, &tmB, fb, p.tap_b[ti] * p.Kc + kbb * 64, nn0);
+          }
+          BDBNN_TR(0, 2);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN));
+      const uint32_t desc_hi = kmajor128_hi();
+      uint32_t it = 0, pcount = 0, wcount = 0;
+      int tr_n = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wcount) {
+        const int sup = w / p.n_ntiles;
+        const SuperGeom g = super_geom(p, sup);
+        const uint32_t buf = wcount % uint32_t(p.NB);
+        BDBNN_TR(1, 0);
+        mbar_wait(smem_u32(&tempty_bar[buf]), ((wcount / uint32_t(p.NB)) & 1u) ^ 1u);
+        tc_fence_after();
+        BDBNN_TR(1, 1);
+        const uint32_t acc0 = tmem_d + buf * uint32_t(kTS * p.BN);
+        bool first = true;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          uint32_t patch = 0, pa = 0;
+          if (p.halo) {
+            pa = pcount & 1u;
+            mbar_wait(smem_u32(&pfull_bar[pa]), (pcount >> 1) & 1u);
+            tc_fence_after();
+            patch = smem_base + pa * p.patch_bytes;
+            ++pcount;
+            BDBNN_TR(1, 2);
+          }
+          for (int ti = 0; ti < p.n_taps; ++ti, ++it) {
+            const uint32_t stage = it % uint32_t(p.stages);
+            const uint32_t phase = (it / uint32_t(p.stages)) & 1u;
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            if (ti == 0) BDBNN_TR(1, 3);
+            const uint32_t b_src = ring_base + stage * p.stage_bytes;
+            const uint32_t b_lo = kmajor128_lo(b_src);
+            // low descriptor word advances by 8 per 128-byte row: 1024 per M tile
+            uint32_t a_lo = p.halo ? kmajor128_lo(patch) + tap_shift_rows[ti] * 8u
+                                   : kmajor128_lo(b_src + p.b_bytes);
+            uint32_t acc = acc0;
+            if (!(p.dbg & 4))
+              for (int j = 0; j < g.ntl; ++j, a_lo += kTileM * 8u, acc += uint32_t(p.BN))
+                umma_bf16_k4(acc, a_lo, b_lo, desc_hi, idesc, first ? 0u : 1u);
+            first = false;
+            umma_commit(smem_u32(&empty_bar[stage]));
+          }
+          if (p.halo) umma_commit(smem_u32(&pempty_bar[pa]));
+        }
+        umma_commit(smem_u32(&tfull_bar[buf]));
+        BDBNN_TR(1, 4);
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 0..3) ================================
+    const int mask_words = (p.Nout + 31) >> 5;
+    uint32_t wcount = 0;
+    int tr_n = (threadIdx.x == 0) ? 0 : 100000;
+    // 4 KB per-warp staging tile behind the TMA ring (generic-proxy only, never touched by TMA/UMMA)
+    uint8_t* stage_warp = smem_raw + (ring_base - smem_u32(smem_raw)) + size_t(p.stages) * p.stage_bytes +
+                          size_t(warp) * 4096;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wcount) {
+      const int sup = w / p.n_ntiles, nt = w - sup * p.n_ntiles;
+      const SuperGeom g = super_geom(p, sup);
+      const int nn0 = nt * p.BN;
+      const uint32_t buf = wcount % uint32_t(p.NB);
+      BDBNN_TR(2, 0);
+      mbar_wait(smem_u32(&tfull_bar[buf]), (wcount / uint32_t(p.NB)) & 1u);
+      tc_fence_after();
+      BDBNN_TR(2, 1);
+      for (int j = 0; j < g.ntl; ++j) {
+        const int m = j * kTileM + warp * 32 + lane;
+        int ni, hi, wi;
+        bool valid;
+        if (p.halo) {
+          const int blk = (p.HBNI > 1 || p.supers_per_img == 1) ? m / p.IB : 0;
+          const int rem = m - blk * p.IB;
+          hi = rem / p.PW;
+          wi = rem - hi * p.PW;
+          ni = g.n0 + blk;
+          hi += g.h0;
+          valid = wi < p.OW && hi < p.OH && ni < p.NIMG && blk < p.HBNI &&
+                  (p.HBNI > 1 || p.supers_per_img == 1 || hi < g.h0 + p.SH);
+        } else {
+          const int t = sup * kTS + j;
+          const int tile_n = t / p.tiles_h, tile_h = t - tile_n * p.tiles_h;
+          const int r = warp * 32 + lane;
+          wi = r % p.BW;
+          const int q = r / p.BW;
+          hi = tile_h * p.BH + q % p.BH;
+          const int nl = q / p.BH;
+          ni = tile_n * p.BNI + nl;
+          valid = nl < p.BNI && hi < p.OH && ni < p.NIMG;
+        }
+        const int oh = hi * p.out_step + p.out_off_h, ow = wi * p.out_step + p.out_off_w;
+        valid = valid && oh < p.OHf && ow < p.OWf;
+        const int64_t pix = (int64_t(ni) * p.OHf + oh) * p.OWf + ow;
+        const uint32_t tbase = tmem_d + (uint32_t(warp * 32) << 16) + buf * uint32_t(kTS * p.BN) + uint32_t(j * p.BN);
+        if (p.dbg & 1) valid = false;
+        if (p.dbg & 2) continue;
+        // Row offsets/validity of this warp's 32 rows are exchanged by shuffle in the store phase.
+        const int64_t row_off = valid ? pix * p.Nout + nn0 : int64_t(-1);
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tbase + uint32_t(c0), v);
+          uint32_t word = 0;
+          if (MODE == 1 && valid) word = __ldg(p.mask + pix * mask_words + ((nn0 + c0) >> 5));
+          tmem_ld_wait();
+          // (1) scale/mask and park the 32x32 fp32 block in this warp's swizzled staging tile:
+          //     row r = lane, 16-byte chunk c at r*128 + ((c ^ (r&7)) * 16)  (4 wavefronts per STS.128)
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int q = c * 4;
+            float4 o;
+            if (MODE == 0) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.alpha + nn0 + c0 + q));
+              o = make_float4(__uint_as_float(v[q]) * a.x, __uint_as_float(v[q + 1]) * a.y,
+                              __uint_as_float(v[q + 2]) * a.z, __uint_as_float(v[q + 3]) * a.w);
+            } else {
+              o = make_float4(((word >> q) & 1u) ? __uint_as_float(v[q]) : 0.0f,
+                              ((word >> (q + 1)) & 1u) ? __uint_as_float(v[q + 1]) : 0.0f,
+                              ((word >> (q + 2)) & 1u) ? __uint_as_float(v[q + 2]) : 0.0f,
+                              ((word >> (q + 3)) & 1u) ? __uint_as_float(v[q + 3]) : 0.0f);
+            }
+            *reinterpret_cast<float4*>(stage_warp + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
+          }
+          __syncwarp();
+          // (2) read back transposed: one instruction stores 4 complete 128-byte rows (8 lanes per row)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3), c = lane & 7;
+            const int64_t off = __shfl_sync(0xffffffffu, row_off, r);
+            const float4 o = *reinterpret_cast<const float4*>(stage_warp + r * 128 + ((c ^ (r & 7)) << 4));
+            if (off >= 0) *reinterpret_cast<float4*>(p.out + off + c0 + c * 4) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      BDBNN_TR(2, 2);
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_d, 512);
+  }
+}
+
+static long long* g_trace = nullptr;
+void set_tc_trace(long long* buf) { g_trace = buf; }
+
+// mode: 0 = alpha epilogue (forward), 1 = STE-mask epilogue (dgrad)
+int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
+  if (L.Kc % 64 != 0 || L.n_taps <= 0) return BDBNN_ERR_UNSUPPORTED;
+  if (L.Nout != 64 && L.Nout % 128 != 0) return BDBNN_ERR_UNSUPPORTED;
+  TcConv2Params p;
+  memset(&p, 0, sizeof(p));
+  p.OW = L.OW; p.OH = L.OH; p.NIMG = L.NIMG;
+  p.Kc = L.Kc; p.n_kb = L.Kc / 64; p.a_halves = L.a_halves; p.in_step = L.in_step;
+  p.n_taps = L.n_taps;
+  memcpy(p.tap_dh, L.dh, sizeof(p.tap_dh));
+  memcpy(p.tap_dw, L.dw, sizeof(p.tap_dw));
+  memcpy(p.tap_b, L.tb, sizeof(p.tap_b));
+  p.out_step = L.out_step; p.out_off_h = L.off_h; p.out_off_w = L.off_w; p.OHf = L.OHf; p.OWf = L.OWf;
+  p.Nout = L.Nout;
+  p.BN = L.Nout >= 128 ? 128 : 64;
+  p.n_ntiles = L.Nout / p.BN;
+  p.NB = p.BN == 64 ? 2 : 1;
+  p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
+  p.b_bytes = uint32_t(p.BN) * 128u;
+
+  int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
+  for (int i = 0; i < p.n_taps; ++i) {
+    dh0 = min(dh0, int(p.tap_dh[i])); dh1 = max(dh1, int(p.tap_dh[i]));
+    dw0 = min(dw0, int(p.tap_dw[i])); dw1 = max(dw1, int(p.tap_dw[i]));
+  }
+  const int dh_span = dh1 - dh0, dw_span = dw1 - dw0;
+  const int PW = L.OW + dw_span;
+  const int super_rows = kTS * kTileM;  // 512 padded rows
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (L.in_step == 1 && L.OH * L.OW > kTileM && PW <= 256 && PW * (1 + dh_span) <= super_rows) {
+    p.halo = 1;
+    p.PW = PW; p.dh_min = dh0; p.dw_min = dw0;
+    const int img_block = (L.OH + dh_span) * PW;      // whole image incl. halo rows, padded raster
+    if (img_block <= super_rows) {
+      p.HBNI = super_rows / img_block;
+      if (p.HBNI > L.NIMG) p.HBNI = L.NIMG;
+      if (p.HBNI > 256) p.HBNI = 256;
+      p.IB = img_block; p.SH = L.OH; p.PH = L.OH + dh_span; p.supers_per_img = 1;
+      p.n_supers = (L.NIMG + p.HBNI - 1) / p.HBNI;
+    } else {
+      p.HBNI = 1;
+      p.SH = super_rows / PW;
+      if (p.SH > 256 - dh_span) p.SH = 256 - dh_span;
+      p.PH = p.SH + dh_span;
+      p.IB = super_rows;                               // single block: m / IB == 0 for every row
+      p.supers_per_img = (L.OH + p.SH - 1) / p.SH;
+      if (p.supers_per_img == 1) { p.IB = p.PH * PW > super_rows ? p.PH * PW : super_rows; }
+      p.n_supers = L.NIMG * p.supers_per_img;
+    }
+    const uint32_t rows = uint32_t(super_rows + dh_span * PW + dw_span);
+    p.patch_bytes = (rows * 128u + 1023u) & ~1023u;
+    if (uint32_t(p.PW * p.PH * p.HBNI) * 128u > p.patch_bytes) return BDBNN_ERR_UNSUPPORTED;
+    p.stage_bytes = (p.b_bytes + 1023u) & ~1023u;
+    rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.PW, p.PH, p.HBNI, 1);
+  } else {
+    p.halo = 0;
+    p.BW = L.OW;
+    if (L.OW > kTileM) return BDBNN_ERR_UNSUPPORTED;
+    if (L.OH * L.OW <= kTileM) {
+      p.BH = L.OH;
+      p.BNI = kTileM / (L.OH * L.OW);
+      if (p.BNI > L.NIMG) p.BNI = L.NIMG;
+      if (p.BNI > 256) p.BNI = 256;
+    } else {
+      p.BH = kTileM / L.OW;
+      p.BNI = 1;
+    }
+    p.tiles_h = (L.OH + p.BH - 1) / p.BH;
+    p.n_mtiles = p.tiles_h * ((L.NIMG + p.BNI - 1) / p.BNI);
+    p.n_supers = (p.n_mtiles + kTS - 1) / kTS;
+    p.stage_bytes = (p.b_bytes + kTS * kTileM * 128u + 1023u) & ~1023u;
+    rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.BW, p.BH, p.BNI, L.in_step);
+  }
+  if (rc) return rc;
+  rc = make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, 64, p.BN);
+  if (rc) return rc;
+  const uint32_t kStaging = 4u * 4096u;   // epilogue transpose tiles
+  const uint32_t fixed = (p.halo ? 2u * p.patch_bytes : 0u) + kStaging;
+  const uint32_t budget = 224u * 1024u - 1024u;
+  if (fixed + 2u * p.stage_bytes > budget) return BDBNN_ERR_UNSUPPORTED;
+  int stages = int((budget - fixed) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  const size_t smem = size_t(fixed) + size_t(stages) * p.stage_bytes + 1024;
+  static const int dbg_env = [] { const char* e = getenv("BDBNN_TC_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg_env;
+  p.trace = g_trace;
+  const int n_work = p.n_supers * p.n_ntiles;
+  int grid = num_sms();
+  if (grid > n_work) grid = n_work;
+  if (mode == 0) {
+    BDBNN_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    tc_conv2_kernel<0><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+  } else {
+    BDBNN_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    tc_conv2_kernel<1><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+  }
+  return check_launch("tc_conv2_kernel");
+}
+
+}  // namespace bdbnn

@@ -282,9 +282,12 @@ def main():
     # ---- device-resident timing (value) -----------------------------------------------------------
     if args.profile_mode:
         args.no_e2e = args.no_cpu_baseline = True
-    n_warm = 1 if args.profile_mode else max(3, args.warmup)
+    n_warm = 2 if args.profile_mode else max(3, args.warmup)
     for _ in range(n_warm):
         step(x_dev, y_dev)
+    if args.profile_mode:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()          # ncu --profile-from-start off: only the timed step(s)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -298,6 +301,8 @@ def main():
         step(x_dev, y_dev)
     e1.record()
     barrier()
+    if args.profile_mode:
+        torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - n0
     kern = KernelTimer.stop()

@@ -51,6 +51,9 @@ typedef struct bdbnn_conv_shape {
 BDBNN_API int bdbnn_version(void);
 /* Thread-local description of the last error returned on this thread ("" if none). */
 BDBNN_API const char* bdbnn_last_error_string(void);
+/* Developer aid: when device_buf != NULL (3*2048 int64), CTA 0 of the persistent conv kernel records
+ * (event id, clock64) pairs per warp role into it (scripts/trace_tc.py decodes). NULL disables. */
+BDBNN_API int bdbnn_debug_trace(long long* device_buf);
 /* Which tcgen05/TMA implicit-GEMM kernels can serve this shape: bitmask
  * BDBNN_TC_FWD | BDBNN_TC_DGRAD | BDBNN_TC_WGRAD (0 = none: the CUDA-core kernels do all three). */
 #define BDBNN_TC_FWD 1

@@ -13,9 +13,9 @@ timeout 900 python scripts/kernel_bench.py --impl ${IMPL:-xnor} --out gpurun_out
 timeout 1200 python bench.py --steps ${STEPS:-5} --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit: $?" >> gpurun_out/${TAG}_bench.err
 if [ -z "$NO_NCU" ]; then
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 6000 --csv \
    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --profile-mode > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_K:-binconv_fwd_xnor|act_pack}" -c ${NCU_C:-4} \
+timeout 900 ncu --set full --clock-control none --profile-from-start off --import-source on -k regex:"${NCU_K:-binconv_fwd_xnor|act_pack}" -c ${NCU_C:-4} \
    -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --profile-mode > gpurun_out/${TAG}_ncu_full.log 2>&1
 fi
 tail -5 gpurun_out/${TAG}_pytest.log; tail -3 gpurun_out/${TAG}_smoke.log; cat gpurun_out/${TAG}_bench.json | head -c 3000; tail -3 gpurun_out/${TAG}_bench.err

@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--impl", default="xnor")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--layers", default=None, help="comma list of layer names to run")
+    ap.add_argument("--kernels", default=None, help="comma list of kernel names to time")
     a = ap.parse_args()
     L = _lib.lib()
     peak = 6575.1
@@ -48,6 +50,8 @@ def main():
     flush = torch.empty(64 * 1024 * 1024, device="cuda")
     rows = []
     for name, cin, hw, cout, stride in R18:
+        if a.layers and name not in a.layers.split(","):
+            continue
         n = a.batch
         sh = conv_shape((n, cin, hw, hw), (cout, cin, 3, 3), stride, 1)
         cw = (cin + 31) // 32
@@ -96,6 +100,8 @@ def main():
                 "wgrad": lambda: ck(L.bdbnn_binconv_wgrad(_p(gy), _p(sb), _p(wm), _p(gw), shp, st), "w"),
             })
         for kname, fn in kernels.items():
+            if a.kernels and kname not in a.kernels.split(",") and "pack" not in kname:
+                continue
             fn()
             torch.cuda.synchronize()
             ms = timeit(fn, flush, iters=3 if kname in ("dgrad", "wgrad") else 7)
