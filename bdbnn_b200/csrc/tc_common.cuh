@@ -166,6 +166,21 @@ __device__ __forceinline__ void umma_bf16_k4(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
+// One MMA from pre-split descriptor words (cheap to advance: only the low words change per K step).
+__device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Low / high words of a SWIZZLE_128B K-major descriptor (see make_kmajor_desc).
 __device__ __forceinline__ uint32_t kmajor128_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint32_t kmajor128_hi() { return (1024u >> 4) | (1u << 14) | (2u << 29); }
@@ -261,5 +276,6 @@ struct TcConvLaunch {
 // does not qualify (caller falls back to the one-tile-per-CTA kernel in tc_conv.cu).
 int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st);
 void set_tc_trace(long long* buf);
+bool wgrad_tc_ok(const bdbnn_conv_shape* s);
 
 }  // namespace bdbnn
