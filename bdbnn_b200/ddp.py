@@ -22,7 +22,9 @@ class GradAllReduce:
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)     # autograd accumulates in place into the view
+            # autograd accumulates in place into the view; keep the parameter's own strides
+            # (channels_last conv weights) so fused optimizers see matching layouts
+            p.grad = torch.as_strided(self.flat, p.size(), p.stride(), storage_offset=off)
             off += n
         if broadcast_params and self.world > 1:
             # DDP broadcasts rank-0 parameters and buffers at construction (train.py:304)
