@@ -29,16 +29,16 @@ SIGNATURES = {
     "bdbnn_last_error_string": (ctypes.c_char_p, []),
     "bdbnn_tc_supported": (c_int, [_SH]),
     "bdbnn_debug_trace": (c_int, [_P]),
-    "bdbnn_act_pack": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P]),
-    "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bdbnn_act_pack": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P]),
+    "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "bdbnn_binconv_fwd_xnor": (c_int, [_P, _P, _P, _P, _SH, _P]),
-    "bdbnn_binconv_fwd_tc": (c_int, [_P, _P, _P, _P, _SH, _P]),
+    "bdbnn_binconv_fwd_tc": (c_int, [_P, _P, c_int, _P, _P, _SH, _P]),
     "bdbnn_binconv_dgrad": (c_int, [_P, _P, _P, _P, _P, _SH, _P]),
     "bdbnn_binconv_wgrad": (c_int, [_P, _P, _P, _P, _SH, _P]),
-    "bdbnn_grad_pack": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),
-    "bdbnn_binconv_dgrad_tc": (c_int, [_P, c_int, _P, _P, _P, _SH, _P]),
+    "bdbnn_grad_pack": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
+    "bdbnn_binconv_dgrad_tc": (c_int, [_P, c_int, _P, _P, _P, _P, _SH, _P]),
     "bdbnn_wgrad_tc_workspace_bytes": (c_size_t, [_SH]),
-    "bdbnn_binconv_wgrad_tc": (c_int, [_P, c_int, _P, _P, _P, _P, _SH, _P, c_size_t, _P]),
+    "bdbnn_binconv_wgrad_tc": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _SH, _P, c_size_t, _P]),
     "bdbnn_kurtosis_multi_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P]),
     "bdbnn_kurtosis_multi_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P]),
     "bdbnn_kd_logits_fwd_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),

@@ -61,6 +61,23 @@ inline int num_sms() {
   return n;
 }
 
+// Power-of-two scale for the FP16S gradient mode: amax * 2^e lands in [2^13, 2^14).
+// inverse=false -> 2^e, inverse=true -> 2^-e (both exact).  amax == 0 / denormal -> 1.
+__host__ __device__ inline float amax_pow2_scale(uint32_t amax_bits, bool inverse) {
+  const int be = int((amax_bits >> 23) & 0xffu);
+  if (be == 0) return 1.0f;
+  int e = 13 - (be - 127);
+  e = e > 120 ? 120 : (e < -120 ? -120 : e);
+  const uint32_t bits = uint32_t(127 + (inverse ? -e : e)) << 23;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(bits);
+#else
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -18,7 +18,7 @@ constexpr int kPackUnroll = 8;
 __global__ void __launch_bounds__(256)
 act_pack_kernel(const float* __restrict__ x, int64_t n_words, int32_t C, int32_t Cw,
                 uint32_t* __restrict__ sign_bits, uint32_t* __restrict__ mask_bits,
-                uint16_t* __restrict__ xb) {
+                uint16_t* __restrict__ xb, uint16_t one16) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -49,7 +49,7 @@ act_pack_kernel(const float* __restrict__ x, int64_t n_words, int32_t C, int32_t
       const uint32_t sb = __ballot_sync(0xffffffffu, v[j] >= 0.0f);
       const uint32_t mb = __ballot_sync(0xffffffffu, fabsf(v[j]) <= 1.0f);
       if (lane == j) { my_sign = sb; my_mask = mb; }
-      if (xb != nullptr && ok[j]) xb[idx[j]] = (v[j] >= 0.0f) ? uint16_t(0x3F80) : uint16_t(0xBF80);
+      if (xb != nullptr && ok[j]) xb[idx[j]] = (v[j] >= 0.0f) ? one16 : uint16_t(one16 | 0x8000u);
     }
     if (lane < kPackUnroll && (w0 + lane) < n_words) {
       sign_bits[w0 + lane] = my_sign;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256)
 weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32_t T, int32_t Cw,
                    float* __restrict__ alpha, uint32_t* __restrict__ wsign,
                    uint16_t* __restrict__ wf, uint16_t* __restrict__ wt,
-                   float* __restrict__ gscale, float* __restrict__ inv_gscale) {
+                   float* __restrict__ gscale, float* __restrict__ inv_gscale, uint16_t one16) {
   const int o = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int per = Cin * T;
@@ -105,7 +105,7 @@ weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32
     for (int i = tid; i < per; i += blockDim.x) {
       const int t = i / Cin, c = i - t * Cin;  // (t, c) with c fastest: coalesced wf writes
       const float v = Wo[c * T + t];
-      const uint16_t sg = (v >= 0.0f) ? uint16_t(0x3F80) : uint16_t(0xBF80);
+      const uint16_t sg = (v >= 0.0f) ? one16 : uint16_t(one16 | 0x8000u);
       if (wf) wf[(int64_t(o) * T + t) * Cin + c] = sg;
       if (wt) wt[(int64_t(c) * T + (T - 1 - t)) * Cout + o] = live ? sg : uint16_t(0);
     }
@@ -134,17 +134,51 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// v = gy[i] * gscale[i % Cout]; halves==1: out[i] = bf16_rn(v);
-// halves==2: out[pix*2*Cout + o] = hi = bf16_rn(v), out[pix*2*Cout + Cout + o] = bf16_rn(v - hi).
+// ---- gradient operand packing -----------------------------------------------------------------------
+// v = gy[i] * gscale[i % Cout]
+//   MODE 1 (BF16)   : out[i] = bf16_rn(v)
+//   MODE 2 (BF16X2) : out[pix*2C + o] = hi = bf16_rn(v), out[pix*2C + C + o] = bf16_rn(v - hi)
+//   MODE 3 (FP16S)  : out[i] = fp16_rn(v * 2^e), e = 13 - floor(log2(amax)), amax = max|v| of this call
 __device__ __forceinline__ float bf16_round(float v) {
   return __uint_as_float(pack_bf16x2(0.f, v) & 0xffff0000u);
 }
-template <int HALVES>
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __global__ void __launch_bounds__(256)
-grad_pack_kernel(const float* __restrict__ gy, const float* __restrict__ gscale, int64_t n,
-                 int32_t Cout, uint16_t* __restrict__ out) {
+grad_amax_kernel(const float* __restrict__ gy, const float* __restrict__ gscale, int64_t n, int32_t Cout,
+                 uint32_t* __restrict__ amax_bits) {
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  float m = 0.f;
+  if ((Cout & 3) == 0) {
+    const int64_t n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(gy);
+    for (int64_t i = tid; i < n4; i += nthreads) {
+      const float4 v = __ldg(g4 + i);                    // keep in L2 for the pack pass that follows
+      const int o = int((i * 4) % Cout);
+      const float4 s = *reinterpret_cast<const float4*>(gscale + o);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x * s.x), fabsf(v.y * s.y)), fmaxf(fabsf(v.z * s.z), fabsf(v.w * s.w))));
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) m = fmaxf(m, fabsf(gy[i] * gscale[i % Cout]));
+  }
+  // NaN never wins fmaxf; an Inf does and yields scale 2^-115 (result stays Inf like the reference's)
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+grad_pack_kernel(const float* __restrict__ gy, const float* __restrict__ gscale, int64_t n,
+                 int32_t Cout, const uint32_t* __restrict__ amax_bits, uint16_t* __restrict__ out) {
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  constexpr int HALVES = MODE == 2 ? 2 : 1;
+  const float up = MODE == 3 ? amax_pow2_scale(*amax_bits, false) : 1.0f;
   if ((Cout & 3) == 0) {
     const int64_t n4 = n >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(gy);
@@ -154,13 +188,18 @@ grad_pack_kernel(const float* __restrict__ gy, const float* __restrict__ gscale,
       const int64_t pix = e / Cout;
       const int o = int(e - pix * Cout);
       const float4 s = *reinterpret_cast<const float4*>(gscale + o);
-      const float a0 = v.x * s.x, a1 = v.y * s.y, a2 = v.z * s.z, a3 = v.w * s.w;
+      const float a0 = v.x * s.x * up, a1 = v.y * s.y * up, a2 = v.z * s.z * up, a3 = v.w * s.w * up;
       uint2 r;
-      r.x = pack_bf16x2(a0, a1);
-      r.y = pack_bf16x2(a2, a3);
+      if (MODE == 3) {
+        r.x = pack_f16x2(a0, a1);
+        r.y = pack_f16x2(a2, a3);
+      } else {
+        r.x = pack_bf16x2(a0, a1);
+        r.y = pack_bf16x2(a2, a3);
+      }
       uint16_t* dst = out + pix * (int64_t(HALVES) * Cout) + o;
       *reinterpret_cast<uint2*>(dst) = r;
-      if (HALVES == 2) {
+      if (MODE == 2) {
         uint2 l;
         l.x = pack_bf16x2(a0 - bf16_round(a0), a1 - bf16_round(a1));
         l.y = pack_bf16x2(a2 - bf16_round(a2), a3 - bf16_round(a3));
@@ -171,10 +210,14 @@ grad_pack_kernel(const float* __restrict__ gy, const float* __restrict__ gscale,
     for (int64_t i = tid; i < n; i += nthreads) {
       const int64_t pix = i / Cout;
       const int o = int(i - pix * Cout);
-      const float v = gy[i] * gscale[o];
+      const float v = gy[i] * gscale[o] * up;
       uint16_t* dst = out + pix * (int64_t(HALVES) * Cout) + o;
-      *dst = uint16_t(pack_bf16x2(v, 0.f) & 0xffffu);
-      if (HALVES == 2) dst[Cout] = uint16_t(pack_bf16x2(v - bf16_round(v), 0.f) & 0xffffu);
+      if (MODE == 3) {
+        *dst = uint16_t(pack_f16x2(v, 0.f) & 0xffffu);
+      } else {
+        *dst = uint16_t(pack_bf16x2(v, 0.f) & 0xffffu);
+        if (MODE == 2) dst[Cout] = uint16_t(pack_bf16x2(v - bf16_round(v), 0.f) & 0xffffu);
+      }
     }
   }
 }
@@ -183,8 +226,11 @@ grad_pack_kernel(const float* __restrict__ gy, const float* __restrict__ gscale,
 
 using namespace bdbnn;
 
+static inline uint16_t one_bits(int fmt) { return fmt == BDBNN_FMT_FP16 ? uint16_t(0x3C00) : uint16_t(0x3F80); }
+
 extern "C" int bdbnn_act_pack(const float* x, int64_t n_pix, int32_t C, uint32_t* sign_bits,
-                              uint32_t* mask_bits, uint16_t* xb_bf16, void* stream) {
+                              uint32_t* mask_bits, uint16_t* xb_bf16, int32_t fmt, void* stream) {
+  BDBNN_REQUIRE(fmt == BDBNN_FMT_FP16 || fmt == BDBNN_FMT_BF16, "act_pack: bad operand format");
   BDBNN_REQUIRE(n_pix >= 0 && C > 0, "act_pack: bad n_pix/C");
   if (n_pix == 0) return BDBNN_OK;
   BDBNN_REQUIRE(x && sign_bits && mask_bits, "act_pack: NULL pointer");
@@ -197,19 +243,20 @@ extern "C" int bdbnn_act_pack(const float* x, int64_t n_pix, int32_t C, uint32_t
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   act_pack_kernel<<<unsigned(blocks), threads, 0, cudaStream_t(stream)>>>(
-      x, n_words, C, Cw, sign_bits, mask_bits, xb_bf16);
+      x, n_words, C, Cw, sign_bits, mask_bits, xb_bf16, one_bits(fmt));
   return check_launch("act_pack_kernel");
 }
 
 extern "C" int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
                                  float* alpha, uint32_t* wsign_bits, uint32_t* wmask_bits,
                                  uint16_t* wf_bf16, uint16_t* wt_bf16, float* gscale,
-                                 float* inv_gscale, void* stream) {
+                                 float* inv_gscale, int32_t fmt, void* stream) {
+  BDBNN_REQUIRE(fmt == BDBNN_FMT_FP16 || fmt == BDBNN_FMT_BF16, "weight_pack: bad operand format");
   BDBNN_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "weight_pack: bad dims");
   BDBNN_REQUIRE(W && alpha && wsign_bits && wmask_bits, "weight_pack: NULL pointer");
   const int32_t T = kh * kw, Cw = (Cin + 31) / 32;
   weight_pack_kernel<<<Cout, 256, 0, cudaStream_t(stream)>>>(W, Cout, Cin, T, Cw, alpha, wsign_bits,
-                                                            wf_bf16, wt_bf16, gscale, inv_gscale);
+                                                            wf_bf16, wt_bf16, gscale, inv_gscale, one_bits(fmt));
   int rc = check_launch("weight_pack_kernel");
   if (rc) return rc;
   const int64_t n = int64_t(Cout) * Cin * T;
@@ -221,19 +268,28 @@ extern "C" int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int3
 }
 
 extern "C" int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_pix, int32_t Cout,
-                               int32_t halves, uint16_t* gys_bf16, void* stream) {
+                               int32_t mode, uint32_t* amax_bits, uint16_t* gys, void* stream) {
   BDBNN_REQUIRE(n_pix >= 0 && Cout > 0, "grad_pack: bad dims");
-  BDBNN_REQUIRE(halves == 1 || halves == 2, "grad_pack: halves must be 1 or 2");
+  BDBNN_REQUIRE(mode >= BDBNN_GRAD_BF16 && mode <= BDBNN_GRAD_FP16S, "grad_pack: bad mode %d", mode);
   if (n_pix == 0) return BDBNN_OK;
-  BDBNN_REQUIRE(gy && gscale && gys_bf16, "grad_pack: NULL pointer");
+  BDBNN_REQUIRE(gy && gscale && gys, "grad_pack: NULL pointer");
+  BDBNN_REQUIRE(mode != BDBNN_GRAD_FP16S || amax_bits, "grad_pack: FP16S mode needs the amax scratch word");
+  cudaStream_t st = cudaStream_t(stream);
   const int64_t n = n_pix * Cout;
   int64_t blocks = ((n >> 2) + 255) / 256;
   const int64_t cap = int64_t(num_sms()) * 8 * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (halves == 2)
-    grad_pack_kernel<2><<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(gy, gscale, n, Cout, gys_bf16);
-  else
-    grad_pack_kernel<1><<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(gy, gscale, n, Cout, gys_bf16);
+  if (mode == BDBNN_GRAD_FP16S) {
+    BDBNN_CUDA(cudaMemsetAsync(amax_bits, 0, sizeof(uint32_t), st));
+    grad_amax_kernel<<<unsigned(blocks), 256, 0, st>>>(gy, gscale, n, Cout, amax_bits);
+    int rc = check_launch("grad_amax_kernel");
+    if (rc) return rc;
+    grad_pack_kernel<3><<<unsigned(blocks), 256, 0, st>>>(gy, gscale, n, Cout, amax_bits, gys);
+  } else if (mode == BDBNN_GRAD_BF16X2) {
+    grad_pack_kernel<2><<<unsigned(blocks), 256, 0, st>>>(gy, gscale, n, Cout, nullptr, gys);
+  } else {
+    grad_pack_kernel<1><<<unsigned(blocks), 256, 0, st>>>(gy, gscale, n, Cout, nullptr, gys);
+  }
   return check_launch("grad_pack_kernel");
 }

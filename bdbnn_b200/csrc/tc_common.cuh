@@ -122,8 +122,9 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t ro
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
 // K-major A and B (0) @15/@16, N>>3 @17, M>>4 @24.
-__host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// fmt: BDBNN_FMT_FP16 (0) or BDBNN_FMT_BF16 (1) for both A and B (kind::f16).
+__host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t fmt = 1u) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 constexpr int kTcThreads = 192;
@@ -270,6 +271,8 @@ struct TcConvLaunch {
   int n_taps; int8_t dh[kMaxTaps], dw[kMaxTaps]; uint8_t tb[kMaxTaps];
   int out_step, off_h, off_w, OHf, OWf;
   const float* alpha; const uint32_t* mask; float* out;
+  int fmt;                       // operand format (BDBNN_FMT_*)
+  const uint32_t* amax_bits;     // FP16S gradient: device word with max|A|; epilogue multiplies by 2^-e
 };
 
 // Persistent multi-accumulator kernel (tc_conv2.cu). Returns BDBNN_ERR_UNSUPPORTED if the geometry

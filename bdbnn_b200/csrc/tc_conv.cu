@@ -36,6 +36,8 @@ struct TcConvParams {
   int32_t halo, PW, PH, dh_min, dw_min, patch_bytes;
   int32_t stages;
   int32_t row_bytes;         // KB * 2 = swizzle span (32/64/128)
+  int32_t fmt;               // operand format
+  const uint32_t* amax_bits; // FP16S: post-scale 2^-e (NULL otherwise)
   const float* alpha;        // MODE 0: per-output-channel scale
   const uint32_t* mask;      // MODE 1: STE mask words [pix][Nout/32 (ceil)]
   float* out;                // [pix][Nout] fp32
@@ -111,7 +113,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     } else if (warp == 5) {
       if (lane == 0) {
-        const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN));
+        const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN), uint32_t(p.fmt));
         int it = 0;
         for (int kb = 0; kb < kb_total; ++kb) {
           const int pa = kb & 1;
@@ -158,7 +160,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN));
+      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN), uint32_t(p.fmt));
       const int k_steps = p.KB / 16;                  // UMMA K = 16 bf16 = 32 bytes
       for (int it = 0; it < n_iters; ++it) {
         const int stage = it % p.stages;
@@ -191,6 +193,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     mbar_wait(smem_u32(&accum_bar), 0);
     tc_fence_after();
+    const float post = p.amax_bits ? amax_pow2_scale(__ldg(p.amax_bits), true) : 1.0f;
     const uint32_t lane_base = tmem_d + (uint32_t(warp * 32) << 16);
     for (int c0 = 0; c0 < p.BN; c0 += 16) {
       uint32_t v[16];
@@ -205,7 +208,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int col = nn0 + c0;
           const uint32_t word = __ldg(p.mask + pix * mask_words + (col >> 5)) >> (col & 31);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = ((word >> j) & 1u) ? __uint_as_float(v[j]) : 0.0f;
+          for (int j = 0; j < 16; ++j) f[j] = ((word >> j) & 1u) ? __uint_as_float(v[j]) * post : 0.0f;
         }
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
@@ -271,6 +274,7 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   p.Nout = L.Nout;
   p.BN = pick_bn(L.Nout);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
+  p.fmt = L.fmt; p.amax_bits = L.amax_bits;
   // Halo mode (stride-1 launches with >128-pixel images and 64-channel K blocks): see TcConvParams.
   static const int halo_env = [] { const char* e = getenv("BDBNN_TC_HALO"); return e ? atoi(e) : 1; }();
   if (halo_env > 0 && L.in_step == 1 && p.KB == 64 && L.OH * L.OW > kTileM && p.n_taps > 0) {
@@ -331,8 +335,9 @@ extern "C" int bdbnn_tc_supported(const bdbnn_conv_shape* s) {
   return BDBNN_TC_FWD | BDBNN_TC_DGRAD | (wgrad_tc_ok(s) ? BDBNN_TC_WGRAD : 0);
 }
 
-extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, const float* alpha,
-                                    float* y, const bdbnn_conv_shape* s, void* stream) {
+extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, int32_t fmt,
+                                    const float* alpha, float* y, const bdbnn_conv_shape* s, void* stream) {
+  BDBNN_REQUIRE(fmt == BDBNN_FMT_FP16 || fmt == BDBNN_FMT_BF16, "binconv_fwd_tc: bad operand format");
   int rc = validate_shape(s);
   if (rc) return rc;
   BDBNN_REQUIRE(xb_bf16 && wf_bf16 && alpha && y, "binconv_fwd_tc: NULL pointer");
@@ -349,17 +354,19 @@ extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_
     }
   L.n_taps = s->kh * s->kw;
   L.out_step = 1; L.OHf = s->Ho; L.OWf = s->Wo;
-  L.alpha = alpha; L.out = y;
+  L.alpha = alpha; L.out = y; L.fmt = fmt;
   return launch_tc_conv<0>(L, cudaStream_t(stream));
 }
 
-extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_halves,
+extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
                                       const uint16_t* wt_bf16, const uint32_t* mask_bits, float* gx,
                                       const bdbnn_conv_shape* s, void* stream) {
   int rc = validate_shape(s);
   if (rc) return rc;
   BDBNN_REQUIRE(gys_bf16 && wt_bf16 && mask_bits && gx, "binconv_dgrad_tc: NULL pointer");
-  BDBNN_REQUIRE(grad_halves == 1 || grad_halves == 2, "binconv_dgrad_tc: grad_halves must be 1 or 2");
+  BDBNN_REQUIRE(grad_mode >= BDBNN_GRAD_BF16 && grad_mode <= BDBNN_GRAD_FP16S, "binconv_dgrad_tc: bad grad_mode");
+  BDBNN_REQUIRE(grad_mode != BDBNN_GRAD_FP16S || amax_bits, "binconv_dgrad_tc: FP16S needs amax_bits");
+  const int grad_halves = grad_mode == BDBNN_GRAD_BF16X2 ? 2 : 1;
   if (!tc_shape_ok(s)) { set_error("binconv_dgrad_tc: shape not supported by the tcgen05 path"); return BDBNN_ERR_UNSUPPORTED; }
   cudaStream_t st = cudaStream_t(stream);
   const int T = s->kh * s->kw, sd = s->stride;
@@ -391,6 +398,8 @@ extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_hal
       L.NIMG = s->N;
       L.out_step = sd; L.off_h = a; L.off_w = b; L.OHf = s->H; L.OWf = s->W;
       L.mask = mask_bits; L.out = gx;
+      L.fmt = grad_mode == BDBNN_GRAD_FP16S ? BDBNN_FMT_FP16 : BDBNN_FMT_BF16;
+      L.amax_bits = grad_mode == BDBNN_GRAD_FP16S ? amax_bits : nullptr;
       ++n_launch;
     }
   if (empty_phase)

@@ -40,6 +40,8 @@ struct TcConv2Params {
   int32_t stages;
   int32_t dbg;               // BDBNN_TC_DBG experiment bits: 1 = no global stores, 2 = no TMEM loads, 4 = no MMAs
   uint32_t stage_bytes, b_bytes;
+  int32_t fmt;
+  const uint32_t* amax_bits;
   const float* alpha;
   const uint32_t* mask;
   float* out;
@@ -173,7 +175,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 5) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN));
+      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN), uint32_t(p.fmt));
       const uint32_t desc_hi = kmajor128_hi();
       uint32_t it = 0, pcount = 0, wcount = 0;
       int tr_n = 0;
@@ -224,6 +226,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ================================ epilogue (warps 0..3) ================================
     const int mask_words = (p.Nout + 31) >> 5;
+    const float post = p.amax_bits ? amax_pow2_scale(__ldg(p.amax_bits), true) : 1.0f;
     uint32_t wcount = 0;
     int tr_n = (threadIdx.x == 0) ? 0 : 100000;
     // 4 KB per-warp staging tile behind the TMA ring (generic-proxy only, never touched by TMA/UMMA)
@@ -288,10 +291,10 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               o = make_float4(__uint_as_float(v[q]) * a.x, __uint_as_float(v[q + 1]) * a.y,
                               __uint_as_float(v[q + 2]) * a.z, __uint_as_float(v[q + 3]) * a.w);
             } else {
-              o = make_float4(((word >> q) & 1u) ? __uint_as_float(v[q]) : 0.0f,
-                              ((word >> (q + 1)) & 1u) ? __uint_as_float(v[q + 1]) : 0.0f,
-                              ((word >> (q + 2)) & 1u) ? __uint_as_float(v[q + 2]) : 0.0f,
-                              ((word >> (q + 3)) & 1u) ? __uint_as_float(v[q + 3]) : 0.0f);
+              o = make_float4(((word >> q) & 1u) ? __uint_as_float(v[q]) * post : 0.0f,
+                              ((word >> (q + 1)) & 1u) ? __uint_as_float(v[q + 1]) * post : 0.0f,
+                              ((word >> (q + 2)) & 1u) ? __uint_as_float(v[q + 2]) * post : 0.0f,
+                              ((word >> (q + 3)) & 1u) ? __uint_as_float(v[q + 3]) * post : 0.0f);
             }
             *reinterpret_cast<float4*>(stage_warp + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
           }
@@ -342,6 +345,7 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   p.n_ntiles = L.Nout / p.BN;
   p.NB = p.BN == 64 ? 2 : 1;
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
+  p.fmt = L.fmt; p.amax_bits = L.amax_bits;
   p.b_bytes = uint32_t(p.BN) * 128u;
 
   int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;

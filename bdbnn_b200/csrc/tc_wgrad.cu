@@ -43,6 +43,7 @@ struct TcWgradParams {
   int32_t n_units, G;            // (tap, chunk) units; M tiles (accumulators) per CTA
   int32_t BN;                    // N tile (output channels per CTA)
   int32_t stages;
+  int32_t fmt;                   // operand format (BDBNN_FMT_*)
   float* ws;                     // [T*Cin][Cout] fp32, zero-initialised
 };
 
@@ -175,7 +176,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else if (warp == 5) {
     if (lane == 0) {
       // M=128, N=BN, A and B MN-major (bits 15/16)
-      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN)) | (1u << 15) | (1u << 16);
+      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN), uint32_t(p.fmt)) | (1u << 15) | (1u << 16);
       const int k_steps = p.k_stage / 16;
       int it = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
@@ -236,16 +237,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // gW[o][c][t] = wmask ? ws[(t*Cin + c)*Cout + o] * inv_gscale[o] : 0
 __global__ void __launch_bounds__(256)
 wgrad_finalize_kernel(const float* __restrict__ ws, const uint32_t* __restrict__ wmask,
-                      const float* __restrict__ inv_gscale, float* __restrict__ gW, int Cout, int Cin,
-                      int T) {
+                      const float* __restrict__ inv_gscale, const uint32_t* __restrict__ amax_bits,
+                      float* __restrict__ gW, int Cout, int Cin, int T) {
   const int64_t n = int64_t(Cout) * Cin * T;
+  const float post = amax_bits ? amax_pow2_scale(__ldg(amax_bits), true) : 1.0f;
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
        e += int64_t(gridDim.x) * blockDim.x) {
     const int t = int(e % T);
     const int64_t oc = e / T;
     const int c = int(oc % Cin), o = int(oc / Cin);
     const bool pass = (wmask[e >> 5] >> (e & 31)) & 1u;
-    gW[e] = pass ? ws[(int64_t(t) * Cin + c) * Cout + o] * inv_gscale[o] : 0.0f;
+    gW[e] = pass ? ws[(int64_t(t) * Cin + c) * Cout + o] * post * inv_gscale[o] : 0.0f;
   }
 }
 
@@ -361,7 +363,8 @@ extern "C" size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s) {
   return size_t(s->kh) * s->kw * s->Cin * s->Cout * sizeof(float);
 }
 
-extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_halves, const uint16_t* xb_bf16,
+extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
+                                      const uint16_t* xb_bf16,
                                       const uint32_t* wmask_bits, const float* inv_gscale, float* gW,
                                       const bdbnn_conv_shape* s, void* workspace, size_t workspace_bytes,
                                       void* stream) {
@@ -369,8 +372,11 @@ extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_hal
   if (rc) return rc;
   BDBNN_REQUIRE(gys_bf16 && xb_bf16 && wmask_bits && inv_gscale && gW && workspace,
                 "binconv_wgrad_tc: NULL pointer");
-  BDBNN_REQUIRE(grad_halves == 1 || grad_halves == 2, "binconv_wgrad_tc: grad_halves must be 1 or 2");
+  BDBNN_REQUIRE(grad_mode >= BDBNN_GRAD_BF16 && grad_mode <= BDBNN_GRAD_FP16S, "binconv_wgrad_tc: bad grad_mode");
+  BDBNN_REQUIRE(grad_mode != BDBNN_GRAD_FP16S || amax_bits, "binconv_wgrad_tc: FP16S needs amax_bits");
+  const int grad_halves = grad_mode == BDBNN_GRAD_BF16X2 ? 2 : 1;
   WgradPlan pl = plan_wgrad(s, grad_halves);
+  pl.p.fmt = grad_mode == BDBNN_GRAD_FP16S ? BDBNN_FMT_FP16 : BDBNN_FMT_BF16;
   if (!pl.ok) { set_error("binconv_wgrad_tc: shape not supported by the tcgen05 path"); return BDBNN_ERR_UNSUPPORTED; }
   const size_t need = bdbnn_wgrad_tc_workspace_bytes(s);
   if (workspace_bytes < need) {
@@ -396,7 +402,8 @@ extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_hal
   const int64_t n = int64_t(s->Cout) * s->Cin * s->kh * s->kw;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 2048) blocks = 2048;
-  wgrad_finalize_kernel<<<unsigned(blocks), 256, 0, st>>>(pl.p.ws, wmask_bits, inv_gscale, gW, s->Cout,
-                                                          s->Cin, s->kh * s->kw);
+  wgrad_finalize_kernel<<<unsigned(blocks), 256, 0, st>>>(
+      pl.p.ws, wmask_bits, inv_gscale, grad_mode == BDBNN_GRAD_FP16S ? amax_bits : nullptr, gW, s->Cout, s->Cin,
+      s->kh * s->kw);
   return check_launch("wgrad_finalize_kernel");
 }

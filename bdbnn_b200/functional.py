@@ -11,14 +11,19 @@ from . import _lib
 from ._lib import ConvShape
 
 _IMPL_ENV = "BDBNN_IMPL"          # auto | xnor | tc
-_GRAD_ENV = "BDBNN_GRAD_HALVES"   # 2 (default): gy as bf16 hi+lo pair (fp32-class accuracy); 1: single bf16
+_GRAD_ENV = "BDBNN_GRAD_MODE"     # fp16s (default) | bf16x2 | bf16  — rounding of gy*gscale (include/bdbnn.h)
+GRAD_MODES = {"bf16": 1, "bf16x2": 2, "fp16s": 3}
+FMT_FP16, FMT_BF16 = 0, 1
 
 
-def grad_halves():
-    h = int(os.environ.get(_GRAD_ENV, "2"))
-    if h not in (1, 2):
-        raise ValueError(f"{_GRAD_ENV} must be 1 or 2")
-    return h
+def grad_mode():
+    """(name, BDBNN_GRAD_* code, halves, operand format).  fp16s: fp16 with a per-call power-of-two scale
+    (11 significand bits = what cuDNN's default TF32 convs give the reference); bf16x2: hi+lo pair."""
+    name = os.environ.get(_GRAD_ENV, "fp16s").lower()
+    if name not in GRAD_MODES:
+        raise ValueError(f"{_GRAD_ENV} must be one of {sorted(GRAD_MODES)}")
+    code = GRAD_MODES[name]
+    return name, code, (2 if code == 2 else 1), (FMT_FP16 if code == 3 else FMT_BF16)
 _VALID_IMPL = ("auto", "xnor", "tc")
 
 
@@ -86,6 +91,7 @@ def algorithmic_bytes(kernel, sh, gh=1):
         "dgrad": 4 * n_out + n_w // 8 + n_in // 8 + 4 * n_in,  # read gy, bits; write gx
         "wgrad": 4 * n_out + n_in // 8 + n_w // 8 + 4 * n_w,
         "grad_pack": 4 * n_out + 2 * gh * n_out,
+        "grad_pack_amax": 4 * n_out + 2 * gh * n_out,          # the amax pre-pass re-read is not compulsory
         "dgrad_tc": 2 * gh * n_out + 2 * n_w + n_in // 8 + 4 * n_in,
         "wgrad_tc": 2 * gh * n_out + 2 * n_in + n_w // 8 + 4 * n_w,
     }[kernel]
@@ -156,27 +162,28 @@ class _BinConv2d(torch.autograd.Function):
         sign_bits = torch.empty((n, h, wd, cw), **i32)
         mask_bits = torch.empty((n, h, wd, cw), **i32)
         tc = bool(use & 1)
-        xb = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=dev) if tc else None
+        gname, gcode, ghalves, fmt = grad_mode()
+        xb = torch.empty((n, h, wd, cin), dtype=torch.int16, device=dev) if tc else None
         key = _shape_key(sh)
         with _timed("act_pack", key, algorithmic_bytes("act_pack_tc" if tc else "act_pack", sh)):
-            _lib.check(L.bdbnn_act_pack(_p(xc), n * h * wd, cin, _p(sign_bits), _p(mask_bits), _p(xb), st),
+            _lib.check(L.bdbnn_act_pack(_p(xc), n * h * wd, cin, _p(sign_bits), _p(mask_bits), _p(xb), fmt, st),
                        "act_pack")
         alpha = torch.empty((cout,), dtype=torch.float32, device=dev)
         wsign = torch.empty((cout, T, cw), **i32)
         wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
         wf = wt = gscale = inv_gscale = None
         if tc:
-            wf = torch.empty((cout, T, cin), dtype=torch.bfloat16, device=dev)
-            wt = torch.empty((cin, T, cout), dtype=torch.bfloat16, device=dev)
+            wf = torch.empty((cout, T, cin), dtype=torch.int16, device=dev)
+            wt = torch.empty((cin, T, cout), dtype=torch.int16, device=dev)
             gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
             inv_gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
         _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask),
-                                       _p(wf), _p(wt), _p(gscale), _p(inv_gscale), st), "weight_pack")
+                                       _p(wf), _p(wt), _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
         y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
                         memory_format=torch.channels_last)
         if tc:
             with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
-                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), ctypes.byref(sh), st),
+                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), st),
                            "binconv_fwd_tc")
         else:
             with _timed("binconv_fwd_xnor", key, algorithmic_bytes("fwd_xnor", sh)):
@@ -185,6 +192,7 @@ class _BinConv2d(torch.autograd.Function):
         _lib.count(4)
         ctx.sh = sh
         ctx.use = use
+        ctx.gmode = (gname, gcode, ghalves)
         ctx.x_shape = tuple(x.shape)
         ctx.w_shape = tuple(weight.shape)
         if tc:
@@ -208,18 +216,20 @@ class _BinConv2d(torch.autograd.Function):
         if ctx.use & 1:
             xb, wt, gscale, inv_gscale = saved[5:]
             n_pix_out = sh.N * sh.Ho * sh.Wo
-            gh = grad_halves()
-            gys = torch.empty((sh.N, sh.Ho, sh.Wo, gh * sh.Cout), dtype=torch.bfloat16, device=dev)
-            with _timed("grad_pack", key, algorithmic_bytes("grad_pack", sh, gh)):
-                _lib.check(L.bdbnn_grad_pack(_p(g), _p(gscale), n_pix_out, sh.Cout, gh, _p(gys), st), "grad_pack")
-            _lib.count(1)
+            gname, gcode, gh = ctx.gmode          # the +-1 operands were packed in this mode's format
+            gys = torch.empty((sh.N, sh.Ho, sh.Wo, gh * sh.Cout), dtype=torch.int16, device=dev)
+            amax = torch.empty((1,), dtype=torch.int32, device=dev) if gcode == 3 else None
+            with _timed("grad_pack", key, algorithmic_bytes("grad_pack_amax" if gcode == 3 else "grad_pack", sh, gh)):
+                _lib.check(L.bdbnn_grad_pack(_p(g), _p(gscale), n_pix_out, sh.Cout, gcode, _p(amax), _p(gys), st),
+                           "grad_pack")
+            _lib.count(2 if gcode == 3 else 1)
             if need_x and not (ctx.use & 2):
                 raise RuntimeError("bdbnn_b200: dgrad_tc unavailable for a shape fwd_tc accepted")
             if need_x:
                 gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev,
                                  memory_format=torch.channels_last)
                 with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh)):
-                    _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gh, _p(wt), _p(mask_bits), _p(gx),
+                    _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(mask_bits), _p(gx),
                                                         ctypes.byref(sh), st), "binconv_dgrad_tc")
                 _lib.count(1)
             if need_w and not (ctx.use & 4):
@@ -234,7 +244,7 @@ class _BinConv2d(torch.autograd.Function):
                 nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
                 ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
                 with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh, gh)):
-                    _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gh, _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
+                    _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gcode, _p(amax), _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
                                                         ctypes.byref(sh), _p(ws), nbytes, st),
                                "binconv_wgrad_tc")
                 _lib.count(2)

@@ -33,6 +33,14 @@ extern "C" {
 #define BDBNN_API
 #endif
 
+/* +-1 / gradient operand element format fed to the tensor cores (both are exact for +-1) */
+#define BDBNN_FMT_FP16 0
+#define BDBNN_FMT_BF16 1
+/* how gy*gscale is rounded for the tensor-core backward */
+#define BDBNN_GRAD_BF16 1    /* bf16(v): 8 significand bits                                        */
+#define BDBNN_GRAD_BF16X2 2  /* [bf16 hi | bf16 lo]: 16 bits, two MMAs per K step (fp32-class)      */
+#define BDBNN_GRAD_FP16S 3   /* fp16(v * 2^e), e per call from max|v|: 11 bits (TF32-class), 1 MMA  */
+
 #define BDBNN_OK 0
 #define BDBNN_ERR_INVALID_ARG (-1)
 #define BDBNN_ERR_CUDA (-2)
@@ -66,10 +74,10 @@ BDBNN_API int bdbnn_tc_supported(const bdbnn_conv_shape* s);
  * train.py:492 / train.py:602 (spec in DESIGN.md §2).
  *   sign_bits[p*Cw+k] bit j = (x[p*C+32k+j] >= 0)           (forward operand, bit-exact)
  *   mask_bits[p*Cw+k] bit j = (|x[p*C+32k+j]| <= 1)         (STE mask saved for backward)
- *   xb_bf16 [p*C+c]        = +1.0/-1.0 as bf16 (0x3F80/0xBF80); may be NULL (tensor-core operand)
+ *   xb_bf16 [p*C+c]        = +1.0/-1.0 in `fmt` (bf16 0x3F80/0xBF80, fp16 0x3C00/0xBC00); may be NULL
  * n_pix = N*H*W, Cw = ceil(C/32).  NaN inputs: sign bit 0 (-1), mask bit 0. */
 BDBNN_API int bdbnn_act_pack(const float* x, int64_t n_pix, int32_t C, uint32_t* sign_bits,
-                   uint32_t* mask_bits, uint16_t* xb_bf16, void* stream);
+                   uint32_t* mask_bits, uint16_t* xb_bf16, int32_t fmt, void* stream);
 
 /* ---- weight sign/pack -------------------------------------------------------------------------
  * Replaces the weight binarisation of HardBinaryConv*.forward (same call sites).
@@ -82,7 +90,7 @@ BDBNN_API int bdbnn_act_pack(const float* x, int64_t n_pix, int32_t C, uint32_t*
 BDBNN_API int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
                       float* alpha, uint32_t* wsign_bits, uint32_t* wmask_bits,
                       uint16_t* wf_bf16, uint16_t* wt_bf16, float* gscale, float* inv_gscale,
-                      void* stream);
+                      int32_t fmt, void* stream);
 
 /* ---- binary conv forward, XNOR-popcount (bit-serial, CUDA cores) -------------------------------
  * y[n,ho,wo,o] = alpha[o] * sum_{valid taps} (Cin - 2*popc(xbits ^ wbits)); zero padding
@@ -93,8 +101,8 @@ BDBNN_API int bdbnn_binconv_fwd_xnor(const uint32_t* sign_bits, const uint32_t* 
 
 /* ---- binary conv forward, tcgen05 implicit GEMM on +-1 bf16 operands (exact, fp32 accumulate) --
  * Same result as bdbnn_binconv_fwd_xnor.  Requires bdbnn_tc_supported(s). */
-BDBNN_API int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, const float* alpha,
-                         float* y, const bdbnn_conv_shape* s, void* stream);
+BDBNN_API int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, int32_t fmt,
+                         const float* alpha, float* y, const bdbnn_conv_shape* s, void* stream);
 
 /* ---- backward: data gradient -------------------------------------------------------------------
  * gx[n,h,w,c] = mask(n,h,w,c) * sum_{t,o} gy[n,ho,wo,o] * alpha[o] * sign(W[o,c,t])
@@ -111,23 +119,27 @@ BDBNN_API int bdbnn_binconv_dgrad(const float* gy, const uint32_t* wsign_bits, c
 BDBNN_API int bdbnn_binconv_wgrad(const float* gy, const uint32_t* sign_bits, const uint32_t* wmask_bits,
                         float* gW, const bdbnn_conv_shape* s, void* stream);
 
-/* ---- backward on tensor cores (tcgen05, bf16 operands, fp32 accumulate) ------------------------
- * grad_pack: v = gy[p*Cout+o] * gscale[o];  halves==1: gys[p*Cout+o] = bf16_rn(v)
- *            halves==2: gys[p*2Cout+o] = hi = bf16_rn(v), gys[p*2Cout+Cout+o] = bf16_rn(v - hi)
- *            (hi+lo carries 16 mantissa bits: backward then matches fp32 to ~1e-5 of max|grad|)
- * dgrad_tc : gx = mask * conv_transpose(gys, wt_bf16)                  (sign-only weights, exact)
- * wgrad_tc : gW = wmask * inv_gscale[o] * sum_pix gys[pix,o]*xb[pix',c]
+/* ---- backward on tensor cores (tcgen05, 16-bit operands, fp32 accumulate) -----------------------
+ * grad_pack: v = gy[p*Cout+o] * gscale[o], written per `mode` (BDBNN_GRAD_*):
+ *              BF16   gys[p*Cout+o]             = bf16_rn(v)
+ *              BF16X2 gys[p*2Cout+o] = hi = bf16_rn(v), gys[p*2Cout+Cout+o] = bf16_rn(v - hi)
+ *              FP16S  gys[p*Cout+o]             = fp16_rn(v * 2^e), e = 13 - floor(log2 max|v|); the max is
+ *                     reduced into the device word amax_bits (float bits) by the same call
+ *            gys is shared by dgrad_tc (K-major) and wgrad_tc (MN-major).
+ * dgrad_tc : gx = mask * 2^-e * conv_transpose(gys, wt)              (sign-only weights, exact)
+ * wgrad_tc : gW = wmask * inv_gscale[o] * 2^-e * sum_pix gys[pix,o]*xb[pix',c]
+ * The +-1 operands (xb, wt) must be in the format matching the mode: fp16 for FP16S, bf16 otherwise.
  * wgrad_tc needs a workspace of bdbnn_wgrad_tc_workspace_bytes(s) bytes (split-K partials).
- * grad_halves must be the value grad_pack was called with. */
+ * grad_mode / amax_bits must be the values grad_pack was called with (amax_bits may be NULL unless FP16S). */
 BDBNN_API int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_pix, int32_t Cout,
-                    int32_t halves, uint16_t* gys_bf16, void* stream);
-BDBNN_API int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_halves, const uint16_t* wt_bf16,
-                           const uint32_t* mask_bits, float* gx, const bdbnn_conv_shape* s,
-                           void* stream);
+                    int32_t mode, uint32_t* amax_bits, uint16_t* gys, void* stream);
+BDBNN_API int bdbnn_binconv_dgrad_tc(const uint16_t* gys, int32_t grad_mode, const uint32_t* amax_bits,
+                           const uint16_t* wt, const uint32_t* mask_bits, float* gx,
+                           const bdbnn_conv_shape* s, void* stream);
 BDBNN_API size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s);
-BDBNN_API int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_halves, const uint16_t* xb_bf16,
-                           const uint32_t* wmask_bits, const float* inv_gscale, float* gW,
-                           const bdbnn_conv_shape* s, void* workspace, size_t workspace_bytes,
+BDBNN_API int bdbnn_binconv_wgrad_tc(const uint16_t* gys, int32_t grad_mode, const uint32_t* amax_bits,
+                           const uint16_t* xb, const uint32_t* wmask_bits, const float* inv_gscale,
+                           float* gW, const bdbnn_conv_shape* s, void* workspace, size_t workspace_bytes,
                            void* stream);
 
 /* ---- kurtosis regulariser, multi-tensor --------------------------------------------------------

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from bdbnn_b200 import _lib  # noqa: E402
-from bdbnn_b200.functional import _p, _stream, algorithmic_bytes, conv_shape  # noqa: E402
+from bdbnn_b200.functional import _p, _stream, algorithmic_bytes, conv_shape, grad_mode  # noqa: E402
 
 R18 = [("layer1", 64, 56, 64, 1), ("layer2.0.conv1", 64, 56, 128, 2), ("layer2", 128, 28, 128, 1),
        ("layer3.0.conv1", 128, 28, 256, 2), ("layer3", 256, 14, 256, 1),
@@ -59,17 +59,18 @@ def main():
         w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
         sb = torch.empty((n, hw, hw, cw), dtype=torch.int32, device="cuda")
         mb = torch.empty_like(sb)
-        xb = torch.empty((n, hw, hw, cin), dtype=torch.bfloat16, device="cuda")
+        xb = torch.empty((n, hw, hw, cin), dtype=torch.int16, device="cuda")
+        gname, GC, GH, FMT = grad_mode()
         alpha = torch.empty(cout, device="cuda")
         ws = torch.empty((cout, 9, cw), dtype=torch.int32, device="cuda")
         wm = torch.empty(((w.numel() + 31) // 32,), dtype=torch.int32, device="cuda")
-        wf = torch.empty((cout, 9, cin), dtype=torch.bfloat16, device="cuda")
-        wt = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device="cuda")
+        wf = torch.empty((cout, 9, cin), dtype=torch.int16, device="cuda")
+        wt = torch.empty((cin, 9, cout), dtype=torch.int16, device="cuda")
+        amax = torch.zeros(1, dtype=torch.int32, device="cuda")
         gs, igs = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
         y = torch.empty((n, sh.Ho, sh.Wo, cout), device="cuda")
         gy = torch.randn_like(y)
-        GH = int(os.environ.get("BDBNN_GRAD_HALVES", "2"))
-        gys = torch.empty(y.shape[:3] + (GH * cout,), dtype=torch.bfloat16, device="cuda")
+        gys = torch.empty(y.shape[:3] + (GH * cout,), dtype=torch.int16, device="cuda")
         gx = torch.empty_like(x)
         gw = torch.empty_like(w)
         st = _stream()
@@ -78,19 +79,19 @@ def main():
         tc = bool(caps & 1)
         ck = _lib.check
         kernels = {
-            "act_pack" + ("_tc" if tc else ""): lambda: ck(L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb if tc else None), st), "p"),
-            "weight_pack": lambda: ck(L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(gs), _p(igs), st), "w"),
+            "act_pack" + ("_tc" if tc else ""): lambda: ck(L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb if tc else None), FMT, st), "p"),
+            "weight_pack": lambda: ck(L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(gs), _p(igs), FMT, st), "w"),
         }
         if tc:
             nb = int(L.bdbnn_wgrad_tc_workspace_bytes(shp))
             wsb = torch.empty(max(nb, 4) // 4, device="cuda")
             kernels.update({
-                "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), shp, st), "f"),
-                "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, GH, _p(gys), st), "g"),
-                "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), GH, _p(wt), _p(mb), _p(gx), shp, st), "d"),
+                "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), FMT, _p(alpha), _p(y), shp, st), "f"),
+                "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, GC, _p(amax), _p(gys), st), "g"),
+                "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), GC, _p(amax), _p(wt), _p(mb), _p(gx), shp, st), "d"),
             })
             if caps & 4:
-                kernels["wgrad_tc"] = lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), GH, _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w")
+                kernels["wgrad_tc"] = lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), GC, _p(amax), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w")
             else:
                 kernels["wgrad"] = lambda: ck(L.bdbnn_binconv_wgrad(_p(gy), _p(sb), _p(wm), _p(gw), shp, st), "w")
         else:

@@ -22,11 +22,11 @@ gs = torch.empty(cout, device="cuda"); igs = torch.empty(cout, device="cuda")
 y = torch.empty((n, hw, hw, cout), device="cuda"); gy = torch.randn_like(y)
 gys = torch.empty((n, hw, hw, 2 * cout), dtype=torch.bfloat16, device="cuda"); gx = torch.empty_like(x)
 st = _stream(); shp = ctypes.byref(sh)
-L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb), st)
-L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(gs), _p(igs), st)
-L.bdbnn_grad_pack(_p(gy), _p(gs), n * hw * hw, cout, 2, _p(gys), st)
-run = (lambda: L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), _p(alpha), _p(y), shp, st)) if which == "fwd" else \
-      (lambda: L.bdbnn_binconv_dgrad_tc(_p(gys), 2, _p(wt), _p(mb), _p(gx), shp, st))
+L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb), 1, st)
+L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(gs), _p(igs), 1, st)
+L.bdbnn_grad_pack(_p(gy), _p(gs), n * hw * hw, cout, 2, _p(None), _p(gys), st)
+run = (lambda: L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), 1, _p(alpha), _p(y), shp, st)) if which == "fwd" else \
+      (lambda: L.bdbnn_binconv_dgrad_tc(_p(gys), 2, _p(None), _p(wt), _p(mb), _p(gx), shp, st))
 run(); torch.cuda.synchronize()
 tr = torch.zeros(3 * 2048, dtype=torch.int64, device="cuda")
 L.bdbnn_debug_trace(_p(tr)); run(); torch.cuda.synchronize(); L.bdbnn_debug_trace(None)

@@ -50,8 +50,10 @@ def test_act_pack_bit_exact(shape, with_bf16):
     cw = (c + 31) // 32
     sb = torch.full((n, h, w, cw), -1, dtype=torch.int32, device="cuda")
     mb = torch.full((n, h, w, cw), -1, dtype=torch.int32, device="cuda")
-    xb = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device="cuda") if with_bf16 else None
-    _lib.check(L.bdbnn_act_pack(_p(xc), n * h * w, c, _p(sb), _p(mb), _p(xb), _stream()), "act_pack")
+    fmt = 1 if sum(shape) % 2 else 0            # alternate bf16 / fp16 encodings of +-1
+    xdt = torch.bfloat16 if fmt == 1 else torch.float16
+    xb = torch.zeros((n, h, w, c), dtype=xdt, device="cuda") if with_bf16 else None
+    _lib.check(L.bdbnn_act_pack(_p(xc), n * h * w, c, _p(sb), _p(mb), _p(xb), fmt, _stream()), "act_pack")
     torch.cuda.synchronize()
     assert torch.equal(_as_u32(sb), B.pack_bits_nhwc(x))
     assert torch.equal(_as_u32(mb), B.pack_mask_nhwc(x))
@@ -62,13 +64,14 @@ def test_act_pack_bit_exact(shape, with_bf16):
 def test_act_pack_empty_is_ok():
     _lib, L, _p, _stream, _ = _env()
     e = torch.empty(0, device="cuda")
-    assert L.bdbnn_act_pack(_p(e), 0, 64, _p(e), _p(e), _p(None), _stream()) == 0
+    assert L.bdbnn_act_pack(_p(e), 0, 64, _p(e), _p(e), _p(None), 1, _stream()) == 0
 
 
 def test_bad_arguments_return_error_codes():
     _lib, L, _p, _stream, conv_shape = _env()
     e = torch.empty(4, device="cuda")
-    assert L.bdbnn_act_pack(_p(e), 4, 0, _p(e), _p(e), _p(None), _stream()) == -1
+    assert L.bdbnn_act_pack(_p(e), 4, 0, _p(e), _p(e), _p(None), 1, _stream()) == -1
+    assert L.bdbnn_act_pack(_p(e), 4, 32, _p(e), _p(e), _p(None), 7, _stream()) == -1
     assert b"act_pack" in L.bdbnn_last_error_string()
     sh = conv_shape((1, 4, 5, 5), (4, 4, 3, 3), 1, 1)
     sh.Ho = 7
@@ -96,12 +99,14 @@ def test_weight_pack(shape):
     alpha = torch.empty(cout, device="cuda")
     ws = torch.empty((cout, T, cw), dtype=torch.int32, device="cuda")
     wm = torch.empty(((wt.numel() + 31) // 32,), dtype=torch.int32, device="cuda")
-    wf = torch.empty((cout, T, cin), dtype=torch.bfloat16, device="cuda")
-    wtt = torch.empty((cin, T, cout), dtype=torch.bfloat16, device="cuda")
+    fmt = 1 if sum(shape) % 2 else 0
+    wdt = torch.bfloat16 if fmt == 1 else torch.float16
+    wf = torch.empty((cout, T, cin), dtype=wdt, device="cuda")
+    wtt = torch.empty((cin, T, cout), dtype=wdt, device="cuda")
     gs = torch.empty(cout, device="cuda")
     igs = torch.empty(cout, device="cuda")
     _lib.check(L.bdbnn_weight_pack(_p(wd), cout, cin, kh, kw, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wtt),
-                                   _p(gs), _p(igs), _stream()), "weight_pack")
+                                   _p(gs), _p(igs), fmt, _stream()), "weight_pack")
     torch.cuda.synchronize()
     a_ref = B.weight_alpha(wt.double()).float()
     torch.testing.assert_close(alpha.cpu(), a_ref, rtol=2e-6, atol=0)

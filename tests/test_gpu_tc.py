@@ -56,15 +56,20 @@ def test_fwd_tc_equals_xnor_bit_exact_and_oracle(shape):
     torch.testing.assert_close(y_tc.cpu(), ref, rtol=3e-6, atol=0)
 
 
-@pytest.mark.parametrize("halves", [2, 1])
+GRAD_TOL = {"fp16s": 1.5e-3, "bf16x2": 5e-5, "bf16": 1e-2}
+
+
+@pytest.mark.parametrize("mode", ["fp16s", "bf16x2", "bf16"])
 @pytest.mark.parametrize("shape", TC_SHAPES)
-def test_backward_tc_vs_oracle(shape, halves, monkeypatch):
-    """Weights are +-1 and accumulation is fp32, so the only rounding is gy*gscale -> bf16.
-    halves=2 (default): hi+lo bf16 pair, 16 mantissa bits -> tolerance 5e-5 of max|ref|.
-    halves=1: single bf16 (2^-9 per element, random sign) -> tolerance 1e-2 of max|ref|."""
+def test_backward_tc_vs_oracle(shape, mode, monkeypatch):
+    """Weights are +-1 and accumulation is fp32, so the only rounding is that of gy*gscale:
+    fp16s  (default): fp16 with a per-call power-of-two scale, 11 significand bits (= TF32, which is
+                      what cuDNN gives the reference by default)      -> 1.5e-3 of max|ref| (observed ~3e-4)
+    bf16x2          : bf16 hi+lo pair, 16 bits                        -> 5e-5
+    bf16            : single bf16, 8 bits                             -> 1e-2."""
     from bdbnn_b200.functional import binconv2d
-    monkeypatch.setenv("BDBNN_GRAD_HALVES", str(halves))
-    tol = 5e-5 if halves == 2 else 1e-2
+    monkeypatch.setenv("BDBNN_GRAD_MODE", mode)
+    tol = GRAD_TOL[mode]
     caps = _caps(shape)
     assert caps & 2
     n, cin, h, w, cout, k, stride, pad = shape
@@ -87,7 +92,7 @@ def test_backward_tc_vs_oracle(shape, halves, monkeypatch):
     assert (wd.grad.cpu()[wt.abs() > 1] == 0).all()
     # exactness check of the data path: gy representable in bf16 and alpha a power of two -> exact dgrad
     wt2 = B.sign_pm1(torch.randn(cout, cin, k, k, generator=g)) * 0.5
-    gy2 = torch.randint(-8, 9, y.shape, generator=g).float()
+    gy2 = torch.randint(-8, 9, y.shape, generator=g).float() * 2.0 ** -20   # tiny grads: exercises the scale
     xd2 = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
     y2 = binconv2d(xd2, wt2.cuda(), stride, pad, "tc")
     y2.backward(gy2.cuda())
