@@ -397,3 +397,39 @@ class _KDLayerMulti(torch.autograd.Function):
 def kd_layer_loss(student_weights, teacher_weights):
     """Student/teacher weight lists of equal length and matching shapes -> 0-d loss."""
     return _KDLayerMulti.apply(len(student_weights), *student_weights, *teacher_weights)
+
+
+class _MaxPoolNHWC(torch.autograd.Function):
+    """torch.nn.MaxPool2d on NHWC fp32 with a one-byte winner index and a gather backward."""
+
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        _require_cuda(x, "max_pool2d_nhwc")
+        n, c, h, w = x.shape
+        if c % 4:
+            raise RuntimeError("max_pool2d_nhwc: channel count must be a multiple of 4")
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        xc = _nhwc(x.detach())
+        y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device)
+        _lib.check(_lib.lib().bdbnn_maxpool_fwd(_p(xc), _p(y), _p(idx), n, h, w, c, k, stride, pad, ho, wo, _stream()),
+                   "maxpool_fwd")
+        _lib.count(1)
+        ctx.geom = (n, h, w, c, k, stride, pad, ho, wo)
+        ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (idx,) = ctx.saved_tensors
+        n, h, w, c, k, stride, pad, ho, wo = ctx.geom
+        g = _nhwc(gy)
+        gx = torch.empty((n, c, h, w), dtype=torch.float32, device=gy.device, memory_format=torch.channels_last)
+        _lib.check(_lib.lib().bdbnn_maxpool_bwd(_p(g), _p(idx), _p(gx), n, h, w, c, k, stride, pad, ho, wo, _stream()),
+                   "maxpool_bwd")
+        _lib.count(1)
+        return gx, None, None, None
+
+
+def max_pool2d_nhwc(x, kernel_size, stride, padding):
+    return _MaxPoolNHWC.apply(x, int(kernel_size), int(stride), int(padding))

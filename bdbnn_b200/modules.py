@@ -17,7 +17,7 @@ forward(x[N,Cin,H,W]) -> [N,Cout,Ho,Wo], differentiable through torch.autograd.
 import torch
 import torch.nn as nn
 
-from .functional import binconv2d
+from .functional import binconv2d, max_pool2d_nhwc
 
 
 class BinarizeConv2d(nn.Conv2d):
@@ -67,3 +67,17 @@ class HardBinaryConv_cifar(BinarizeConv2d):
 
     def __init__(self, in_chn, out_chn, kernel_size=3, stride=1, padding=1, **kw):
         super().__init__(in_chn, out_chn, kernel_size, stride, padding, **kw)
+
+
+class MaxPool2dNHWC(nn.Module):
+    """nn.MaxPool2d(kernel_size, stride, padding) semantics on channels_last CUDA tensors."""
+
+    def __init__(self, kernel_size, stride=None, padding=0):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = kernel_size, stride or kernel_size, padding
+
+    def forward(self, x):
+        return max_pool2d_nhwc(x, self.kernel_size, self.stride, self.padding)
+
+    def extra_repr(self):
+        return f"kernel_size={self.kernel_size}, stride={self.stride}, padding={self.padding}"

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .modules import HardBinaryConv, HardBinaryConv_cifar
+from .modules import HardBinaryConv, HardBinaryConv_cifar, MaxPool2dNHWC
 
 
 class BasicBlock(nn.Module):
@@ -35,12 +35,12 @@ class BasicBlock(nn.Module):
 class ResNetImageNet(nn.Module):
     """ResNet-18/34 for 224x224 inputs; binary 3x3 convs, fp32 stem / 1x1 shortcuts / classifier."""
 
-    def __init__(self, layers, num_classes=1000, conv_cls=HardBinaryConv):
+    def __init__(self, layers, num_classes=1000, conv_cls=HardBinaryConv, pool_cls=MaxPool2dNHWC):
         super().__init__()
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
-        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.maxpool = pool_cls(kernel_size=3, stride=2, padding=1)
         self.layer1 = self._make_layer(64, layers[0], 1, conv_cls)
         self.layer2 = self._make_layer(128, layers[1], 2, conv_cls)
         self.layer3 = self._make_layer(256, layers[2], 2, conv_cls)

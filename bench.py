@@ -388,14 +388,19 @@ def main():
                "sample": f"2 timed steps (1 warm-up) of a {cb}-image slice of the {batch}-image batch, "
                          f"{ms:.0f} ms/step, oracle CPU step"}
 
+    from bdbnn_b200.functional import grad_mode
+    gname = grad_mode()[0]
+    dtype_str = {"fp16s": "f16 (+-1 operands exact; gradient = fp16 x per-call 2^e scale), f32 accumulate",
+                 "bf16x2": "bf16 (+-1 operands exact; gradient = bf16 hi+lo pair), f32 accumulate",
+                 "bf16": "bf16 (+-1 operands exact; gradient = bf16), f32 accumulate"}[gname]
     line = {"metric": "images/sec", "value": round(value, 2), "unit": "images/sec", "n_gpus": world,
             "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 (+-1 fwd operands exact; gradient as bf16 hi+lo pair), fp32 accumulate",
+            "dtype": dtype_str,
             "data": "synthetic",
             "config": {"workload": workload, "global_batch": batch * world,
                        "parallelism": f"dp{world}", "optimizer": "Adam (train.py:323-336)" if dataset == "imagenet"
-                       else "SGD (train.py:319-321)", "conv_impl": args.conv_impl or "auto",
+                       else "SGD (train.py:319-321)", "conv_impl": args.conv_impl or "auto", "grad_mode": gname,
                        "l2_policy": "per-step working set (>3 GB of activations) exceeds the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "kernels": kernels, "cpu_baseline": cpu}

@@ -179,6 +179,17 @@ BDBNN_API int bdbnn_kd_layer_multi_bwd(const float* const* wt_ptrs_host, const i
                              int32_t L, const float* gout, float* const* grad_ptrs_host,
                              int32_t accumulate, void* stream);
 
+/* ---- NHWC max-pool (stem of the ImageNet shells; torch.nn.MaxPool2d semantics) --------------------
+ * Caller side of the path (the ops either side of the binary convs).  x,y,gy,gx fp32
+ * NHWC, C % 4 == 0; idx = winning tap (r*k+s) per output element, one byte each [N,Ho,Wo,C].
+ * First maximum in scan order wins, NaN propagates; backward is a gather (deterministic, no atomics). */
+BDBNN_API int bdbnn_maxpool_fwd(const float* x, float* y, uint8_t* idx, int32_t N, int32_t H, int32_t W,
+                      int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t Ho, int32_t Wo,
+                      void* stream);
+BDBNN_API int bdbnn_maxpool_bwd(const float* gy, const uint8_t* idx, float* gx, int32_t N, int32_t H,
+                      int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t Ho, int32_t Wo,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,7 @@
 pure-PyTorch RefBinarizeConv2d, plus pure-PyTorch loss ops for the shared TrainStep driver.
 This is the CPU implementation `bench.py --impl reference` times."""
 import torch
+import torch.nn as nn
 
 from bdbnn_b200 import resnet as _resnet
 from bdbnn_b200.losses import matched_weight_pairs
@@ -11,11 +12,11 @@ from . import losses_ref
 
 
 def resnet18_ref(**kw):
-    return _resnet.ResNetImageNet([2, 2, 2, 2], conv_cls=RefBinarizeConv2d, **kw)
+    return _resnet.ResNetImageNet([2, 2, 2, 2], conv_cls=RefBinarizeConv2d, pool_cls=nn.MaxPool2d, **kw)
 
 
 def resnet34_ref(**kw):
-    return _resnet.ResNetImageNet([3, 4, 6, 3], conv_cls=RefBinarizeConv2d, **kw)
+    return _resnet.ResNetImageNet([3, 4, 6, 3], conv_cls=RefBinarizeConv2d, pool_cls=nn.MaxPool2d, **kw)
 
 
 def resnet20_ref(**kw):

@@ -291,3 +291,29 @@ def test_kd_layer_matches_reference_golden():
                 assert p.grad is None
             else:
                 torch.testing.assert_close(p.grad.cpu(), gref * 200.0, rtol=2e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("geom", [(2, 64, 16, 16, 3, 2, 1), (1, 8, 7, 9, 3, 2, 1), (2, 4, 6, 6, 2, 2, 0),
+                                  (1, 16, 9, 9, 3, 1, 1), (1, 64, 112, 112, 3, 2, 1)])
+def test_maxpool_nhwc_matches_torch(geom):
+    from bdbnn_b200.functional import max_pool2d_nhwc
+    import torch.nn.functional as F
+    n, c, h, w, k, s, p = geom
+    g = torch.Generator().manual_seed(sum(geom))
+    x = torch.randn(n, c, h, w, generator=g)
+    x[0, 0, 0, 0] = float("nan")
+    x[0, 1, :, :] = 0.5                                   # ties everywhere in this plane
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    y = max_pool2d_nhwc(xd, k, s, p)
+    yr = F.max_pool2d(xr, k, s, p)
+    assert torch.equal(torch.nan_to_num(y.cpu(), nan=7.0), torch.nan_to_num(yr.detach(), nan=7.0))
+    gy = torch.randn(yr.shape, generator=g)
+    y.backward(gy.cuda())
+    yr.backward(gy)
+    # tie plane: the gradient mass per window must match even if the tie-break differs; elsewhere exact
+    gd, gr = xd.grad.cpu(), xr.grad
+    sel = torch.ones(c, dtype=torch.bool); sel[1] = False
+    gd0, gr0 = torch.nan_to_num(gd[:, sel]), torch.nan_to_num(gr[:, sel])
+    torch.testing.assert_close(gd0, gr0, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(gd[:, 1].sum(), gr[:, 1].sum(), rtol=1e-5, atol=1e-5)
