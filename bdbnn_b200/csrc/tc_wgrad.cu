@@ -341,7 +341,9 @@ static WgradPlan plan_wgrad(const bdbnn_conv_shape* s, int halves) {
   p.n_kboxes = p.tiles_h * ((s->N + p.BNI - 1) / p.BNI);
   pl.mgroups = (n_mtiles + p.G - 1) / p.G;
   pl.ntiles = s->Cout / p.BN;
-  int ks = (num_sms() + pl.mgroups * pl.ntiles - 1) / (pl.mgroups * pl.ntiles);
+  // split K so that the whole grid is ONE wave (<= #SMs CTAs): 1 CTA/SM by shared-memory size, and a
+  // second partial wave would double the kernel time
+  int ks = num_sms() / (pl.mgroups * pl.ntiles);
   if (ks < 1) ks = 1;
   if (ks > p.n_kboxes) ks = p.n_kboxes;
   p.kboxes_per_cta = (p.n_kboxes + ks - 1) / ks;
