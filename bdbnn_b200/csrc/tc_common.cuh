@@ -279,6 +279,7 @@ struct TcConvLaunch {
 // does not qualify (caller falls back to the one-tile-per-CTA kernel in tc_conv.cu).
 int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st);
 void set_tc_trace(long long* buf);
+long long* get_tc_trace();
 bool wgrad_tc_ok(const bdbnn_conv_shape* s);
 
 }  // namespace bdbnn

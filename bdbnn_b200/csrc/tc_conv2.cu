@@ -326,6 +326,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 static long long* g_trace = nullptr;
 void set_tc_trace(long long* buf) { g_trace = buf; }
+long long* get_tc_trace() { return g_trace; }
 
 // mode: 0 = alpha epilogue (forward), 1 = STE-mask epilogue (dgrad)
 int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {

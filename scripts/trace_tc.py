@@ -25,7 +25,11 @@ st = _stream(); shp = ctypes.byref(sh)
 L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb), 1, st)
 L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(gs), _p(igs), 1, st)
 L.bdbnn_grad_pack(_p(gy), _p(gs), n * hw * hw, cout, 2, _p(None), _p(gys), st)
-run = (lambda: L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), 1, _p(alpha), _p(y), shp, st)) if which == "fwd" else \
+nb = int(L.bdbnn_wgrad_tc_workspace_bytes(shp)); wsb = torch.empty(max(nb, 4) // 4, device="cuda"); gw = torch.empty_like(w)
+if which == "wgrad":
+    run = lambda: L.bdbnn_binconv_wgrad_tc(_p(gys), 2, _p(None), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st)
+else:
+  run = (lambda: L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), 1, _p(alpha), _p(y), shp, st)) if which == "fwd" else \
       (lambda: L.bdbnn_binconv_dgrad_tc(_p(gys), 2, _p(None), _p(wt), _p(mb), _p(gx), shp, st))
 run(); torch.cuda.synchronize()
 tr = torch.zeros(3 * 2048, dtype=torch.int64, device="cuda")
@@ -33,7 +37,7 @@ L.bdbnn_debug_trace(_p(tr)); run(); torch.cuda.synchronize(); L.bdbnn_debug_trac
 t = tr.cpu().view(3, 1024, 2)
 t0 = min(int(t[r, 0, 1]) for r in range(3) if int(t[r, 0, 1]) > 0)
 names = {0: {0: "P.wait_pempty", 1: "P.got_pempty", 2: "P.issued_kb"},
-         1: {0: "M.wait_tempty", 1: "M.got_tempty", 2: "M.got_patch", 3: "M.got_B0", 4: "M.item_committed"},
+         1: {0: "M.wait", 1: "M.got", 2: "M.got_patch", 3: "M.got_B0", 4: "M.committed"},
          2: {0: "E.wait_tfull", 1: "E.got_tfull", 2: "E.done"}}
 ev = []
 for r in range(3):
