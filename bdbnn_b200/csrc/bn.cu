@@ -1,0 +1,325 @@
+// Fused BatchNorm(train) + residual add + sign/pack around the binary conv ("the
+// step either side of the conv").  The binary conv writes y; these kernels replace the cuDNN BN
+// forward/backward, the ATen residual adds and the separate act_pack / grad_amax / grad_pack passes:
+//
+//   forward : bn_stats (1 read of y)  ->  bn_finalize ([C] math + running stats)
+//             bn_apply_add_pack: z = y*a[c] + b[c] (+ residual)  [+ sign bits, STE mask bits and the +-1
+//             16-bit copy of z, i.e. the NEXT conv's act_pack, in the same pass]
+//   backward: bn_bwd_reduce (1 read of gz,y: sum gz, sum gz*yhat, max|gz| per channel)
+//             bn_bwd_bound  ([C] math: dgamma, dbeta, per-channel constants, FP16S scale from a bound)
+//             bn_bwd_pack   (1 read of gz,y -> gys = 16-bit operand of dgrad_tc / wgrad_tc; the fp32
+//                            conv-output gradient is never materialised)
+// Per element: forward 4 + 12(+2.25) bytes instead of 12 (BN) + 12 (add) + 6.25 (pack);
+//              backward 8 + 10 bytes instead of ~20 (BN bwd) + 4 (amax) + 6 (pack).
+// All tensors fp32 NHWC [n_pix][C], C % 4 == 0 (packing: C % 32 == 0).
+#include "common.cuh"
+
+namespace bdbnn {
+
+constexpr int kBnThreads = 256;
+
+__device__ __forceinline__ uint32_t bn_pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t bn_pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bn_bf16_round(float v) {
+  return __uint_as_float(bn_pack_bf16x2(0.f, v) & 0xffff0000u);
+}
+
+// Per-channel (sum a, sum b, max c) over pixels; thread = one float4 channel group, strided over pixels.
+// Block partials go through shared-memory atomics, then one double atomicAdd per channel per block.
+template <bool BWD>
+__global__ void __launch_bounds__(kBnThreads)
+bn_reduce_kernel(const float4* __restrict__ p0, const float4* __restrict__ p1, const float* __restrict__ mean,
+                 const float* __restrict__ invstd, int64_t n_pix, int C4, double* __restrict__ sums,
+                 uint32_t* __restrict__ maxbits) {
+  extern __shared__ float sh[];               // [3][C]
+  const int C = C4 * 4;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int64_t gtid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;   // multiple of C4 (host guarantees)
+  const int c4 = int(gtid % C4);
+  const int64_t p_step = nthreads / C4;
+  float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
+  if (BWD) {
+    mu = *reinterpret_cast<const float4*>(mean + c4 * 4);
+    is = *reinterpret_cast<const float4*>(invstd + c4 * 4);
+  }
+  float4 sa = make_float4(0, 0, 0, 0), sb = sa, mx = sa;
+  for (int64_t p = gtid / C4; p < n_pix; p += p_step) {
+    const float4 u = __ldg(p0 + p * C4 + c4);
+    if (BWD) {   // u = gz, v = y:  a = gz, b = gz * yhat, c = |gz|
+      const float4 v = __ldg(p1 + p * C4 + c4);
+      sa.x += u.x; sa.y += u.y; sa.z += u.z; sa.w += u.w;
+      sb.x += u.x * ((v.x - mu.x) * is.x); sb.y += u.y * ((v.y - mu.y) * is.y);
+      sb.z += u.z * ((v.z - mu.z) * is.z); sb.w += u.w * ((v.w - mu.w) * is.w);
+    } else {     // u = y:  a = y, b = y*y, c = |y|
+      sa.x += u.x; sa.y += u.y; sa.z += u.z; sa.w += u.w;
+      sb.x += u.x * u.x; sb.y += u.y * u.y; sb.z += u.z * u.z; sb.w += u.w * u.w;
+    }
+    mx.x = fmaxf(mx.x, fabsf(u.x)); mx.y = fmaxf(mx.y, fabsf(u.y));
+    mx.z = fmaxf(mx.z, fabsf(u.z)); mx.w = fmaxf(mx.w, fabsf(u.w));
+  }
+  const int c = c4 * 4;
+  atomicAdd(&sh[c + 0], sa.x); atomicAdd(&sh[c + 1], sa.y); atomicAdd(&sh[c + 2], sa.z); atomicAdd(&sh[c + 3], sa.w);
+  atomicAdd(&sh[C + c + 0], sb.x); atomicAdd(&sh[C + c + 1], sb.y);
+  atomicAdd(&sh[C + c + 2], sb.z); atomicAdd(&sh[C + c + 3], sb.w);
+  uint32_t* shm = reinterpret_cast<uint32_t*>(sh + 2 * C);   // non-negative floats order like uints
+  atomicMax(&shm[c + 0], __float_as_uint(mx.x)); atomicMax(&shm[c + 1], __float_as_uint(mx.y));
+  atomicMax(&shm[c + 2], __float_as_uint(mx.z)); atomicMax(&shm[c + 3], __float_as_uint(mx.w));
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(sums + i, double(sh[i]));
+    atomicAdd(sums + C + i, double(sh[C + i]));
+    atomicMax(maxbits + i, shm[i]);
+  }
+}
+
+// [C] math of the forward: mean, invstd, a = gamma*invstd, b = beta - mean*a, running statistics
+// (torch.nn.BatchNorm2d: biased variance for normalisation, unbiased for running_var).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n_pix, int C, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ a,
+                                   float* __restrict__ b, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = double(n_pix);
+  const double m = sums[c] / n;
+  double var = sums[C + c] / n - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = float(1.0 / sqrt(var + double(eps)));
+  const float mf = float(m);
+  mean[c] = mf;
+  invstd[c] = is;
+  const float av = gamma[c] * is;
+  a[c] = av;
+  b[c] = beta[c] - mf * av;
+  if (running_mean != nullptr) {
+    const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mf;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * float(unb);
+  }
+}
+
+// z = y*a + b (+ residual); optionally the sign / STE-mask bits and the +-1 16-bit copy of z.
+template <bool PACK>
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_add_pack_kernel(const float4* __restrict__ y, const float4* __restrict__ res,
+                         const float* __restrict__ a, const float* __restrict__ b, int64_t n4, int C4,
+                         float4* __restrict__ z, uint32_t* __restrict__ sign_bits,
+                         uint32_t* __restrict__ mask_bits, uint2* __restrict__ xb4, uint32_t one16) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t group_mask = 0xffu << (lane & 24);
+  const int sh = (lane & 7) * 4;
+  const uint32_t pos = one16, neg = one16 | 0x8000u;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;       // multiple of C4 (host guarantees)
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c4 = int(i % C4);                                     // constant per thread
+  const float4 av = *reinterpret_cast<const float4*>(a + c4 * 4);
+  const float4 bv = *reinterpret_cast<const float4*>(b + c4 * 4);
+  for (; i < n4; i += nthreads) {
+    const float4 v = __ldcs(y + i);
+    float4 o = make_float4(fmaf(v.x, av.x, bv.x), fmaf(v.y, av.y, bv.y), fmaf(v.z, av.z, bv.z),
+                           fmaf(v.w, av.w, bv.w));
+    if (res != nullptr) {
+      const float4 r = __ldg(res + i);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    z[i] = o;
+    if (PACK) {
+      const uint32_t s0 = o.x >= 0.0f, s1 = o.y >= 0.0f, s2 = o.z >= 0.0f, s3 = o.w >= 0.0f;
+      const uint32_t m0 = fabsf(o.x) <= 1.0f, m1 = fabsf(o.y) <= 1.0f, m2 = fabsf(o.z) <= 1.0f,
+                     m3 = fabsf(o.w) <= 1.0f;
+      const uint32_t sw = __reduce_or_sync(group_mask, (s0 | (s1 << 1) | (s2 << 2) | (s3 << 3)) << sh);
+      const uint32_t mw = __reduce_or_sync(group_mask, (m0 | (m1 << 1) | (m2 << 2) | (m3 << 3)) << sh);
+      if ((lane & 7) == 0) {
+        sign_bits[i >> 3] = sw;
+        mask_bits[i >> 3] = mw;
+      }
+      uint2 q;
+      q.x = (s0 ? pos : neg) | ((s1 ? pos : neg) << 16);
+      q.y = (s2 ? pos : neg) | ((s3 ? pos : neg) << 16);
+      xb4[i] = q;
+    }
+  }
+}
+
+// [C] math of the backward.  consts[c] = {m1, m2*invstd, mean, a*gscale}; gy*gscale = (gz - m1 -
+// (y-mean)*m2*invstd) * a*gscale.  FP16S scale from the bound
+//   |gy*gscale| <= |a*gscale| * (max|gz| + |m1| + (max|y| + |mean|)*invstd*|m2|).
+__global__ void bn_bwd_bound_kernel(const double* __restrict__ sums, const uint32_t* __restrict__ gmax_bits,
+                                    const uint32_t* __restrict__ ymax_bits, int64_t n_pix, int C,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ gscale,
+                                    float4* __restrict__ consts, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, uint32_t* __restrict__ amax_bits) {
+  __shared__ float red[32];
+  float bound = 0.f;
+  const double n = double(n_pix);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s1 = float(sums[c]), s2 = float(sums[C + c]);
+    dbeta[c] = s1;
+    dgamma[c] = s2;
+    const float m1 = float(sums[c] / n), m2 = float(sums[C + c] / n);
+    const float is = invstd[c], mu = mean[c];
+    const float A = gamma[c] * is * gscale[c];
+    consts[c] = make_float4(m1, m2 * is, mu, A);
+    const float ymax = __uint_as_float(ymax_bits[c]), gmax = __uint_as_float(gmax_bits[c]);
+    bound = fmaxf(bound, fabsf(A) * (gmax + fabsf(m1) + (ymax + fabsf(mu)) * is * fabsf(m2)));
+  }
+  bound = warp_max(bound);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bound;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < int(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    *amax_bits = __float_as_uint(m);
+  }
+}
+
+// gys = 16-bit operand of the conv backward, straight from gz and y.
+template <int MODE>
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_pack_kernel(const float4* __restrict__ gz, const float4* __restrict__ y, const float4* __restrict__ consts,
+                   const uint32_t* __restrict__ amax_bits, int64_t n4, int C4, uint16_t* __restrict__ out) {
+  constexpr int HALVES = MODE == 2 ? 2 : 1;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;       // multiple of C4
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c4 = int(i % C4);
+  const float up = MODE == 3 ? amax_pow2_scale(*amax_bits, false) : 1.0f;
+  const float4 k0 = consts[c4 * 4 + 0], k1 = consts[c4 * 4 + 1], k2 = consts[c4 * 4 + 2], k3 = consts[c4 * 4 + 3];
+  const int C = C4 * 4;
+  int64_t pix = i / C4;
+  const int64_t pix_step = nthreads / C4;
+  for (; i < n4; i += nthreads, pix += pix_step) {
+    const float4 g = __ldcs(gz + i);
+    const float4 v = __ldcs(y + i);
+    const float a0 = (g.x - k0.x - (v.x - k0.z) * k0.y) * k0.w * up;
+    const float a1 = (g.y - k1.x - (v.y - k1.z) * k1.y) * k1.w * up;
+    const float a2 = (g.z - k2.x - (v.z - k2.z) * k2.y) * k2.w * up;
+    const float a3 = (g.w - k3.x - (v.w - k3.z) * k3.y) * k3.w * up;
+    uint2 r;
+    if (MODE == 3) {
+      r.x = bn_pack_f16x2(a0, a1);
+      r.y = bn_pack_f16x2(a2, a3);
+    } else {
+      r.x = bn_pack_bf16x2(a0, a1);
+      r.y = bn_pack_bf16x2(a2, a3);
+    }
+    uint16_t* dst = out + pix * (int64_t(HALVES) * C) + c4 * 4;
+    *reinterpret_cast<uint2*>(dst) = r;
+    if (MODE == 2) {
+      uint2 l;
+      l.x = bn_pack_bf16x2(a0 - bn_bf16_round(a0), a1 - bn_bf16_round(a1));
+      l.y = bn_pack_bf16x2(a2 - bn_bf16_round(a2), a3 - bn_bf16_round(a3));
+      *reinterpret_cast<uint2*>(dst + C) = l;
+    }
+  }
+}
+
+static int bn_grid(int64_t work, int C4) {
+  // full-occupancy grid whose thread count is a multiple of C4 (C4 in {4,..,128} divides 256*k)
+  int64_t blocks = (work + kBnThreads - 1) / kBnThreads;
+  const int64_t cap = int64_t(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  while ((blocks * kBnThreads) % C4 != 0) ++blocks;
+  return int(blocks);
+}
+
+}  // namespace bdbnn
+
+using namespace bdbnn;
+
+static int bn_dims_ok(int64_t n_pix, int32_t C, bool pack) {
+  BDBNN_REQUIRE(n_pix > 0 && C > 0 && (C & 3) == 0, "bn: C must be a positive multiple of 4");
+  BDBNN_REQUIRE(C <= 4096, "bn: C too large");
+  BDBNN_REQUIRE(!pack || (C & 31) == 0, "bn: packing needs C %% 32 == 0");
+  return BDBNN_OK;
+}
+
+extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* gamma, const float* beta,
+                            int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
+                            float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean,
+                            float* invstd, float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits,
+                            uint16_t* xb, int32_t fmt, void* stream) {
+  const bool pack = sign_bits != nullptr;
+  int rc = bn_dims_ok(n_pix, C, pack);
+  if (rc) return rc;
+  BDBNN_REQUIRE(y && gamma && beta && sums_ws && ymax_bits && mean && invstd && ab_ws && z, "bn_fwd: NULL pointer");
+  BDBNN_REQUIRE(!pack || (mask_bits && xb), "bn_fwd: packing needs sign_bits, mask_bits and xb");
+  BDBNN_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_fwd: running stats come in pairs");
+  cudaStream_t st = cudaStream_t(stream);
+  const int C4 = C / 4;
+  BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
+  BDBNN_CUDA(cudaMemsetAsync(ymax_bits, 0, size_t(C) * sizeof(uint32_t), st));
+  bn_reduce_kernel<false><<<bn_grid(n_pix * C4, C4), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+      reinterpret_cast<const float4*>(y), nullptr, nullptr, nullptr, n_pix, C4, sums_ws, ymax_bits);
+  rc = check_launch("bn_reduce_kernel<fwd>");
+  if (rc) return rc;
+  float* a = ab_ws;
+  float* b = ab_ws + C;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_ws, n_pix, C, eps, gamma, beta, mean, invstd, a, b,
+                                                       running_mean, running_var, momentum);
+  rc = check_launch("bn_finalize_kernel");
+  if (rc) return rc;
+  const int64_t n4 = n_pix * C4;
+  const int grid = bn_grid(n4, C4);
+  if (pack) {
+    const uint32_t one16 = fmt == BDBNN_FMT_FP16 ? 0x3C00u : 0x3F80u;
+    bn_apply_add_pack_kernel<true><<<grid, kBnThreads, 0, st>>>(
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(residual), a, b, n4, C4,
+        reinterpret_cast<float4*>(z), sign_bits, mask_bits, reinterpret_cast<uint2*>(xb), one16);
+  } else {
+    bn_apply_add_pack_kernel<false><<<grid, kBnThreads, 0, st>>>(
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(residual), a, b, n4, C4,
+        reinterpret_cast<float4*>(z), nullptr, nullptr, nullptr, 0u);
+  }
+  return check_launch("bn_apply_add_pack_kernel");
+}
+
+extern "C" int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* mean, const float* invstd,
+                                 const float* gamma, const float* gscale, const uint32_t* ymax_bits,
+                                 int64_t n_pix, int32_t C, int32_t grad_mode, double* sums_ws,
+                                 uint32_t* gmax_bits, float* consts_ws, float* dgamma, float* dbeta,
+                                 uint32_t* amax_bits, uint16_t* gys, void* stream) {
+  int rc = bn_dims_ok(n_pix, C, false);
+  if (rc) return rc;
+  BDBNN_REQUIRE(gz && y && mean && invstd && gamma && gscale && ymax_bits && sums_ws && gmax_bits && consts_ws &&
+                    dgamma && dbeta && amax_bits && gys,
+                "bn_bwd_pack: NULL pointer");
+  BDBNN_REQUIRE(grad_mode >= BDBNN_GRAD_BF16 && grad_mode <= BDBNN_GRAD_FP16S, "bn_bwd_pack: bad grad_mode");
+  cudaStream_t st = cudaStream_t(stream);
+  const int C4 = C / 4;
+  BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
+  BDBNN_CUDA(cudaMemsetAsync(gmax_bits, 0, size_t(C) * sizeof(uint32_t), st));
+  bn_reduce_kernel<true><<<bn_grid(n_pix * C4, C4), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+      reinterpret_cast<const float4*>(gz), reinterpret_cast<const float4*>(y), mean, invstd, n_pix, C4, sums_ws,
+      gmax_bits);
+  rc = check_launch("bn_reduce_kernel<bwd>");
+  if (rc) return rc;
+  bn_bwd_bound_kernel<<<1, 256, 0, st>>>(sums_ws, gmax_bits, ymax_bits, n_pix, C, mean, invstd, gamma, gscale,
+                                         reinterpret_cast<float4*>(consts_ws), dgamma, dbeta, amax_bits);
+  rc = check_launch("bn_bwd_bound_kernel");
+  if (rc) return rc;
+  const int64_t n4 = n_pix * C4;
+  const int grid = bn_grid(n4, C4);
+  const float4* g4 = reinterpret_cast<const float4*>(gz);
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  const float4* k4 = reinterpret_cast<const float4*>(consts_ws);
+  if (grad_mode == BDBNN_GRAD_FP16S)
+    bn_bwd_pack_kernel<3><<<grid, kBnThreads, 0, st>>>(g4, y4, k4, amax_bits, n4, C4, gys);
+  else if (grad_mode == BDBNN_GRAD_BF16X2)
+    bn_bwd_pack_kernel<2><<<grid, kBnThreads, 0, st>>>(g4, y4, k4, amax_bits, n4, C4, gys);
+  else
+    bn_bwd_pack_kernel<1><<<grid, kBnThreads, 0, st>>>(g4, y4, k4, amax_bits, n4, C4, gys);
+  return check_launch("bn_bwd_pack_kernel");
+}

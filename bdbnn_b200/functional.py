@@ -433,3 +433,149 @@ class _MaxPoolNHWC(torch.autograd.Function):
 
 def max_pool2d_nhwc(x, kernel_size, stride, padding):
     return _MaxPoolNHWC.apply(x, int(kernel_size), int(stride), int(padding))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Fused unit: z = BatchNorm_train(binconv(x)) + residual, emitting the next conv's packs (csrc/bn.cu)
+# ---------------------------------------------------------------------------------------------------
+_FUSE_ENV = "BDBNN_FUSE_BN"     # 1 (default) | 0
+
+
+def fuse_enabled():
+    return os.environ.get(_FUSE_ENV, "1") != "0"
+
+
+def unit_supported(x_shape, w_shape, stride, padding):
+    """The fused unit needs all three tcgen05 kernels for the conv shape."""
+    sh = conv_shape(x_shape, w_shape, stride, padding)
+    return int(_lib.lib().bdbnn_tc_supported(ctypes.byref(sh))) == 7
+
+
+class _ConvBNAddUnit(torch.autograd.Function):
+    """forward : [act_pack(x) unless packs are handed in] -> weight_pack -> fwd_tc -> bn_fwd(+residual, +pack of z)
+    backward: bn_bwd_pack(gz, y) -> dgrad_tc, wgrad_tc ; residual grad = gz."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride,
+                padding, xs, xm, xb):
+        _require_cuda(x, "conv_bn_add(x)")
+        L = _lib.lib()
+        sh = conv_shape(x.shape, weight.shape, stride, padding)
+        dev = x.device
+        n, cin, h, wd = x.shape
+        cout, _, kh, kw = weight.shape
+        cw, T = (cin + 31) // 32, kh * kw
+        st = _stream()
+        gname, gcode, ghalves, fmt = grad_mode()
+        key = _shape_key(sh)
+        i32 = dict(dtype=torch.int32, device=dev)
+        if xs is None:
+            xc = _nhwc(x.detach())
+            xs = torch.empty((n, h, wd, cw), **i32)
+            xm = torch.empty((n, h, wd, cw), **i32)
+            xb = torch.empty((n, h, wd, cin), dtype=torch.int16, device=dev)
+            with _timed("act_pack", key, algorithmic_bytes("act_pack_tc", sh)):
+                _lib.check(L.bdbnn_act_pack(_p(xc), n * h * wd, cin, _p(xs), _p(xm), _p(xb), fmt, st), "act_pack")
+            _lib.count(1)
+        w = weight.detach().contiguous()
+        alpha = torch.empty((cout,), dtype=torch.float32, device=dev)
+        wsign = torch.empty((cout, T, cw), **i32)
+        wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
+        wf = torch.empty((cout, T, cin), dtype=torch.int16, device=dev)
+        wt = torch.empty((cin, T, cout), dtype=torch.int16, device=dev)
+        gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
+        inv_gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
+        _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask), _p(wf), _p(wt),
+                                       _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
+        y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
+                        memory_format=torch.channels_last)
+        with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
+            _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), st),
+                       "binconv_fwd_tc")
+        _lib.count(3)
+        n_pix = n * sh.Ho * sh.Wo
+        rc = _nhwc(residual.detach()) if residual is not None else None
+        z = torch.empty_like(y)
+        sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
+        ymax = torch.empty((cout,), **i32)
+        mean = torch.empty((cout,), dtype=torch.float32, device=dev)
+        invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
+        ab = torch.empty((2 * cout,), dtype=torch.float32, device=dev)
+        pack = cout % 32 == 0
+        zs = torch.empty((n, sh.Ho, sh.Wo, cout // 32), **i32) if pack else None
+        zm = torch.empty((n, sh.Ho, sh.Wo, cout // 32), **i32) if pack else None
+        zb = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.int16, device=dev) if pack else None
+        with _timed("bn_fwd", key, (4 + 12 + (2.25 if pack else 0)) * n_pix * cout):
+            _lib.check(L.bdbnn_bn_fwd(_p(y), _p(rc), _p(gamma.detach()), _p(beta.detach()), n_pix, cout, float(eps),
+                                      float(momentum), _p(running_mean), _p(running_var), _p(sums), _p(ymax),
+                                      _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm), _p(zb), fmt, st), "bn_fwd")
+        _lib.count(3)
+        ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
+        ctx.shapes = (tuple(x.shape), tuple(weight.shape))
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale)
+        if pack:
+            ctx.mark_non_differentiable(zs, zm, zb)
+            return z, zs, zm, zb
+        return z, None, None, None
+
+    @staticmethod
+    def backward(ctx, gz, _g1, _g2, _g3):
+        L = _lib.lib()
+        sh = ctx.sh
+        st = _stream()
+        dev = gz.device
+        y, mean, invstd, gamma, ymax, xm, xb, wt, wmask, gscale, inv_gscale = ctx.saved_tensors
+        gname, gcode, gh = ctx.gmode
+        key = _shape_key(sh)
+        g = _nhwc(gz)
+        cout = sh.Cout
+        n_pix = sh.N * sh.Ho * sh.Wo
+        i32 = dict(dtype=torch.int32, device=dev)
+        sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
+        gmax = torch.empty((cout,), **i32)
+        consts = torch.empty((4 * cout,), dtype=torch.float32, device=dev)
+        dgamma = torch.empty((cout,), dtype=torch.float32, device=dev)
+        dbeta = torch.empty((cout,), dtype=torch.float32, device=dev)
+        amax = torch.empty((1,), **i32)
+        gys = torch.empty((sh.N, sh.Ho, sh.Wo, gh * cout), dtype=torch.int16, device=dev)
+        with _timed("bn_bwd_pack", key, (8 + 8 + 2 * gh) * n_pix * cout):
+            _lib.check(L.bdbnn_bn_bwd_pack(_p(g), _p(y), _p(mean), _p(invstd), _p(gamma), _p(gscale), _p(ymax), n_pix,
+                                           cout, gcode, _p(sums), _p(gmax), _p(consts), _p(dgamma), _p(dbeta),
+                                           _p(amax), _p(gys), st), "bn_bwd_pack")
+        _lib.count(3)
+        x_shape, w_shape = ctx.shapes
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(x_shape, dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+            with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh)):
+                _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(xm), _p(gx),
+                                                    ctypes.byref(sh), st), "binconv_dgrad_tc")
+            _lib.count(1)
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty(w_shape, dtype=torch.float32, device=dev)
+            nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
+            ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+            with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh, gh)):
+                _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gcode, _p(amax), _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
+                                                    ctypes.byref(sh), _p(ws), nbytes, st), "binconv_wgrad_tc")
+            _lib.count(2)
+        gres = gz if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        return (gx, gw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
+                gres, None, None, None, None, None, None, None, None, None)
+
+
+def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride, padding):
+    """z = BN_train(binconv2d(x, weight)) + residual on the fused kernels.  The returned tensor carries
+    `_bdbnn_pack` = (sign bits, mask bits, +-1 copy, fmt) of z so that a following conv_bn_add skips its
+    own activation pack; x's own `_bdbnn_pack` (if present and of the current format) is consumed."""
+    fmt = grad_mode()[3]
+    pk = getattr(x, "_bdbnn_pack", None)
+    xs = xm = xb = None
+    if pk is not None and pk[3] == fmt:
+        xs, xm, xb = pk[:3]
+    z, zs, zm, zb = _ConvBNAddUnit.apply(x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps,
+                                         int(stride), int(padding), xs, xm, xb)
+    if zs is not None:
+        z._bdbnn_pack = (zs, zm, zb, fmt)
+    return z

@@ -12,7 +12,24 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .modules import HardBinaryConv, HardBinaryConv_cifar, MaxPool2dNHWC
+from . import functional as F_
+from .modules import BinarizeConv2d, HardBinaryConv, HardBinaryConv_cifar, MaxPool2dNHWC
+
+
+def _fused_unit(x, conv, bn, residual):
+    """BN_train(conv(x)) + residual through the fused kernels when the pair qualifies, else None."""
+    if not (x.is_cuda and bn.training and isinstance(conv, BinarizeConv2d) and isinstance(bn, nn.BatchNorm2d)):
+        return None
+    if not (bn.affine and bn.track_running_stats and bn.momentum is not None and F_.fuse_enabled()):
+        return None
+    if conv.impl == "xnor" or x.dtype != torch.float32:
+        return None
+    if not F_.unit_supported(x.shape, conv.weight.shape, conv.stride[0], conv.padding[0]):
+        return None
+    z = F_.conv_bn_add(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.momentum,
+                       bn.eps, conv.stride[0], conv.padding[0])
+    bn.num_batches_tracked.add_(1)
+    return z
 
 
 class BasicBlock(nn.Module):
@@ -28,8 +45,13 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         residual = x if self.downsample is None else self.downsample(x)
-        out = self.bn1(self.conv1(x)) + residual
-        return self.bn2(self.conv2(out)) + out
+        out = _fused_unit(x, self.conv1, self.bn1, residual)
+        if out is None:
+            out = self.bn1(self.conv1(x)) + residual
+        out2 = _fused_unit(out, self.conv2, self.bn2, out)
+        if out2 is None:
+            out2 = self.bn2(self.conv2(out)) + out
+        return out2
 
 
 class ResNetImageNet(nn.Module):

@@ -179,6 +179,30 @@ BDBNN_API int bdbnn_kd_layer_multi_bwd(const float* const* wt_ptrs_host, const i
                              int32_t L, const float* gout, float* const* grad_ptrs_host,
                              int32_t accumulate, void* stream);
 
+/* ---- BatchNorm(train) + residual add (+ next conv's sign/pack) around the binary conv --------------
+ * Caller side of the path.  y = conv output fp32 NHWC [n_pix][C], C % 4 == 0.
+ * bn_fwd : mean/var over n_pix per channel (biased var, eps), mean/invstd saved for backward,
+ *          running_mean/var (may be NULL) updated with `momentum` (unbiased var), then
+ *          z = gamma*(y-mean)*invstd + beta (+ residual if non-NULL).
+ *          If sign_bits != NULL (needs C % 32 == 0) also emits what bdbnn_act_pack(z) would:
+ *          sign_bits, mask_bits, xb (format fmt) — the next binary conv then skips its own pack.
+ *          ymax_bits[C] receives max|y| per channel (float bits) for the backward's FP16S bound.
+ *          Scratch: sums_ws double[2C], ab_ws float[2C].
+ * bn_bwd_pack : from gz (grad of z) and the saved y/mean/invstd computes dgamma, dbeta and writes
+ *          gys = packed(gy * gscale[c]) with gy = gamma*invstd*(gz - mean(gz) - yhat*mean(gz*yhat)),
+ *          in the layout bdbnn_grad_pack produces for `grad_mode` (FP16S scale from an upper bound of
+ *          max|gy*gscale|, written to amax_bits).  The residual branch's gradient is gz itself.
+ *          Scratch: sums_ws double[2C], gmax_bits u32[C], consts_ws float[4C]. */
+BDBNN_API int bdbnn_bn_fwd(const float* y, const float* residual, const float* gamma, const float* beta,
+                 int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
+                 float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean, float* invstd,
+                 float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits, uint16_t* xb,
+                 int32_t fmt, void* stream);
+BDBNN_API int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* mean, const float* invstd,
+                      const float* gamma, const float* gscale, const uint32_t* ymax_bits, int64_t n_pix,
+                      int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits, float* consts_ws,
+                      float* dgamma, float* dbeta, uint32_t* amax_bits, uint16_t* gys, void* stream);
+
 /* ---- NHWC max-pool (stem of the ImageNet shells; torch.nn.MaxPool2d semantics) --------------------
  * Caller side of the path (the ops either side of the binary convs).  x,y,gy,gx fp32
  * NHWC, C % 4 == 0; idx = winning tap (r*k+s) per output element, one byte each [N,Ho,Wo,C].

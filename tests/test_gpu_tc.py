@@ -118,3 +118,88 @@ def test_fwd_tc_full_size_layers_equal_xnor():
         x = torch.randn(256, cin, hw, hw, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
         w = torch.randn(cin, cin, 3, 3, device="cuda", generator=g) * 0.05
         assert torch.equal(binconv2d(x, w, 1, 1, "tc"), binconv2d(x, w, 1, 1, "xnor"))
+
+
+UNIT_SHAPES = [(2, 64, 16, 16, 64, 1), (2, 64, 20, 20, 128, 2), (3, 128, 14, 14, 128, 1), (4, 256, 7, 7, 256, 1)]
+
+
+@pytest.mark.parametrize("mode", ["fp16s", "bf16x2"])
+@pytest.mark.parametrize("with_res", [True, False])
+@pytest.mark.parametrize("shape", UNIT_SHAPES)
+def test_fused_conv_bn_add_unit_vs_oracle(shape, with_res, mode, monkeypatch):
+    """z = BN_train(binconv(x)) + residual: fused kernels vs RefBinarizeConv2d + nn.BatchNorm2d + add on CPU
+    (values, running statistics, and the gradients of x, W, gamma, beta, residual)."""
+    import torch.nn as nn
+    from bdbnn_b200.functional import conv_bn_add, unit_supported
+    monkeypatch.setenv("BDBNN_GRAD_MODE", mode)
+    n, cin, h, w, cout, stride = shape
+    assert unit_supported((n, cin, h, w), (cout, cin, 3, 3), stride, 1)
+    g = torch.Generator().manual_seed(31 + sum(shape))
+    x = torch.randn(n, cin, h, w, generator=g) * 1.2
+    conv = B.RefBinarizeConv2d(cin, cout, 3, stride, 1)
+    conv.weight.data = torch.randn(cout, cin, 3, 3, generator=g) * 0.7
+    bn = nn.BatchNorm2d(cout)
+    bn.weight.data = torch.rand(cout, generator=g) + 0.5
+    bn.bias.data = torch.randn(cout, generator=g) * 0.2
+    bn.running_mean.data = torch.randn(cout, generator=g) * 0.1
+    bn.running_var.data = torch.rand(cout, generator=g) + 0.5
+    ho = (h + 2 - 3) // stride + 1
+    res = torch.randn(n, cout, ho, ho, generator=g) if with_res else None
+    # --- CPU oracle (double precision module chain)
+    xr = x.double().requires_grad_(True)
+    rr = res.double().requires_grad_(True) if with_res else None
+    conv_d, bn_d = conv.double(), bn.double()
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    zr = bn_d(conv_d(xr))
+    if with_res:
+        zr = zr + rr
+    gz = torch.randn(zr.shape, generator=g, dtype=torch.float64)
+    zr.backward(gz)
+    # --- fused
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wd = conv.weight.detach().float().cuda().requires_grad_(True)
+    gam = bn.weight.detach().float().cuda().requires_grad_(True)
+    bet = bn.bias.detach().float().cuda().requires_grad_(True)
+    rd = res.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True) if with_res else None
+    rm, rv = rm0.float().cuda(), rv0.float().cuda()
+    z = conv_bn_add(xd, wd, gam, bet, rd, rm, rv, 0.1, bn_d.eps, stride, 1)
+    z.backward(gz.float().cuda())
+    torch.testing.assert_close(z.detach().cpu().double(), zr.detach(), rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(rm.cpu().double(), bn_d.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv.cpu().double(), bn_d.running_var, rtol=1e-5, atol=1e-6)
+    tol = GRAD_TOL[mode] * 2
+    pairs = [("gx", xd.grad, xr.grad), ("gw", wd.grad, conv_d.weight.grad), ("dgamma", gam.grad, bn_d.weight.grad),
+             ("dbeta", bet.grad, bn_d.bias.grad)]
+    if with_res:
+        pairs.append(("gres", rd.grad, rr.grad))
+    for name, got, ref in pairs:
+        scale = ref.abs().max().item() + 1e-30
+        err = (got.cpu().double() - ref).abs().max().item()
+        assert err <= (1e-5 if name in ("dgamma", "dbeta", "gres") else tol) * scale, (name, err, scale)
+    # the emitted packs are exactly act_pack(z)
+    zs, zm, zb, fmt = z._bdbnn_pack
+    zc = z.detach().cpu()
+    assert torch.equal(zs.cpu().to(torch.int64) & 0xFFFFFFFF, B.pack_bits_nhwc(zc))
+    assert torch.equal(zm.cpu().to(torch.int64) & 0xFFFFFFFF, B.pack_mask_nhwc(zc))
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
+    assert torch.equal(zb.view(dt).float().cpu(), B.sign_pm1(zc).permute(0, 2, 3, 1))
+
+
+def test_fused_blocks_match_unfused_network(monkeypatch):
+    """ResNet-18 BasicBlocks with the fused units vs the same network with BDBNN_FUSE_BN=0 (module chain on
+    the same kernels + cuDNN BN): forward output and all gradients agree to BN-implementation round-off."""
+    from bdbnn_b200.resnet import ResNetImageNet
+    torch.manual_seed(0)
+    net = ResNetImageNet([1, 1, 1, 1], num_classes=10).cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(4, 3, 64, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    outs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("BDBNN_FUSE_BN", fuse)
+        net.zero_grad(set_to_none=True)
+        y = net(x)
+        y.square().mean().backward()
+        outs.append((y.detach().clone(), {n: p.grad.detach().clone() for n, p in net.named_parameters()}))
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=2e-3, atol=2e-4)
+    for n in outs[0][1]:
+        a, b = outs[0][1][n], outs[1][1][n]
+        assert (a - b).abs().max().item() <= 3e-2 * (b.abs().max().item() + 1e-12), n
