@@ -273,6 +273,7 @@ struct TcConvLaunch {
   const float* alpha; const uint32_t* mask; float* out;
   int fmt;                       // operand format (BDBNN_FMT_*)
   const uint32_t* amax_bits;     // FP16S gradient: device word with max|A|; epilogue multiplies by 2^-e
+  const float* add;              // dgrad: optional tensor added to the result (shortcut gradient), or NULL
 };
 
 // Persistent multi-accumulator kernel (tc_conv2.cu). Returns BDBNN_ERR_UNSUPPORTED if the geometry

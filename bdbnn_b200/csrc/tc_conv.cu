@@ -38,6 +38,7 @@ struct TcConvParams {
   int32_t row_bytes;         // KB * 2 = swizzle span (32/64/128)
   int32_t fmt;               // operand format
   const uint32_t* amax_bits; // FP16S: post-scale 2^-e (NULL otherwise)
+  const float* add;          // dgrad: optional additive tensor
   const float* alpha;        // MODE 0: per-output-channel scale
   const uint32_t* mask;      // MODE 1: STE mask words [pix][Nout/32 (ceil)]
   float* out;                // [pix][Nout] fp32
@@ -209,6 +210,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t word = __ldg(p.mask + pix * mask_words + (col >> 5)) >> (col & 31);
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = ((word >> j) & 1u) ? __uint_as_float(v[j]) * post : 0.0f;
+          if (p.add != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.add + pix * p.Nout + nn0 + c0 + j);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
@@ -274,7 +279,7 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   p.Nout = L.Nout;
   p.BN = pick_bn(L.Nout);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
-  p.fmt = L.fmt; p.amax_bits = L.amax_bits;
+  p.fmt = L.fmt; p.amax_bits = L.amax_bits; p.add = L.add;
   // Halo mode (stride-1 launches with >128-pixel images and 64-channel K blocks): see TcConvParams.
   static const int halo_env = [] { const char* e = getenv("BDBNN_TC_HALO"); return e ? atoi(e) : 1; }();
   if (halo_env > 0 && L.in_step == 1 && p.KB == 64 && L.OH * L.OW > kTileM && p.n_taps > 0) {
@@ -359,8 +364,8 @@ extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_
 }
 
 extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
-                                      const uint16_t* wt_bf16, const uint32_t* mask_bits, float* gx,
-                                      const bdbnn_conv_shape* s, void* stream) {
+                                      const uint16_t* wt_bf16, const uint32_t* mask_bits, const float* add,
+                                      float* gx, const bdbnn_conv_shape* s, void* stream) {
   int rc = validate_shape(s);
   if (rc) return rc;
   BDBNN_REQUIRE(gys_bf16 && wt_bf16 && mask_bits && gx, "binconv_dgrad_tc: NULL pointer");
@@ -400,10 +405,14 @@ extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mod
       L.mask = mask_bits; L.out = gx;
       L.fmt = grad_mode == BDBNN_GRAD_FP16S ? BDBNN_FMT_FP16 : BDBNN_FMT_BF16;
       L.amax_bits = grad_mode == BDBNN_GRAD_FP16S ? amax_bits : nullptr;
+      L.add = add;
       ++n_launch;
     }
-  if (empty_phase)
-    BDBNN_CUDA(cudaMemsetAsync(gx, 0, size_t(s->N) * s->H * s->W * s->Cin * sizeof(float), st));
+  if (empty_phase) {
+    const size_t bytes = size_t(s->N) * s->H * s->W * s->Cin * sizeof(float);
+    if (add != nullptr) BDBNN_CUDA(cudaMemcpyAsync(gx, add, bytes, cudaMemcpyDeviceToDevice, st));
+    else BDBNN_CUDA(cudaMemsetAsync(gx, 0, bytes, st));
+  }
   for (int i = 0; i < n_launch; ++i) {
     rc = launch_tc_conv<1>(Ls[i], st);
     if (rc) return rc;

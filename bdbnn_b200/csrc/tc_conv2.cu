@@ -19,7 +19,7 @@
 
 namespace bdbnn {
 
-constexpr int kTS = 4;  // M tiles (accumulators) per super tile
+constexpr int kMaxTS = 4;  // max M tiles (accumulators) per super tile; p.TS is the per-launch value
 
 struct TcConv2Params {
   int32_t OW, OH, NIMG;
@@ -36,12 +36,13 @@ struct TcConv2Params {
   int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
   uint8_t tap_b[kMaxTaps];
   int32_t out_step, out_off_h, out_off_w, OHf, OWf;
-  int32_t Nout, BN, NB;
+  int32_t Nout, BN, NB, TS;
   int32_t stages;
   int32_t dbg;               // BDBNN_TC_DBG experiment bits: 1 = no global stores, 2 = no TMEM loads, 4 = no MMAs
   uint32_t stage_bytes, b_bytes;
   int32_t fmt;
   const uint32_t* amax_bits;
+  const float* add;
   const float* alpha;
   const uint32_t* mask;
   float* out;
@@ -77,11 +78,11 @@ __device__ __forceinline__ SuperGeom super_geom(const TcConv2Params& p, int sup)
       g.ntl = (rows * p.PW + kTileM - 1) / kTileM;
     }
   } else {
-    const int t0 = sup * kTS;
+    const int t0 = sup * p.TS;
     g.n0 = 0; g.h0 = 0;
-    g.ntl = min(kTS, p.n_mtiles - t0);
+    g.ntl = min(p.TS, p.n_mtiles - t0);
   }
-  if (g.ntl > kTS) g.ntl = kTS;
+  if (g.ntl > p.TS) g.ntl = p.TS;
   return g;
 }
 
@@ -160,7 +161,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             } else {
               mbar_expect_tx(fb, p.b_bytes + uint32_t(g.ntl * p.BNI * p.BH * p.BW) * 128u);
               for (int j = 0; j < g.ntl; ++j) {
-                const int t = sup * kTS + j;
+                const int t = sup * p.TS + j;
                 const int tile_n = t / p.tiles_h, tile_h = t - tile_n * p.tiles_h;
                 tma_load_4d(dst + p.b_bytes + uint32_t(j) * (kTileM * 128u), &tmA, fb, kb * 64, p.tap_dw[ti],
                             tile_h * p.BH * p.in_step + p.tap_dh[ti], tile_n * p.BNI);
@@ -187,7 +188,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(smem_u32(&tempty_bar[buf]), ((wcount / uint32_t(p.NB)) & 1u) ^ 1u);
         tc_fence_after();
         BDBNN_TR(1, 1);
-        const uint32_t acc0 = tmem_d + buf * uint32_t(kTS * p.BN);
+        const uint32_t acc0 = tmem_d + buf * uint32_t(p.TS * p.BN);
         bool first = true;
         for (int kb = 0; kb < kb_total; ++kb) {
           uint32_t patch = 0, pa = 0;
@@ -255,7 +256,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           valid = wi < p.OW && hi < p.OH && ni < p.NIMG && blk < p.HBNI &&
                   (p.HBNI > 1 || p.supers_per_img == 1 || hi < g.h0 + p.SH);
         } else {
-          const int t = sup * kTS + j;
+          const int t = sup * p.TS + j;
           const int tile_n = t / p.tiles_h, tile_h = t - tile_n * p.tiles_h;
           const int r = warp * 32 + lane;
           wi = r % p.BW;
@@ -268,7 +269,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int oh = hi * p.out_step + p.out_off_h, ow = wi * p.out_step + p.out_off_w;
         valid = valid && oh < p.OHf && ow < p.OWf;
         const int64_t pix = (int64_t(ni) * p.OHf + oh) * p.OWf + ow;
-        const uint32_t tbase = tmem_d + (uint32_t(warp * 32) << 16) + buf * uint32_t(kTS * p.BN) + uint32_t(j * p.BN);
+        const uint32_t tbase = tmem_d + (uint32_t(warp * 32) << 16) + buf * uint32_t(p.TS * p.BN) + uint32_t(j * p.BN);
         if (p.dbg & 1) valid = false;
         if (p.dbg & 2) continue;
         // Row offsets/validity of this warp's 32 rows are exchanged by shuffle in the store phase.
@@ -299,13 +300,28 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             *reinterpret_cast<float4*>(stage_warp + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
           }
           __syncwarp();
-          // (2) read back transposed: one instruction stores 4 complete 128-byte rows (8 lanes per row)
+          // (2) read back transposed: one instruction stores 4 complete 128-byte rows (8 lanes per row).
+          //     Row offsets come by shuffle; the optional additive tensor is fetched for all 8 row groups
+          //     up front so its latency is paid once per block, not once per store.
+          int64_t offs[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) offs[i] = __shfl_sync(0xffffffffu, row_off, 4 * i + (lane >> 3));
+          const int cq = lane & 7;
+          float4 addv[8];
+          if (MODE == 1 && p.add != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              addv[i] = offs[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.add + offs[i] + c0 + cq * 4))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3), c = lane & 7;
-            const int64_t off = __shfl_sync(0xffffffffu, row_off, r);
-            const float4 o = *reinterpret_cast<const float4*>(stage_warp + r * 128 + ((c ^ (r & 7)) << 4));
-            if (off >= 0) *reinterpret_cast<float4*>(p.out + off + c0 + c * 4) = o;
+            const int r = 4 * i + (lane >> 3);
+            float4 o = *reinterpret_cast<const float4*>(stage_warp + r * 128 + ((cq ^ (r & 7)) << 4));
+            if (MODE == 1 && p.add != nullptr) {
+              o.x += addv[i].x; o.y += addv[i].y; o.z += addv[i].z; o.w += addv[i].w;
+            }
+            if (offs[i] >= 0) *reinterpret_cast<float4*>(p.out + offs[i] + c0 + cq * 4) = o;
           }
         }
       }
@@ -344,9 +360,17 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   p.Nout = L.Nout;
   p.BN = L.Nout >= 128 ? 128 : 64;
   p.n_ntiles = L.Nout / p.BN;
-  p.NB = p.BN == 64 ? 2 : 1;
+  // 512 TMEM columns = NB buffers x TS accumulators x BN columns.  BDBNN_TC_TS128 picks the BN=128 split:
+  // 4 = four tiles sharing each weight stage, single buffer (epilogue exposed);
+  // 2 = two tiles, double-buffered (epilogue overlaps the next item's MMAs, weights re-read twice as often)
+  // Measured (ResNet-18 N=256): TS=2 wins while the weight slab per item is small (K <= 128 channels:
+  // layer2 fwd 0.109 -> 0.097 ms, stride-2 fwd 0.081 -> 0.058), TS=4 wins for K >= 256 (layers 3, 4).
+  static const int ts128 = [] { const char* e = getenv("BDBNN_TC_TS128"); return e ? atoi(e) : 0; }();
+  const int ts_auto = (L.Kc * L.a_halves <= 128) ? 2 : 4;
+  p.TS = p.BN == 64 ? 4 : (ts128 == 4 ? 4 : (ts128 == 2 ? 2 : ts_auto));
+  p.NB = 512 / (p.TS * p.BN);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
-  p.fmt = L.fmt; p.amax_bits = L.amax_bits;
+  p.fmt = L.fmt; p.amax_bits = L.amax_bits; p.add = L.add;
   p.b_bytes = uint32_t(p.BN) * 128u;
 
   int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
@@ -356,7 +380,7 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   }
   const int dh_span = dh1 - dh0, dw_span = dw1 - dw0;
   const int PW = L.OW + dw_span;
-  const int super_rows = kTS * kTileM;  // 512 padded rows
+  const int super_rows = p.TS * kTileM;  // padded rows per super tile
   CUtensorMap tmA, tmB;
   int rc;
   if (L.in_step == 1 && L.OH * L.OW > kTileM && PW <= 256 && PW * (1 + dh_span) <= super_rows) {
@@ -399,8 +423,8 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
     }
     p.tiles_h = (L.OH + p.BH - 1) / p.BH;
     p.n_mtiles = p.tiles_h * ((L.NIMG + p.BNI - 1) / p.BNI);
-    p.n_supers = (p.n_mtiles + kTS - 1) / kTS;
-    p.stage_bytes = (p.b_bytes + kTS * kTileM * 128u + 1023u) & ~1023u;
+    p.n_supers = (p.n_mtiles + p.TS - 1) / p.TS;
+    p.stage_bytes = (p.b_bytes + uint32_t(p.TS) * kTileM * 128u + 1023u) & ~1023u;
     rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.BW, p.BH, p.BNI, L.in_step);
   }
   if (rc) return rc;

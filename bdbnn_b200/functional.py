@@ -229,7 +229,7 @@ class _BinConv2d(torch.autograd.Function):
                 gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev,
                                  memory_format=torch.channels_last)
                 with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh)):
-                    _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(mask_bits), _p(gx),
+                    _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(mask_bits), _p(None), _p(gx),
                                                         ctypes.byref(sh), st), "binconv_dgrad_tc")
                 _lib.count(1)
             if need_w and not (ctx.use & 4):
@@ -457,7 +457,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride,
-                padding, xs, xm, xb):
+                padding, xs, xm, xb, res_is_x):
         _require_cuda(x, "conv_bn_add(x)")
         L = _lib.lib()
         sh = conv_shape(x.shape, weight.shape, stride, padding)
@@ -494,7 +494,10 @@ class _ConvBNAddUnit(torch.autograd.Function):
                        "binconv_fwd_tc")
         _lib.count(3)
         n_pix = n * sh.Ho * sh.Wo
-        rc = _nhwc(residual.detach()) if residual is not None else None
+        if res_is_x:            # identity shortcut: the residual IS the conv input (one autograd edge)
+            rc = _nhwc(x.detach())
+        else:
+            rc = _nhwc(residual.detach()) if residual is not None else None
         z = torch.empty_like(y)
         sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
         ymax = torch.empty((cout,), **i32)
@@ -513,6 +516,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
         ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
         ctx.shapes = (tuple(x.shape), tuple(weight.shape))
         ctx.has_res = residual is not None
+        ctx.res_is_x = bool(res_is_x)
         ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale)
         if pack:
             ctx.mark_non_differentiable(zs, zm, zb)
@@ -549,7 +553,9 @@ class _ConvBNAddUnit(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty(x_shape, dtype=torch.float32, device=dev, memory_format=torch.channels_last)
             with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh)):
-                _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(xm), _p(gx),
+                # identity shortcut: d/dx = dgrad + gz, summed in the dgrad epilogue (no separate add kernel)
+                _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(xm),
+                                                    _p(g) if ctx.res_is_x else _p(None), _p(gx),
                                                     ctypes.byref(sh), st), "binconv_dgrad_tc")
             _lib.count(1)
         if ctx.needs_input_grad[1]:
@@ -562,7 +568,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
             _lib.count(2)
         gres = gz if (ctx.has_res and ctx.needs_input_grad[4]) else None
         return (gx, gw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
-                gres, None, None, None, None, None, None, None, None, None)
+                gres, None, None, None, None, None, None, None, None, None, None)
 
 
 def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride, padding):
@@ -574,8 +580,9 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
     xs = xm = xb = None
     if pk is not None and pk[3] == fmt:
         xs, xm, xb = pk[:3]
-    z, zs, zm, zb = _ConvBNAddUnit.apply(x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps,
-                                         int(stride), int(padding), xs, xm, xb)
+    res_is_x = residual is x and x.shape[1] == weight.shape[0] and int(stride) == 1
+    z, zs, zm, zb = _ConvBNAddUnit.apply(x, weight, gamma, beta, None if res_is_x else residual, running_mean,
+                                         running_var, momentum, eps, int(stride), int(padding), xs, xm, xb, res_is_x)
     if zs is not None:
         z._bdbnn_pack = (zs, zm, zb, fmt)
     return z

@@ -126,7 +126,9 @@ BDBNN_API int bdbnn_binconv_wgrad(const float* gy, const uint32_t* sign_bits, co
  *              FP16S  gys[p*Cout+o]             = fp16_rn(v * 2^e), e = 13 - floor(log2 max|v|); the max is
  *                     reduced into the device word amax_bits (float bits) by the same call
  *            gys is shared by dgrad_tc (K-major) and wgrad_tc (MN-major).
- * dgrad_tc : gx = mask * 2^-e * conv_transpose(gys, wt)              (sign-only weights, exact)
+ * dgrad_tc : gx = mask * 2^-e * conv_transpose(gys, wt) (+ add)      (sign-only weights, exact; `add`,
+ *            if non-NULL, is an fp32 tensor shaped like gx — the shortcut branch's gradient — summed in
+ *            the epilogue)
  * wgrad_tc : gW = wmask * inv_gscale[o] * 2^-e * sum_pix gys[pix,o]*xb[pix',c]
  * The +-1 operands (xb, wt) must be in the format matching the mode: fp16 for FP16S, bf16 otherwise.
  * wgrad_tc needs a workspace of bdbnn_wgrad_tc_workspace_bytes(s) bytes (split-K partials).
@@ -134,7 +136,7 @@ BDBNN_API int bdbnn_binconv_wgrad(const float* gy, const uint32_t* sign_bits, co
 BDBNN_API int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_pix, int32_t Cout,
                     int32_t mode, uint32_t* amax_bits, uint16_t* gys, void* stream);
 BDBNN_API int bdbnn_binconv_dgrad_tc(const uint16_t* gys, int32_t grad_mode, const uint32_t* amax_bits,
-                           const uint16_t* wt, const uint32_t* mask_bits, float* gx,
+                           const uint16_t* wt, const uint32_t* mask_bits, const float* add, float* gx,
                            const bdbnn_conv_shape* s, void* stream);
 BDBNN_API size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s);
 BDBNN_API int bdbnn_binconv_wgrad_tc(const uint16_t* gys, int32_t grad_mode, const uint32_t* amax_bits,

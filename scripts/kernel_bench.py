@@ -88,7 +88,7 @@ def main():
             kernels.update({
                 "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), FMT, _p(alpha), _p(y), shp, st), "f"),
                 "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, GC, _p(amax), _p(gys), st), "g"),
-                "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), GC, _p(amax), _p(wt), _p(mb), _p(gx), shp, st), "d"),
+                "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), GC, _p(amax), _p(wt), _p(mb), _p(None), _p(gx), shp, st), "d"),
             })
             if caps & 4:
                 kernels["wgrad_tc"] = lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), GC, _p(amax), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w")

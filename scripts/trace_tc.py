@@ -30,7 +30,7 @@ if which == "wgrad":
     run = lambda: L.bdbnn_binconv_wgrad_tc(_p(gys), 2, _p(None), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st)
 else:
   run = (lambda: L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), 1, _p(alpha), _p(y), shp, st)) if which == "fwd" else \
-      (lambda: L.bdbnn_binconv_dgrad_tc(_p(gys), 2, _p(None), _p(wt), _p(mb), _p(gx), shp, st))
+      (lambda: L.bdbnn_binconv_dgrad_tc(_p(gys), 2, _p(None), _p(wt), _p(mb), _p(None), _p(gx), shp, st))
 run(); torch.cuda.synchronize()
 tr = torch.zeros(3 * 2048, dtype=torch.int64, device="cuda")
 L.bdbnn_debug_trace(_p(tr)); run(); torch.cuda.synchronize(); L.bdbnn_debug_trace(None)

@@ -203,3 +203,28 @@ def test_fused_blocks_match_unfused_network(monkeypatch):
     for n in outs[0][1]:
         a, b = outs[0][1][n], outs[1][1][n]
         assert (a - b).abs().max().item() <= 3e-2 * (b.abs().max().item() + 1e-12), n
+
+
+@pytest.mark.parametrize("mode", ["fp16s", "bf16x2"])
+def test_fused_unit_identity_shortcut_adds_in_dgrad_epilogue(mode, monkeypatch):
+    """residual is x itself: d/dx = dgrad + gz comes out of the dgrad epilogue (no autograd add)."""
+    import torch.nn as nn
+    from bdbnn_b200.functional import conv_bn_add
+    monkeypatch.setenv("BDBNN_GRAD_MODE", mode)
+    g = torch.Generator().manual_seed(77)
+    n, c, h = 3, 128, 14
+    x = torch.randn(n, c, h, h, generator=g) * 1.2
+    conv = B.RefBinarizeConv2d(c, c, 3, 1, 1).double()
+    conv.weight.data = torch.randn(c, c, 3, 3, generator=g).double() * 0.7
+    bn = nn.BatchNorm2d(c).double()
+    xr = x.double().requires_grad_(True)
+    zr = bn(conv(xr)) + xr
+    gz = torch.randn(zr.shape, generator=g, dtype=torch.float64)
+    zr.backward(gz)
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    z = conv_bn_add(xd, conv.weight.detach().float().cuda(), torch.ones(c, device="cuda"), torch.zeros(c, device="cuda"),
+                    xd, torch.zeros(c, device="cuda"), torch.ones(c, device="cuda"), 0.1, 1e-5, 1, 1)
+    z.backward(gz.float().cuda())
+    torch.testing.assert_close(z.detach().cpu().double(), zr.detach(), rtol=2e-5, atol=2e-5)
+    scale = xr.grad.abs().max().item()
+    assert (xd.grad.cpu().double() - xr.grad).abs().max().item() <= GRAD_TOL[mode] * 2 * scale
