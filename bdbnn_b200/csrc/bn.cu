@@ -53,8 +53,9 @@ bn_reduce_kernel(const float4* __restrict__ p0, const float4* __restrict__ p1, c
     is = *reinterpret_cast<const float4*>(invstd + c4 * 4);
   }
   float4 sa = make_float4(0, 0, 0, 0), sb = sa, mx = sa;
+#pragma unroll 4
   for (int64_t p = gtid / C4; p < n_pix; p += p_step) {
-    const float4 u = __ldg(p0 + p * C4 + c4);
+    const float4 u = __ldcs(p0 + p * C4 + c4);
     if (BWD) {   // u = gz, v = y:  a = gz, b = gz * yhat, c = |gz|
       const float4 v = __ldg(p1 + p * C4 + c4);
       sa.x += u.x; sa.y += u.y; sa.z += u.z; sa.w += u.w;

@@ -275,8 +275,17 @@ wgrad_finalize_kernel(const float* __restrict__ ws, int ksplit, const uint32_t* 
     const int64_t e = (int64_t(o) * Cin + c) * T + t;              // OIHW flat index
     float acc = 0.f;
     if ((wmask[e >> 5] >> (e & 31)) & 1u) {
-      for (int k = 0; k < ksplit; ++k) acc += ws[int64_t(k) * n + i];
-      acc *= post * inv_gscale[o];
+      // fixed summation order (deterministic); four independent chains hide the load latency
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 3 < ksplit; k += 4) {
+        a0 += ws[int64_t(k) * n + i];
+        a1 += ws[int64_t(k + 1) * n + i];
+        a2 += ws[int64_t(k + 2) * n + i];
+        a3 += ws[int64_t(k + 3) * n + i];
+      }
+      for (; k < ksplit; ++k) a0 += ws[int64_t(k) * n + i];
+      acc = ((a0 + a1) + (a2 + a3)) * post * inv_gscale[o];
     }
     gW[e] = acc;
   }

@@ -459,6 +459,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
     def forward(ctx, x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride,
                 padding, xs, xm, xb, res_is_x):
         _require_cuda(x, "conv_bn_add(x)")
+        ctx.set_materialize_grads(False)     # no zero tensors for the (integer) pack outputs in backward
         L = _lib.lib()
         sh = conv_shape(x.shape, weight.shape, stride, padding)
         dev = x.device
@@ -525,6 +526,8 @@ class _ConvBNAddUnit(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gz, _g1, _g2, _g3):
+        if gz is None:
+            return (None,) * 15
         L = _lib.lib()
         sh = ctx.sh
         st = _stream()
