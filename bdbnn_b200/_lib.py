@@ -30,7 +30,9 @@ SIGNATURES = {
     "bdbnn_tc_supported": (c_int, [_SH]),
     "bdbnn_debug_trace": (c_int, [_P]),
     "bdbnn_act_pack": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P]),
-    "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "bdbnn_bits_to_fp8": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "bdbnn_binconv_fwd_tc8": (c_int, [_P, _P, _P, _P, _SH, _P]),
     "bdbnn_binconv_fwd_xnor": (c_int, [_P, _P, _P, _P, _SH, _P]),
     "bdbnn_binconv_fwd_tc": (c_int, [_P, _P, c_int, _P, _P, _SH, _P]),
     "bdbnn_binconv_dgrad": (c_int, [_P, _P, _P, _P, _P, _SH, _P]),
@@ -44,7 +46,7 @@ SIGNATURES = {
     "bdbnn_kd_logits_fwd_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
     "bdbnn_kd_layer_multi_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P]),
     "bdbnn_kd_layer_multi_bwd": (c_int, [_P, _P, c_int, _P, _P, c_int, _P]),
-    "bdbnn_bn_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, ctypes.c_float, ctypes.c_float] + [_P] * 11 + [c_int, _P]),
+    "bdbnn_bn_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, ctypes.c_float, ctypes.c_float] + [_P] * 12 + [c_int, _P]),
     "bdbnn_bn_bwd_pack": (c_int, [_P] * 7 + [c_int64, c_int, c_int] + [_P] * 8),
     "bdbnn_maxpool_fwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [_P]),
     "bdbnn_maxpool_bwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [_P]),

@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_apply_add_pack_kernel(const float4* __restrict__ y, const float4* __restrict__ res,
                          const float* __restrict__ a, const float* __restrict__ b, int64_t n4, int C4,
                          float4* __restrict__ z, uint32_t* __restrict__ sign_bits,
-                         uint32_t* __restrict__ mask_bits, uint2* __restrict__ xb4, uint32_t one16) {
+                         uint32_t* __restrict__ mask_bits, uint2* __restrict__ xb4, uint32_t* __restrict__ xb8,
+                         uint32_t one16) {
   const int lane = threadIdx.x & 31;
   const uint32_t group_mask = 0xffu << (lane & 24);
   const int sh = (lane & 7) * 4;
@@ -149,6 +150,8 @@ bn_apply_add_pack_kernel(const float4* __restrict__ y, const float4* __restrict_
       q.x = (s0 ? pos : neg) | ((s1 ? pos : neg) << 16);
       q.y = (s2 ? pos : neg) | ((s3 ? pos : neg) << 16);
       xb4[i] = q;
+      if (xb8 != nullptr)   // e4m3 +-1 bytes for the fp8 forward of the next conv
+        xb8[i] = 0x38383838u | ((s0 ? 0u : 0x80u) | (s1 ? 0u : 0x8000u) | (s2 ? 0u : 0x800000u) | (s3 ? 0u : 0x80000000u));
     }
   }
 }
@@ -251,7 +254,7 @@ extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* 
                             int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
                             float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean,
                             float* invstd, float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits,
-                            uint16_t* xb, int32_t fmt, void* stream) {
+                            uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, void* stream) {
   const bool pack = sign_bits != nullptr;
   int rc = bn_dims_ok(n_pix, C, pack);
   if (rc) return rc;
@@ -278,11 +281,12 @@ extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* 
     const uint32_t one16 = fmt == BDBNN_FMT_FP16 ? 0x3C00u : 0x3F80u;
     bn_apply_add_pack_kernel<true><<<grid, kBnThreads, 0, st>>>(
         reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(residual), a, b, n4, C4,
-        reinterpret_cast<float4*>(z), sign_bits, mask_bits, reinterpret_cast<uint2*>(xb), one16);
+        reinterpret_cast<float4*>(z), sign_bits, mask_bits, reinterpret_cast<uint2*>(xb),
+        reinterpret_cast<uint32_t*>(xb_fp8), one16);
   } else {
     bn_apply_add_pack_kernel<false><<<grid, kBnThreads, 0, st>>>(
         reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(residual), a, b, n4, C4,
-        reinterpret_cast<float4*>(z), nullptr, nullptr, nullptr, 0u);
+        reinterpret_cast<float4*>(z), nullptr, nullptr, nullptr, nullptr, 0u);
   }
   return check_launch("bn_apply_add_pack_kernel");
 }

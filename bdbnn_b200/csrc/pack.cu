@@ -62,7 +62,7 @@ act_pack_kernel(const float* __restrict__ x, int64_t n_words, int32_t C, int32_t
 __global__ void __launch_bounds__(256)
 weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32_t T, int32_t Cw,
                    float* __restrict__ alpha, uint32_t* __restrict__ wsign,
-                   uint16_t* __restrict__ wf, uint16_t* __restrict__ wt,
+                   uint16_t* __restrict__ wf, uint16_t* __restrict__ wt, uint8_t* __restrict__ wf8,
                    float* __restrict__ gscale, float* __restrict__ inv_gscale, uint16_t one16) {
   const int o = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -101,14 +101,34 @@ weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32
     if (lane == 0) wsign[(int64_t(o) * T + t) * Cw + k] = sb;
   }
   // bf16 operands for the tensor-core path
-  if (wf != nullptr || wt != nullptr) {
+  if (wf != nullptr || wt != nullptr || wf8 != nullptr) {
     for (int i = tid; i < per; i += blockDim.x) {
       const int t = i / Cin, c = i - t * Cin;  // (t, c) with c fastest: coalesced wf writes
       const float v = Wo[c * T + t];
       const uint16_t sg = (v >= 0.0f) ? one16 : uint16_t(one16 | 0x8000u);
       if (wf) wf[(int64_t(o) * T + t) * Cin + c] = sg;
+      if (wf8) wf8[(int64_t(o) * T + t) * Cin + c] = (v >= 0.0f) ? uint8_t(0x38) : uint8_t(0xB8);  // e4m3 +-1
       if (wt) wt[(int64_t(c) * T + (T - 1 - t)) * Cout + o] = live ? sg : uint16_t(0);
     }
+  }
+}
+
+// sign bits -> fp8 e4m3 +-1 bytes (0x38 / 0xB8), C % 32 == 0: word w expands to 32 consecutive bytes.
+__global__ void __launch_bounds__(256)
+bits_to_fp8_kernel(const uint32_t* __restrict__ bits, int64_t n_words, uint4* __restrict__ out) {
+  // one thread per 16 output bytes (half a word is two threads)
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_words * 2;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const uint32_t w = __ldg(bits + (i >> 1)) >> ((i & 1) * 16);
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t nib = (w >> (4 * q)) & 0xfu;
+      // byte j = 0x38 | (bit ? 0 : 0x80)
+      o[q] = 0x38383838u | (((nib & 1u) ? 0u : 0x80u) | ((nib & 2u) ? 0u : 0x8000u) | ((nib & 4u) ? 0u : 0x800000u) |
+                            ((nib & 8u) ? 0u : 0x80000000u));
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -249,14 +269,15 @@ extern "C" int bdbnn_act_pack(const float* x, int64_t n_pix, int32_t C, uint32_t
 
 extern "C" int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
                                  float* alpha, uint32_t* wsign_bits, uint32_t* wmask_bits,
-                                 uint16_t* wf_bf16, uint16_t* wt_bf16, float* gscale,
+                                 uint16_t* wf_bf16, uint16_t* wt_bf16, uint8_t* wf_fp8, float* gscale,
                                  float* inv_gscale, int32_t fmt, void* stream) {
   BDBNN_REQUIRE(fmt == BDBNN_FMT_FP16 || fmt == BDBNN_FMT_BF16, "weight_pack: bad operand format");
   BDBNN_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "weight_pack: bad dims");
   BDBNN_REQUIRE(W && alpha && wsign_bits && wmask_bits, "weight_pack: NULL pointer");
   const int32_t T = kh * kw, Cw = (Cin + 31) / 32;
   weight_pack_kernel<<<Cout, 256, 0, cudaStream_t(stream)>>>(W, Cout, Cin, T, Cw, alpha, wsign_bits,
-                                                            wf_bf16, wt_bf16, gscale, inv_gscale, one_bits(fmt));
+                                                            wf_bf16, wt_bf16, wf_fp8, gscale, inv_gscale,
+                                                            one_bits(fmt));
   int rc = check_launch("weight_pack_kernel");
   if (rc) return rc;
   const int64_t n = int64_t(Cout) * Cin * T;
@@ -292,4 +313,17 @@ extern "C" int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_p
     grad_pack_kernel<1><<<unsigned(blocks), 256, 0, st>>>(gy, gscale, n, Cout, nullptr, gys);
   }
   return check_launch("grad_pack_kernel");
+}
+
+extern "C" int bdbnn_bits_to_fp8(const uint32_t* sign_bits, int64_t n_pix, int32_t C, uint8_t* xb_fp8, void* stream) {
+  BDBNN_REQUIRE(n_pix >= 0 && C > 0 && (C & 31) == 0, "bits_to_fp8: C must be a positive multiple of 32");
+  if (n_pix == 0) return BDBNN_OK;
+  BDBNN_REQUIRE(sign_bits && xb_fp8, "bits_to_fp8: NULL pointer");
+  const int64_t n_words = n_pix * (C / 32);
+  int64_t blocks = (n_words * 2 + 255) / 256;
+  const int64_t cap = int64_t(num_sms()) * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  bits_to_fp8_kernel<<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(sign_bits, n_words,
+                                                                         reinterpret_cast<uint4*>(xb_fp8));
+  return check_launch("bits_to_fp8_kernel");
 }

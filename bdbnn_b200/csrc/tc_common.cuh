@@ -182,6 +182,30 @@ __device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, 
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp8 (e4m3 x e4m3 -> f32) MMA, K = 32 per instruction; +-1 is exact in e4m3.
+__device__ __forceinline__ void umma_f8_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// e4m3 A and B (format code 0), f32 accumulate, K-major
+__host__ __device__ inline uint32_t make_idesc_f8(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// Low / high descriptor words of a swizzled K-major tile with rows of `row_bytes` (64 or 128)
+__device__ __forceinline__ uint32_t kmajor_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t kmajor_hi(uint32_t row_bytes) {
+  return ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+}
 // Low / high words of a SWIZZLE_128B K-major descriptor (see make_kmajor_desc).
 __device__ __forceinline__ uint32_t kmajor128_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint32_t kmajor128_hi() { return (1024u >> 4) | (1u << 14) | (2u << 29); }
@@ -231,32 +255,35 @@ inline CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 // bf16 NHWC activation tensor [N][H][W][C] -> 4-D map, box [BNI][BH][BW][KB].
+// esize = 2: 16-bit elements (bf16/fp16 bit patterns), esize = 1: fp8 bytes.
 inline int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int KB, int BW,
-                        int BH, int BNI, int step = 1) {
+                        int BH, int BNI, int step = 1, int esize = 2) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return BDBNN_ERR_CUDA; }
   cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
-  cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+  cuuint64_t strides[3] = {cuuint64_t(C) * esize, cuuint64_t(W) * C * esize, cuuint64_t(H) * W * C * esize};
   // element stride `step` in w/h: TMA loads ceil(box/step) elements, so box = loaded * step
   cuuint32_t box[4] = {cuuint32_t(KB), cuuint32_t(BW * step), cuuint32_t(BH * step), cuuint32_t(BNI)};
   cuuint32_t estr[4] = {1, cuuint32_t(step), cuuint32_t(step), 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KB * 2),
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for(KB * esize),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act) failed: %d", int(r)); return BDBNN_ERR_CUDA; }
   return BDBNN_OK;
 }
 
 // bf16 K-major weight matrix [rows][cols] -> 2-D map, box [BN rows][KB cols].
-inline int make_weight_map(CUtensorMap* map, const void* base, int rows, int cols, int KB, int BN) {
+inline int make_weight_map(CUtensorMap* map, const void* base, int rows, int cols, int KB, int BN, int esize = 2) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return BDBNN_ERR_CUDA; }
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  cuuint64_t strides[1] = {cuuint64_t(cols) * 2};
+  cuuint64_t strides[1] = {cuuint64_t(cols) * esize};
   cuuint32_t box[2] = {cuuint32_t(KB), cuuint32_t(BN)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KB * 2),
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for(KB * esize),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight) failed: %d", int(r)); return BDBNN_ERR_CUDA; }
   return BDBNN_OK;
@@ -271,7 +298,7 @@ struct TcConvLaunch {
   int n_taps; int8_t dh[kMaxTaps], dw[kMaxTaps]; uint8_t tb[kMaxTaps];
   int out_step, off_h, off_w, OHf, OWf;
   const float* alpha; const uint32_t* mask; float* out;
-  int fmt;                       // operand format (BDBNN_FMT_*)
+  int fmt;                       // operand format (BDBNN_FMT_*); -1 = fp8 e4m3 bytes (forward only)
   const uint32_t* amax_bits;     // FP16S gradient: device word with max|A|; epilogue multiplies by 2^-e
   const float* add;              // dgrad: optional tensor added to the result (shortcut gradient), or NULL
 };

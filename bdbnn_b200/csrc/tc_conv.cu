@@ -337,7 +337,10 @@ extern "C" int bdbnn_debug_trace(long long* device_buf) {
 
 extern "C" int bdbnn_tc_supported(const bdbnn_conv_shape* s) {
   if (!tc_shape_ok(s)) return 0;
-  return BDBNN_TC_FWD | BDBNN_TC_DGRAD | (wgrad_tc_ok(s) ? BDBNN_TC_WGRAD : 0);
+  // fp8 forward only with 128-byte K rows (Cin % 128 == 0): with 64-channel (64-byte, SWIZZLE_64B) rows
+  // each K=32 MMA took ~240 clk on B200 (vs ~105 clk for the 16-bit K=16 MMA), i.e. no gain for layer1
+  const bool v2 = s->Cin % 128 == 0 && (s->Cout == 64 || s->Cout % 128 == 0);
+  return BDBNN_TC_FWD | BDBNN_TC_DGRAD | (wgrad_tc_ok(s) ? BDBNN_TC_WGRAD : 0) | (v2 ? BDBNN_TC_FWD8 : 0);
 }
 
 extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, int32_t fmt,
@@ -361,6 +364,34 @@ extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_
   L.out_step = 1; L.OHf = s->Ho; L.OWf = s->Wo;
   L.alpha = alpha; L.out = y; L.fmt = fmt;
   return launch_tc_conv<0>(L, cudaStream_t(stream));
+}
+
+extern "C" int bdbnn_binconv_fwd_tc8(const uint8_t* xb_fp8, const uint8_t* wf_fp8, const float* alpha, float* y,
+                                     const bdbnn_conv_shape* s, void* stream) {
+  int rc = validate_shape(s);
+  if (rc) return rc;
+  BDBNN_REQUIRE(xb_fp8 && wf_fp8 && alpha && y, "binconv_fwd_tc8: NULL pointer");
+  if (!tc_shape_ok(s) || s->Cin % 128 != 0) {
+    set_error("binconv_fwd_tc8: shape not supported by the fp8 tcgen05 path");
+    return BDBNN_ERR_UNSUPPORTED;
+  }
+  TcConvLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.A = reinterpret_cast<const uint16_t*>(xb_fp8); L.IH = s->H; L.IW = s->W; L.Kc = s->Cin; L.a_halves = 1;
+  L.in_step = s->stride;
+  L.B = reinterpret_cast<const uint16_t*>(wf_fp8); L.b_taps = s->kh * s->kw; L.Nout = s->Cout;
+  L.NIMG = s->N; L.OH = s->Ho; L.OW = s->Wo;
+  for (int r = 0; r < s->kh; ++r)
+    for (int q = 0; q < s->kw; ++q) {
+      const int t = r * s->kw + q;
+      L.dh[t] = int8_t(r - s->pad); L.dw[t] = int8_t(q - s->pad); L.tb[t] = uint8_t(t);
+    }
+  L.n_taps = s->kh * s->kw;
+  L.out_step = 1; L.OHf = s->Ho; L.OWf = s->Wo;
+  L.alpha = alpha; L.out = y; L.fmt = -1;
+  rc = launch_tc_conv2(L, 0, cudaStream_t(stream));
+  if (rc == BDBNN_ERR_UNSUPPORTED) set_error("binconv_fwd_tc8: geometry not supported by the persistent kernel");
+  return rc;
 }
 
 extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,

@@ -40,7 +40,9 @@ struct TcConv2Params {
   int32_t stages;
   int32_t dbg;               // BDBNN_TC_DBG experiment bits: 1 = no global stores, 2 = no TMEM loads, 4 = no MMAs
   uint32_t stage_bytes, b_bytes;
-  int32_t fmt;
+  int32_t fmt;               // BDBNN_FMT_* or -1 (fp8)
+  int32_t row_bytes;         // bytes per pixel row of a K block: 128 (16-bit x 64 ch, fp8 x 128 ch) or 64 (fp8 x 64 ch)
+  int32_t kb_elems;          // channels per K block
   const uint32_t* amax_bits;
   const float* add;
   const float* alpha;
@@ -146,8 +148,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(smem_u32(&pempty_bar[pa]), ((pcount >> 1) & 1u) ^ 1u);
             BDBNN_TR(0, 1);
             const uint32_t pb = smem_u32(&pfull_bar[pa]);
-            mbar_expect_tx(pb, uint32_t(p.PW * p.PH * p.HBNI) * 128u);
-            tma_load_4d(smem_base + pa * p.patch_bytes, &tmA, pb, kb * 64, p.dw_min, g.h0 + p.dh_min, g.n0);
+            mbar_expect_tx(pb, uint32_t(p.PW * p.PH * p.HBNI) * uint32_t(p.row_bytes));
+            tma_load_4d(smem_base + pa * p.patch_bytes, &tmA, pb, kb * p.kb_elems, p.dw_min, g.h0 + p.dh_min, g.n0);
             ++pcount;
           }
           for (int ti = 0; ti < p.n_taps; ++ti, ++it) {
@@ -159,15 +161,15 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (p.halo) {
               mbar_expect_tx(fb, p.b_bytes);
             } else {
-              mbar_expect_tx(fb, p.b_bytes + uint32_t(g.ntl * p.BNI * p.BH * p.BW) * 128u);
+              mbar_expect_tx(fb, p.b_bytes + uint32_t(g.ntl * p.BNI * p.BH * p.BW) * uint32_t(p.row_bytes));
               for (int j = 0; j < g.ntl; ++j) {
                 const int t = sup * p.TS + j;
                 const int tile_n = t / p.tiles_h, tile_h = t - tile_n * p.tiles_h;
-                tma_load_4d(dst + p.b_bytes + uint32_t(j) * (kTileM * 128u), &tmA, fb, kb * 64, p.tap_dw[ti],
+                tma_load_4d(dst + p.b_bytes + uint32_t(j) * (kTileM * uint32_t(p.row_bytes)), &tmA, fb, kb * p.kb_elems, p.tap_dw[ti],
                             tile_h * p.BH * p.in_step + p.tap_dh[ti], tile_n * p.BNI);
               }
             }
-            tma_load_2d(dst, &tmB, fb, p.tap_b[ti] * p.Kc + kbb * 64, nn0);
+            tma_load_2d(dst, &tmB, fb, p.tap_b[ti] * p.Kc + kbb * p.kb_elems, nn0);
           }
           BDBNN_TR(0, 2);
         }
@@ -176,8 +178,12 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 5) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN), uint32_t(p.fmt));
-      const uint32_t desc_hi = kmajor128_hi();
+      const bool f8 = p.fmt < 0;
+      const uint32_t idesc = f8 ? make_idesc_f8(kTileM, uint32_t(p.BN))
+                                : make_idesc_bf16(kTileM, uint32_t(p.BN), uint32_t(p.fmt));
+      const uint32_t desc_hi = kmajor_hi(uint32_t(p.row_bytes));
+      const uint32_t row16 = uint32_t(p.row_bytes) >> 4;          // descriptor-address units per pixel row
+      const int k_steps = p.row_bytes / 32;
       uint32_t it = 0, pcount = 0, wcount = 0;
       int tr_n = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wcount) {
@@ -207,14 +213,20 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_fence_after();
             if (ti == 0) BDBNN_TR(1, 3);
             const uint32_t b_src = ring_base + stage * p.stage_bytes;
-            const uint32_t b_lo = kmajor128_lo(b_src);
-            // low descriptor word advances by 8 per 128-byte row: 1024 per M tile
-            uint32_t a_lo = p.halo ? kmajor128_lo(patch) + tap_shift_rows[ti] * 8u
-                                   : kmajor128_lo(b_src + p.b_bytes);
+            const uint32_t b_lo = kmajor_lo(b_src);
+            // the low descriptor word advances by row_bytes/16 per pixel row, 128 rows per M tile
+            uint32_t a_lo = p.halo ? kmajor_lo(patch) + tap_shift_rows[ti] * row16 : kmajor_lo(b_src + p.b_bytes);
             uint32_t acc = acc0;
-            if (!(p.dbg & 4))
-              for (int j = 0; j < g.ntl; ++j, a_lo += kTileM * 8u, acc += uint32_t(p.BN))
-                umma_bf16_k4(acc, a_lo, b_lo, desc_hi, idesc, first ? 0u : 1u);
+            if (!(p.dbg & 4)) {
+              for (int j = 0; j < g.ntl; ++j, a_lo += kTileM * row16, acc += uint32_t(p.BN)) {
+                if (f8) {
+                  for (int k = 0; k < k_steps; ++k)
+                    umma_f8_split(acc, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc, (!first || k > 0) ? 1u : 0u);
+                } else {
+                  umma_bf16_k4(acc, a_lo, b_lo, desc_hi, idesc, first ? 0u : 1u);
+                }
+              }
+            }
             first = false;
             umma_commit(smem_u32(&empty_bar[stage]));
           }
@@ -347,11 +359,16 @@ long long* get_tc_trace() { return g_trace; }
 // mode: 0 = alpha epilogue (forward), 1 = STE-mask epilogue (dgrad)
 int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   if (L.Kc % 64 != 0 || L.n_taps <= 0) return BDBNN_ERR_UNSUPPORTED;
+  const bool f8 = L.fmt < 0;
+  const int esize = f8 ? 1 : 2;
+  const int kb_elems = f8 ? (L.Kc % 128 == 0 ? 128 : 64) : 64;
+  const uint32_t row_bytes = uint32_t(kb_elems * esize);
   if (L.Nout != 64 && L.Nout % 128 != 0) return BDBNN_ERR_UNSUPPORTED;
   TcConv2Params p;
   memset(&p, 0, sizeof(p));
   p.OW = L.OW; p.OH = L.OH; p.NIMG = L.NIMG;
-  p.Kc = L.Kc; p.n_kb = L.Kc / 64; p.a_halves = L.a_halves; p.in_step = L.in_step;
+  p.Kc = L.Kc; p.n_kb = L.Kc / kb_elems; p.a_halves = L.a_halves; p.in_step = L.in_step;
+  p.row_bytes = int(row_bytes); p.kb_elems = kb_elems;
   p.n_taps = L.n_taps;
   memcpy(p.tap_dh, L.dh, sizeof(p.tap_dh));
   memcpy(p.tap_dw, L.dw, sizeof(p.tap_dw));
@@ -371,7 +388,7 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   p.NB = 512 / (p.TS * p.BN);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
   p.fmt = L.fmt; p.amax_bits = L.amax_bits; p.add = L.add;
-  p.b_bytes = uint32_t(p.BN) * 128u;
+  p.b_bytes = uint32_t(p.BN) * row_bytes;
 
   int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
   for (int i = 0; i < p.n_taps; ++i) {
@@ -404,10 +421,10 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
       p.n_supers = L.NIMG * p.supers_per_img;
     }
     const uint32_t rows = uint32_t(super_rows + dh_span * PW + dw_span);
-    p.patch_bytes = (rows * 128u + 1023u) & ~1023u;
-    if (uint32_t(p.PW * p.PH * p.HBNI) * 128u > p.patch_bytes) return BDBNN_ERR_UNSUPPORTED;
+    p.patch_bytes = (rows * row_bytes + 1023u) & ~1023u;
+    if (uint32_t(p.PW * p.PH * p.HBNI) * row_bytes > p.patch_bytes) return BDBNN_ERR_UNSUPPORTED;
     p.stage_bytes = (p.b_bytes + 1023u) & ~1023u;
-    rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.PW, p.PH, p.HBNI, 1);
+    rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, kb_elems, p.PW, p.PH, p.HBNI, 1, esize);
   } else {
     p.halo = 0;
     p.BW = L.OW;
@@ -424,11 +441,11 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
     p.tiles_h = (L.OH + p.BH - 1) / p.BH;
     p.n_mtiles = p.tiles_h * ((L.NIMG + p.BNI - 1) / p.BNI);
     p.n_supers = (p.n_mtiles + p.TS - 1) / p.TS;
-    p.stage_bytes = (p.b_bytes + uint32_t(p.TS) * kTileM * 128u + 1023u) & ~1023u;
-    rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.BW, p.BH, p.BNI, L.in_step);
+    p.stage_bytes = (p.b_bytes + uint32_t(p.TS) * kTileM * row_bytes + 1023u) & ~1023u;
+    rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, kb_elems, p.BW, p.BH, p.BNI, L.in_step, esize);
   }
   if (rc) return rc;
-  rc = make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, 64, p.BN);
+  rc = make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, kb_elems, p.BN, esize);
   if (rc) return rc;
   const uint32_t kStaging = 4u * 4096u;   // epilogue transpose tiles
   const uint32_t fixed = (p.halo ? 2u * p.patch_bytes : 0u) + kStaging;

@@ -88,6 +88,7 @@ def algorithmic_bytes(kernel, sh, gh=1):
         "act_pack_tc": 4 * n_in + 2 * n_in // 8 + 2 * n_in,   # + bf16 copy
         "fwd_xnor": n_in // 8 + n_w // 8 + 4 * n_out,         # read bits, write fp32 y
         "fwd_tc": 2 * n_in + 2 * n_w + 4 * n_out,             # read bf16 +-1, write fp32 y
+        "fwd_tc8": n_in + n_w + 4 * n_out,                    # read fp8 +-1, write fp32 y
         "dgrad": 4 * n_out + n_w // 8 + n_in // 8 + 4 * n_in,  # read gy, bits; write gx
         "wgrad": 4 * n_out + n_in // 8 + n_w // 8 + 4 * n_w,
         "grad_pack": 4 * n_out + 2 * gh * n_out,
@@ -171,17 +172,27 @@ class _BinConv2d(torch.autograd.Function):
         alpha = torch.empty((cout,), dtype=torch.float32, device=dev)
         wsign = torch.empty((cout, T, cw), **i32)
         wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
-        wf = wt = gscale = inv_gscale = None
+        wf = wt = gscale = inv_gscale = wf8 = xb8 = None
+        use8 = tc and bool(use & 8) and fwd8_enabled()
+        if use8:
+            wf8 = torch.empty((cout, T, cin), dtype=torch.uint8, device=dev)
+            xb8 = torch.empty((n, h, wd, cin), dtype=torch.uint8, device=dev)
+            _lib.check(L.bdbnn_bits_to_fp8(_p(sign_bits), n * h * wd, cin, _p(xb8), st), "bits_to_fp8")
+            _lib.count(1)
         if tc:
             wf = torch.empty((cout, T, cin), dtype=torch.int16, device=dev)
             wt = torch.empty((cin, T, cout), dtype=torch.int16, device=dev)
             gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
             inv_gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
         _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask),
-                                       _p(wf), _p(wt), _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
+                                       _p(wf), _p(wt), _p(wf8), _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
         y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
                         memory_format=torch.channels_last)
-        if tc:
+        if use8:
+            with _timed("binconv_fwd_tc8", key, algorithmic_bytes("fwd_tc8", sh)):
+                _lib.check(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), ctypes.byref(sh), st),
+                           "binconv_fwd_tc8")
+        elif tc:
             with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
                 _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), st),
                            "binconv_fwd_tc")
@@ -439,6 +450,11 @@ def max_pool2d_nhwc(x, kernel_size, stride, padding):
 # Fused unit: z = BatchNorm_train(binconv(x)) + residual, emitting the next conv's packs (csrc/bn.cu)
 # ---------------------------------------------------------------------------------------------------
 _FUSE_ENV = "BDBNN_FUSE_BN"     # 1 (default) | 0
+_FWD8_ENV = "BDBNN_FWD8"        # 1 (default): forward on fp8 e4m3 +-1 operands when the shape allows | 0
+
+
+def fwd8_enabled():
+    return os.environ.get(_FWD8_ENV, "1") != "0"
 
 
 def fuse_enabled():
@@ -448,7 +464,7 @@ def fuse_enabled():
 def unit_supported(x_shape, w_shape, stride, padding):
     """The fused unit needs all three tcgen05 kernels for the conv shape."""
     sh = conv_shape(x_shape, w_shape, stride, padding)
-    return int(_lib.lib().bdbnn_tc_supported(ctypes.byref(sh))) == 7
+    return (int(_lib.lib().bdbnn_tc_supported(ctypes.byref(sh))) & 7) == 7
 
 
 class _ConvBNAddUnit(torch.autograd.Function):
@@ -457,7 +473,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride,
-                padding, xs, xm, xb, res_is_x):
+                padding, xs, xm, xb, xb8, res_is_x):
         _require_cuda(x, "conv_bn_add(x)")
         ctx.set_materialize_grads(False)     # no zero tensors for the (integer) pack outputs in backward
         L = _lib.lib()
@@ -470,6 +486,8 @@ class _ConvBNAddUnit(torch.autograd.Function):
         gname, gcode, ghalves, fmt = grad_mode()
         key = _shape_key(sh)
         i32 = dict(dtype=torch.int32, device=dev)
+        caps = int(L.bdbnn_tc_supported(ctypes.byref(sh)))
+        use8 = bool(caps & 8) and fwd8_enabled()
         if xs is None:
             xc = _nhwc(x.detach())
             xs = torch.empty((n, h, wd, cw), **i32)
@@ -478,21 +496,32 @@ class _ConvBNAddUnit(torch.autograd.Function):
             with _timed("act_pack", key, algorithmic_bytes("act_pack_tc", sh)):
                 _lib.check(L.bdbnn_act_pack(_p(xc), n * h * wd, cin, _p(xs), _p(xm), _p(xb), fmt, st), "act_pack")
             _lib.count(1)
+            xb8 = None
+        if use8 and xb8 is None:
+            xb8 = torch.empty((n, h, wd, cin), dtype=torch.uint8, device=dev)
+            _lib.check(L.bdbnn_bits_to_fp8(_p(xs), n * h * wd, cin, _p(xb8), st), "bits_to_fp8")
+            _lib.count(1)
         w = weight.detach().contiguous()
         alpha = torch.empty((cout,), dtype=torch.float32, device=dev)
         wsign = torch.empty((cout, T, cw), **i32)
         wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
-        wf = torch.empty((cout, T, cin), dtype=torch.int16, device=dev)
+        wf = torch.empty((cout, T, cin), dtype=torch.int16, device=dev) if not use8 else None
+        wf8 = torch.empty((cout, T, cin), dtype=torch.uint8, device=dev) if use8 else None
         wt = torch.empty((cin, T, cout), dtype=torch.int16, device=dev)
         gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
         inv_gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
         _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask), _p(wf), _p(wt),
-                                       _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
+                                       _p(wf8), _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
         y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
                         memory_format=torch.channels_last)
-        with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
-            _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), st),
-                       "binconv_fwd_tc")
+        if use8:
+            with _timed("binconv_fwd_tc8", key, algorithmic_bytes("fwd_tc8", sh)):
+                _lib.check(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), ctypes.byref(sh), st),
+                           "binconv_fwd_tc8")
+        else:
+            with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
+                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), st),
+                           "binconv_fwd_tc")
         _lib.count(3)
         n_pix = n * sh.Ho * sh.Wo
         if res_is_x:            # identity shortcut: the residual IS the conv input (one autograd edge)
@@ -509,10 +538,12 @@ class _ConvBNAddUnit(torch.autograd.Function):
         zs = torch.empty((n, sh.Ho, sh.Wo, cout // 32), **i32) if pack else None
         zm = torch.empty((n, sh.Ho, sh.Wo, cout // 32), **i32) if pack else None
         zb = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.int16, device=dev) if pack else None
-        with _timed("bn_fwd", key, (4 + 12 + (2.25 if pack else 0)) * n_pix * cout):
+        zb8 = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.uint8, device=dev) if (pack and fwd8_enabled()) else None
+        with _timed("bn_fwd", key, (4 + 12 + (2.25 if pack else 0) + (1 if zb8 is not None else 0)) * n_pix * cout):
             _lib.check(L.bdbnn_bn_fwd(_p(y), _p(rc), _p(gamma.detach()), _p(beta.detach()), n_pix, cout, float(eps),
                                       float(momentum), _p(running_mean), _p(running_var), _p(sums), _p(ymax),
-                                      _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm), _p(zb), fmt, st), "bn_fwd")
+                                      _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm), _p(zb), _p(zb8), fmt, st),
+                       "bn_fwd")
         _lib.count(3)
         ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
         ctx.shapes = (tuple(x.shape), tuple(weight.shape))
@@ -520,14 +551,17 @@ class _ConvBNAddUnit(torch.autograd.Function):
         ctx.res_is_x = bool(res_is_x)
         ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale)
         if pack:
-            ctx.mark_non_differentiable(zs, zm, zb)
-            return z, zs, zm, zb
-        return z, None, None, None
+            if zb8 is not None:
+                ctx.mark_non_differentiable(zs, zm, zb, zb8)
+            else:
+                ctx.mark_non_differentiable(zs, zm, zb)
+            return z, zs, zm, zb, zb8
+        return z, None, None, None, None
 
     @staticmethod
-    def backward(ctx, gz, _g1, _g2, _g3):
+    def backward(ctx, gz, _g1, _g2, _g3, _g4):
         if gz is None:
-            return (None,) * 15
+            return (None,) * 16
         L = _lib.lib()
         sh = ctx.sh
         st = _stream()
@@ -571,7 +605,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
             _lib.count(2)
         gres = gz if (ctx.has_res and ctx.needs_input_grad[4]) else None
         return (gx, gw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
-                gres, None, None, None, None, None, None, None, None, None, None)
+                gres, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride, padding):
@@ -580,12 +614,14 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
     own activation pack; x's own `_bdbnn_pack` (if present and of the current format) is consumed."""
     fmt = grad_mode()[3]
     pk = getattr(x, "_bdbnn_pack", None)
-    xs = xm = xb = None
+    xs = xm = xb = xb8 = None
     if pk is not None and pk[3] == fmt:
         xs, xm, xb = pk[:3]
+        xb8 = pk[4] if len(pk) > 4 else None
     res_is_x = residual is x and x.shape[1] == weight.shape[0] and int(stride) == 1
-    z, zs, zm, zb = _ConvBNAddUnit.apply(x, weight, gamma, beta, None if res_is_x else residual, running_mean,
-                                         running_var, momentum, eps, int(stride), int(padding), xs, xm, xb, res_is_x)
+    z, zs, zm, zb, zb8 = _ConvBNAddUnit.apply(x, weight, gamma, beta, None if res_is_x else residual, running_mean,
+                                              running_var, momentum, eps, int(stride), int(padding), xs, xm, xb, xb8,
+                                              res_is_x)
     if zs is not None:
-        z._bdbnn_pack = (zs, zm, zb, fmt)
+        z._bdbnn_pack = (zs, zm, zb, fmt, zb8)
     return z

@@ -67,6 +67,7 @@ BDBNN_API int bdbnn_debug_trace(long long* device_buf);
 #define BDBNN_TC_FWD 1
 #define BDBNN_TC_DGRAD 2
 #define BDBNN_TC_WGRAD 4
+#define BDBNN_TC_FWD8 8   /* fp8 (e4m3 +-1) forward: bdbnn_binconv_fwd_tc8 */
 BDBNN_API int bdbnn_tc_supported(const bdbnn_conv_shape* s);
 
 /* ---- activation sign/pack ---------------------------------------------------------------------
@@ -86,11 +87,14 @@ BDBNN_API int bdbnn_act_pack(const float* x, int64_t n_pix, int32_t C, uint32_t*
  *   wmask_bits[e/32] bit e%32      = (|W.flat[e]| <= 1)   in OIHW flat order  (STE mask)
  *   wf_bf16[(o*T+t)*Cin+c]   = sign(W[o,c,t]) as bf16              (fwd  B operand; may be NULL)
  *   wt_bf16[(c*T+t)*Cout+o]  = alpha[o]>0 ? sign(W[o,c,T-1-t]) : 0 (dgrad B operand; may be NULL)
+ *   wf_fp8 [(o*T+t)*Cin+c]   = sign(W[o,c,t]) as e4m3 byte           (fwd_tc8 B operand; may be NULL)
  *   gscale[o] = alpha[o] > 0 ? alpha[o] : 1 ;  inv_gscale[o] = 1/gscale[o]   (may be NULL) */
 BDBNN_API int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
                       float* alpha, uint32_t* wsign_bits, uint32_t* wmask_bits,
-                      uint16_t* wf_bf16, uint16_t* wt_bf16, float* gscale, float* inv_gscale,
-                      int32_t fmt, void* stream);
+                      uint16_t* wf_bf16, uint16_t* wt_bf16, uint8_t* wf_fp8, float* gscale,
+                      float* inv_gscale, int32_t fmt, void* stream);
+/* sign bits -> fp8 e4m3 +-1 bytes [n_pix][C] (0x38 = +1, 0xB8 = -1), C % 32 == 0: operand of fwd_tc8. */
+BDBNN_API int bdbnn_bits_to_fp8(const uint32_t* sign_bits, int64_t n_pix, int32_t C, uint8_t* xb_fp8, void* stream);
 
 /* ---- binary conv forward, XNOR-popcount (bit-serial, CUDA cores) -------------------------------
  * y[n,ho,wo,o] = alpha[o] * sum_{valid taps} (Cin - 2*popc(xbits ^ wbits)); zero padding
@@ -103,6 +107,11 @@ BDBNN_API int bdbnn_binconv_fwd_xnor(const uint32_t* sign_bits, const uint32_t* 
  * Same result as bdbnn_binconv_fwd_xnor.  Requires bdbnn_tc_supported(s). */
 BDBNN_API int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, int32_t fmt,
                          const float* alpha, float* y, const bdbnn_conv_shape* s, void* stream);
+
+/* Same forward on fp8 (e4m3) +-1 operands: half the operand bytes and twice the K per MMA of the
+ * 16-bit kernel; still exact.  Requires bdbnn_tc_supported(s) & BDBNN_TC_FWD8. */
+BDBNN_API int bdbnn_binconv_fwd_tc8(const uint8_t* xb_fp8, const uint8_t* wf_fp8, const float* alpha, float* y,
+                          const bdbnn_conv_shape* s, void* stream);
 
 /* ---- backward: data gradient -------------------------------------------------------------------
  * gx[n,h,w,c] = mask(n,h,w,c) * sum_{t,o} gy[n,ho,wo,o] * alpha[o] * sign(W[o,c,t])
@@ -187,7 +196,8 @@ BDBNN_API int bdbnn_kd_layer_multi_bwd(const float* const* wt_ptrs_host, const i
  *          running_mean/var (may be NULL) updated with `momentum` (unbiased var), then
  *          z = gamma*(y-mean)*invstd + beta (+ residual if non-NULL).
  *          If sign_bits != NULL (needs C % 32 == 0) also emits what bdbnn_act_pack(z) would:
- *          sign_bits, mask_bits, xb (format fmt) — the next binary conv then skips its own pack.
+ *          sign_bits, mask_bits, xb (format fmt) and, if xb_fp8 != NULL, the e4m3 +-1 bytes — the next
+ *          binary conv then skips its own pack.
  *          ymax_bits[C] receives max|y| per channel (float bits) for the backward's FP16S bound.
  *          Scratch: sums_ws double[2C], ab_ws float[2C].
  * bn_bwd_pack : from gz (grad of z) and the saved y/mean/invstd computes dgamma, dbeta and writes
@@ -199,7 +209,7 @@ BDBNN_API int bdbnn_bn_fwd(const float* y, const float* residual, const float* g
                  int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
                  float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean, float* invstd,
                  float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits, uint16_t* xb,
-                 int32_t fmt, void* stream);
+                 uint8_t* xb_fp8, int32_t fmt, void* stream);
 BDBNN_API int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* mean, const float* invstd,
                       const float* gamma, const float* gscale, const uint32_t* ymax_bits, int64_t n_pix,
                       int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits, float* consts_ws,

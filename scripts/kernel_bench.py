@@ -67,6 +67,8 @@ def main():
         wf = torch.empty((cout, 9, cin), dtype=torch.int16, device="cuda")
         wt = torch.empty((cin, 9, cout), dtype=torch.int16, device="cuda")
         amax = torch.zeros(1, dtype=torch.int32, device="cuda")
+        wf8 = torch.empty((cout, 9, cin), dtype=torch.uint8, device="cuda")
+        xb8 = torch.empty((n, hw, hw, cin), dtype=torch.uint8, device="cuda")
         gs, igs = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
         y = torch.empty((n, sh.Ho, sh.Wo, cout), device="cuda")
         gy = torch.randn_like(y)
@@ -80,12 +82,13 @@ def main():
         ck = _lib.check
         kernels = {
             "act_pack" + ("_tc" if tc else ""): lambda: ck(L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb if tc else None), FMT, st), "p"),
-            "weight_pack": lambda: ck(L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(gs), _p(igs), FMT, st), "w"),
+            "weight_pack": lambda: ck(L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(wf8), _p(gs), _p(igs), FMT, st), "w"),
         }
         if tc:
             nb = int(L.bdbnn_wgrad_tc_workspace_bytes(shp))
             wsb = torch.empty(max(nb, 4) // 4, device="cuda")
             kernels.update({
+                "fwd_tc8": lambda: (ck(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), shp, st), "f8") if caps & 8 else None),
                 "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), FMT, _p(alpha), _p(y), shp, st), "f"),
                 "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, GC, _p(amax), _p(gys), st), "g"),
                 "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), GC, _p(amax), _p(wt), _p(mb), _p(None), _p(gx), shp, st), "d"),
@@ -100,6 +103,9 @@ def main():
                 "dgrad": lambda: ck(L.bdbnn_binconv_dgrad(_p(gy), _p(ws), _p(alpha), _p(mb), _p(gx), shp, st), "d"),
                 "wgrad": lambda: ck(L.bdbnn_binconv_wgrad(_p(gy), _p(sb), _p(wm), _p(gw), shp, st), "w"),
             })
+        if tc:
+            ck(L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb), FMT, st), "p")
+            ck(L.bdbnn_bits_to_fp8(_p(sb), n * hw * hw, cin, _p(xb8), st), "b8")
         for kname, fn in kernels.items():
             if a.kernels and kname not in a.kernels.split(",") and "pack" not in kname:
                 continue

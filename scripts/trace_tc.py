@@ -23,10 +23,15 @@ y = torch.empty((n, hw, hw, cout), device="cuda"); gy = torch.randn_like(y)
 gys = torch.empty((n, hw, hw, 2 * cout), dtype=torch.bfloat16, device="cuda"); gx = torch.empty_like(x)
 st = _stream(); shp = ctypes.byref(sh)
 L.bdbnn_act_pack(_p(x), n * hw * hw, cin, _p(sb), _p(mb), _p(xb), 1, st)
-L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(gs), _p(igs), 1, st)
+L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(None), _p(gs), _p(igs), 1, st)
 L.bdbnn_grad_pack(_p(gy), _p(gs), n * hw * hw, cout, 2, _p(None), _p(gys), st)
 nb = int(L.bdbnn_wgrad_tc_workspace_bytes(shp)); wsb = torch.empty(max(nb, 4) // 4, device="cuda"); gw = torch.empty_like(w)
-if which == "wgrad":
+wf8 = torch.empty((cout, 9, cin), dtype=torch.uint8, device="cuda"); xb8 = torch.empty((n, hw, hw, cin), dtype=torch.uint8, device="cuda")
+L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(wf8), _p(gs), _p(igs), 1, st)
+L.bdbnn_bits_to_fp8(_p(sb), n * hw * hw, cin, _p(xb8), st)
+if which == "fwd8":
+    run = lambda: L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), shp, st)
+elif which == "wgrad":
     run = lambda: L.bdbnn_binconv_wgrad_tc(_p(gys), 2, _p(None), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st)
 else:
   run = (lambda: L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), 1, _p(alpha), _p(y), shp, st)) if which == "fwd" else \

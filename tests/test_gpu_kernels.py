@@ -105,8 +105,9 @@ def test_weight_pack(shape):
     wtt = torch.empty((cin, T, cout), dtype=wdt, device="cuda")
     gs = torch.empty(cout, device="cuda")
     igs = torch.empty(cout, device="cuda")
+    wf8 = torch.zeros((cout, T, cin), dtype=torch.uint8, device="cuda")
     _lib.check(L.bdbnn_weight_pack(_p(wd), cout, cin, kh, kw, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wtt),
-                                   _p(gs), _p(igs), fmt, _stream()), "weight_pack")
+                                   _p(wf8), _p(gs), _p(igs), fmt, _stream()), "weight_pack")
     torch.cuda.synchronize()
     a_ref = B.weight_alpha(wt.double()).float()
     torch.testing.assert_close(alpha.cpu(), a_ref, rtol=2e-6, atol=0)
@@ -114,6 +115,7 @@ def test_weight_pack(shape):
     assert torch.equal(_as_u32(wm), B.pack_flat_mask(wt))
     sg = B.sign_pm1(wt).reshape(cout, cin, T)
     assert torch.equal(wf.float().cpu(), sg.permute(0, 2, 1))
+    assert torch.equal(wf8.view(torch.float8_e4m3fn).float().cpu(), sg.permute(0, 2, 1))
     live = (alpha.cpu() > 0).float().view(cout, 1, 1)
     exp_wt = (sg * live).flip(2).permute(1, 2, 0)          # [cin, T(flipped), cout]
     assert torch.equal(wtt.float().cpu(), exp_wt)
@@ -317,3 +319,13 @@ def test_maxpool_nhwc_matches_torch(geom):
     gd0, gr0 = torch.nan_to_num(gd[:, sel]), torch.nan_to_num(gr[:, sel])
     torch.testing.assert_close(gd0, gr0, rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(gd[:, 1].sum(), gr[:, 1].sum(), rtol=1e-5, atol=1e-5)
+
+
+def test_bits_to_fp8():
+    _lib, L, _p, _stream, _ = _env()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 64, 5, 7, generator=g)
+    bits = B.pack_bits_nhwc(x).to(torch.int32).cuda()          # low 32 bits
+    out = torch.zeros((3, 5, 7, 64), dtype=torch.uint8, device="cuda")
+    _lib.check(L.bdbnn_bits_to_fp8(_p(bits), 3 * 5 * 7, 64, _p(out), _stream()), "bits_to_fp8")
+    assert torch.equal(out.view(torch.float8_e4m3fn).float().cpu(), B.sign_pm1(x).permute(0, 2, 3, 1))

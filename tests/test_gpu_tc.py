@@ -39,7 +39,7 @@ def _caps(shape):
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)
-def test_fwd_tc_equals_xnor_bit_exact_and_oracle(shape):
+def test_fwd_tc_equals_xnor_bit_exact_and_oracle(shape, monkeypatch):
     from bdbnn_b200.functional import binconv2d
     assert _caps(shape) & 1
     n, cin, h, w, cout, k, stride, pad = shape
@@ -49,9 +49,11 @@ def test_fwd_tc_equals_xnor_bit_exact_and_oracle(shape):
     wt = torch.randn(cout, cin, k, k, generator=g) * 0.1
     xd = x.cuda().contiguous(memory_format=torch.channels_last)
     wd = wt.cuda()
-    y_tc = binconv2d(xd, wd, stride, pad, "tc")
+    y_tc = binconv2d(xd, wd, stride, pad, "tc")          # fp8 operands where the shape allows (default)
     y_x = binconv2d(xd, wd, stride, pad, "xnor")
     assert torch.equal(y_tc, y_x)                       # both: alpha[o] * exact integer, same fp32 multiply
+    monkeypatch.setenv("BDBNN_FWD8", "0")               # 16-bit operand forward
+    assert torch.equal(binconv2d(xd, wd, stride, pad, "tc"), y_x)
     ref = B.binconv_forward(x.double(), wt.double(), stride, pad).float()
     torch.testing.assert_close(y_tc.cpu(), ref, rtol=3e-6, atol=0)
 
@@ -177,7 +179,8 @@ def test_fused_conv_bn_add_unit_vs_oracle(shape, with_res, mode, monkeypatch):
         err = (got.cpu().double() - ref).abs().max().item()
         assert err <= (1e-5 if name in ("dgamma", "dbeta", "gres") else tol) * scale, (name, err, scale)
     # the emitted packs are exactly act_pack(z)
-    zs, zm, zb, fmt = z._bdbnn_pack
+    zs, zm, zb, fmt, zb8 = z._bdbnn_pack
+    assert torch.equal(zb8.view(torch.float8_e4m3fn).float().cpu(), B.sign_pm1(z.detach().cpu()).permute(0, 2, 3, 1))
     zc = z.detach().cpu()
     assert torch.equal(zs.cpu().to(torch.int64) & 0xFFFFFFFF, B.pack_bits_nhwc(zc))
     assert torch.equal(zm.cpu().to(torch.int64) & 0xFFFFFFFF, B.pack_mask_nhwc(zc))
