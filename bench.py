@@ -49,6 +49,25 @@ def parse():
     return ap.parse_args()
 
 
+TRAFFIC_KERNEL = {  # KernelTimer family -> kernel name in profiles/*_dram_traffic.json (ncu --set full)
+    "binconv_dgrad_tc": "tc_conv2_kernel<1>", "binconv_fwd_tc": "tc_conv2_kernel<0>",
+    "binconv_fwd_tc8": "tc_conv2_kernel<0>", "binconv_wgrad_tc": "tc_wgrad_kernel",
+    "bn_fwd": "bn_apply_add_pack_kernel<1>", "bn_bwd_pack": "bn_bwd_pack_kernel<3>",
+}
+
+
+def ncu_traffic(family):
+    """dram__bytes_read+write per launch of the family's main kernel, from the newest committed ncu capture."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")))
+    if not files or family not in TRAFFIC_KERNEL:
+        return None, None
+    with open(files[-1]) as fh:
+        d = json.load(fh)
+    e = d.get(TRAFFIC_KERNEL[family])
+    return (round(e["dram_bytes_per_launch"]), os.path.basename(files[-1])) if e else (None, None)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -374,8 +393,10 @@ def main():
     roofline = None
     if kernels:
         top = kernels[0]
+        traffic, traffic_src = ncu_traffic(top["kernel"])
         roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": round(top["achieved_gbs"] / peak, 4), "traffic": None,
+                    "unit": "GB/s", "frac": round(top["achieved_gbs"] / peak, 4), "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": peak_src,
                     "how": "sum of per-launch algorithmic bytes (DESIGN.md §4) / sum of CUDA-event durations "
                            "of that kernel family over the timed region"}
