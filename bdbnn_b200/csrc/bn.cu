@@ -53,7 +53,7 @@ bn_reduce_kernel(const float4* __restrict__ p0, const float4* __restrict__ p1, c
     is = *reinterpret_cast<const float4*>(invstd + c4 * 4);
   }
   float4 sa = make_float4(0, 0, 0, 0), sb = sa, mx = sa;
-#pragma unroll 4
+#pragma unroll 8
   for (int64_t p = gtid / C4; p < n_pix; p += p_step) {
     const float4 u = __ldcs(p0 + p * C4 + c4);
     if (BWD) {   // u = gz, v = y:  a = gz, b = gz * yhat, c = |gz|
@@ -229,10 +229,10 @@ bn_bwd_pack_kernel(const float4* __restrict__ gz, const float4* __restrict__ y, 
   }
 }
 
-static int bn_grid(int64_t work, int C4) {
-  // full-occupancy grid whose thread count is a multiple of C4 (C4 in {4,..,128} divides 256*k)
+static int bn_grid(int64_t work, int C4, int per_sm = 8) {
+  // grid whose thread count is a multiple of C4 (C4 in {4,..,128} divides 256*k); per_sm blocks per SM at most
   int64_t blocks = (work + kBnThreads - 1) / kBnThreads;
-  const int64_t cap = int64_t(num_sms()) * 8;
+  const int64_t cap = int64_t(num_sms()) * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   while ((blocks * kBnThreads) % C4 != 0) ++blocks;
@@ -265,7 +265,7 @@ extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* 
   const int C4 = C / 4;
   BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
   BDBNN_CUDA(cudaMemsetAsync(ymax_bits, 0, size_t(C) * sizeof(uint32_t), st));
-  bn_reduce_kernel<false><<<bn_grid(n_pix * C4, C4), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+  bn_reduce_kernel<false><<<bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
       reinterpret_cast<const float4*>(y), nullptr, nullptr, nullptr, n_pix, C4, sums_ws, ymax_bits);
   rc = check_launch("bn_reduce_kernel<fwd>");
   if (rc) return rc;
@@ -306,7 +306,7 @@ extern "C" int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* m
   const int C4 = C / 4;
   BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
   BDBNN_CUDA(cudaMemsetAsync(gmax_bits, 0, size_t(C) * sizeof(uint32_t), st));
-  bn_reduce_kernel<true><<<bn_grid(n_pix * C4, C4), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+  bn_reduce_kernel<true><<<bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
       reinterpret_cast<const float4*>(gz), reinterpret_cast<const float4*>(y), mean, invstd, n_pix, C4, sums_ws,
       gmax_bits);
   rc = check_launch("bn_reduce_kernel<bwd>");
@@ -327,4 +327,214 @@ extern "C" int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* m
   else
     bn_bwd_pack_kernel<1><<<grid, kBnThreads, 0, st>>>(g4, y4, k4, amax_bits, n4, C4, gys);
   return check_launch("bn_bwd_pack_kernel");
+}
+
+// ===================================================================================================
+// Stem: BatchNorm(train) + MaxPool fused (the 112x112x64 stem activation is the largest tensor of the
+// step: 822 MB at N=256).  The BN output is never materialised:
+//   forward : bn_reduce<fwd>(y) -> bn_finalize -> bn_pool_fwd: z = maxpool(a*y+b) + winner index +
+//             y at the winner (for the backward's yhat) [+ the first binary conv's sign/mask/+-1 packs]
+//   backward: bn_reduce<bwd>(g_pool, y_sel) over the POOLED tensors (every pooled gradient lands on
+//             exactly one input position, so sum gz = sum g_pool and sum gz*yhat = sum g_pool*yhat_sel)
+//             -> bn_bwd_bound -> bn_pool_bwd: gy = a*(gz - m1 - yhat*m2) for every input position, with
+//             gz gathered from the (<= 4) windows whose winner is that position.
+// torch.nn.MaxPool2d semantics on the BN output (first maximum in scan order wins, NaN propagates).
+// ===================================================================================================
+namespace bdbnn {
+
+template <bool PACK>
+__global__ void __launch_bounds__(kBnThreads)
+bn_pool_fwd_kernel(const float4* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
+                   int N, int H, int W, int C4, int Ho, int Wo, int k, int s, int p, int64_t total,
+                   float4* __restrict__ z, float4* __restrict__ ysel, uint32_t* __restrict__ idx,
+                   uint32_t* __restrict__ sign_bits, uint32_t* __restrict__ mask_bits, uint2* __restrict__ xb4,
+                   uint32_t* __restrict__ xb8, uint32_t one16) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t group_mask = 0xffu << (lane & 24);
+  const int sh = (lane & 7) * 4;
+  const uint32_t pos = one16, neg = one16 | 0x8000u;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;     // multiple of C4
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c = int(i % C4);
+  const float4 av = *reinterpret_cast<const float4*>(a + c * 4);
+  const float4 bv = *reinterpret_cast<const float4*>(b + c * 4);
+  for (; i < total; i += nthreads) {
+    int64_t q = i / C4;
+    const int wo = int(q % Wo); q /= Wo;
+    const int ho = int(q % Ho);
+    const int n = int(q / Ho);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), ys = m;
+    uint32_t w4 = 0;
+    bool first = true;
+    for (int r = 0; r < k; ++r) {
+      const int h = ho * s - p + r;
+      if (h < 0 || h >= H) continue;
+      for (int t = 0; t < k; ++t) {
+        const int w = wo * s - p + t;
+        if (w < 0 || w >= W) continue;
+        const float4 yv = __ldg(y + ((int64_t(n) * H + h) * W + w) * C4 + c);
+        const float4 v = make_float4(fmaf(yv.x, av.x, bv.x), fmaf(yv.y, av.y, bv.y), fmaf(yv.z, av.z, bv.z),
+                                     fmaf(yv.w, av.w, bv.w));
+        const uint32_t tap = uint32_t(r * k + t);
+        if (first || v.x > m.x || v.x != v.x) { m.x = v.x; ys.x = yv.x; w4 = (w4 & 0xffffff00u) | tap; }
+        if (first || v.y > m.y || v.y != v.y) { m.y = v.y; ys.y = yv.y; w4 = (w4 & 0xffff00ffu) | (tap << 8); }
+        if (first || v.z > m.z || v.z != v.z) { m.z = v.z; ys.z = yv.z; w4 = (w4 & 0xff00ffffu) | (tap << 16); }
+        if (first || v.w > m.w || v.w != v.w) { m.w = v.w; ys.w = yv.w; w4 = (w4 & 0x00ffffffu) | (tap << 24); }
+        first = false;
+      }
+    }
+    z[i] = m;
+    ysel[i] = ys;
+    idx[i] = w4;
+    if (PACK) {
+      const uint32_t s0 = m.x >= 0.0f, s1 = m.y >= 0.0f, s2 = m.z >= 0.0f, s3 = m.w >= 0.0f;
+      const uint32_t m0 = fabsf(m.x) <= 1.0f, m1 = fabsf(m.y) <= 1.0f, m2 = fabsf(m.z) <= 1.0f,
+                     m3 = fabsf(m.w) <= 1.0f;
+      const uint32_t sw = __reduce_or_sync(group_mask, (s0 | (s1 << 1) | (s2 << 2) | (s3 << 3)) << sh);
+      const uint32_t mw = __reduce_or_sync(group_mask, (m0 | (m1 << 1) | (m2 << 2) | (m3 << 3)) << sh);
+      if ((lane & 7) == 0) {
+        sign_bits[i >> 3] = sw;
+        mask_bits[i >> 3] = mw;
+      }
+      uint2 o;
+      o.x = (s0 ? pos : neg) | ((s1 ? pos : neg) << 16);
+      o.y = (s2 ? pos : neg) | ((s3 ? pos : neg) << 16);
+      xb4[i] = o;
+      if (xb8 != nullptr)
+        xb8[i] = 0x38383838u | ((s0 ? 0u : 0x80u) | (s1 ? 0u : 0x8000u) | (s2 ? 0u : 0x800000u) | (s3 ? 0u : 0x80000000u));
+    }
+  }
+}
+
+// gy[n,h,w,c] = A*(gz - m1 - (y-mean)*m2'),  gz = sum of g_pool over the windows won by (h,w);
+// consts[c] = {m1, m2*invstd, mean, A} from bn_bwd_bound_kernel (gscale = 1).
+__global__ void __launch_bounds__(kBnThreads)
+bn_pool_bwd_kernel(const float4* __restrict__ gpool, const uint32_t* __restrict__ idx, const float4* __restrict__ y,
+                   const float4* __restrict__ consts, int N, int H, int W, int C4, int Ho, int Wo, int k, int s,
+                   int p, int64_t total, float4* __restrict__ gy) {
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;     // multiple of C4
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c = int(i % C4);
+  const float4 k0 = consts[c * 4 + 0], k1 = consts[c * 4 + 1], k2 = consts[c * 4 + 2], k3 = consts[c * 4 + 3];
+  for (; i < total; i += nthreads) {
+    int64_t q = i / C4;
+    const int w = int(q % W); q /= W;
+    const int h = int(q % H);
+    const int n = int(q / H);
+    float4 gz = make_float4(0.f, 0.f, 0.f, 0.f);
+    int ho0 = (h + p - k + s) / s;
+    if (h + p - k + 1 <= 0) ho0 = 0;
+    int wo0 = (w + p - k + s) / s;
+    if (w + p - k + 1 <= 0) wo0 = 0;
+    const int ho1 = min((h + p) / s, Ho - 1), wo1 = min((w + p) / s, Wo - 1);
+    for (int ho = ho0; ho <= ho1; ++ho) {
+      const uint32_t r = uint32_t(h - (ho * s - p));
+      for (int wo = wo0; wo <= wo1; ++wo) {
+        const uint32_t tap = r * uint32_t(k) + uint32_t(w - (wo * s - p));
+        const int64_t o = ((int64_t(n) * Ho + ho) * Wo + wo) * C4 + c;
+        const uint32_t w4 = __ldg(idx + o);
+        const float4 g = __ldg(gpool + o);
+        if ((w4 & 0xffu) == tap) gz.x += g.x;
+        if (((w4 >> 8) & 0xffu) == tap) gz.y += g.y;
+        if (((w4 >> 16) & 0xffu) == tap) gz.z += g.z;
+        if ((w4 >> 24) == tap) gz.w += g.w;
+      }
+    }
+    const float4 v = __ldcs(y + i);
+    float4 o;
+    o.x = (gz.x - k0.x - (v.x - k0.z) * k0.y) * k0.w;
+    o.y = (gz.y - k1.x - (v.y - k1.z) * k1.y) * k1.w;
+    o.z = (gz.z - k2.x - (v.z - k2.z) * k2.y) * k2.w;
+    o.w = (gz.w - k3.x - (v.w - k3.z) * k3.y) * k3.w;
+    gy[i] = o;
+  }
+}
+
+}  // namespace bdbnn
+
+using namespace bdbnn;
+
+static int pool_geom_ok(int N, int H, int W, int C, int k, int s, int p, int Ho, int Wo) {
+  BDBNN_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0 && C <= 4096, "bn_pool: bad N/H/W/C");
+  BDBNN_REQUIRE(k > 0 && k <= 15 && s > 0 && p >= 0 && 2 * p <= k, "bn_pool: bad k/stride/pad");
+  BDBNN_REQUIRE(Ho == (H + 2 * p - k) / s + 1 && Wo == (W + 2 * p - k) / s + 1 && Ho > 0 && Wo > 0,
+                "bn_pool: inconsistent output size");
+  return BDBNN_OK;
+}
+
+extern "C" int bdbnn_bn_pool_fwd(const float* y, const float* gamma, const float* beta, int32_t N, int32_t H,
+                                 int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t Ho,
+                                 int32_t Wo, float eps, float momentum, float* running_mean, float* running_var,
+                                 double* sums_ws, uint32_t* ymax_bits, float* mean, float* invstd, float* ab_ws,
+                                 float* z, float* y_sel, uint8_t* idx, uint32_t* sign_bits, uint32_t* mask_bits,
+                                 uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, void* stream) {
+  int rc = pool_geom_ok(N, H, W, C, k, stride, pad, Ho, Wo);
+  if (rc) return rc;
+  const bool pack = sign_bits != nullptr;
+  BDBNN_REQUIRE(y && gamma && beta && sums_ws && ymax_bits && mean && invstd && ab_ws && z && y_sel && idx,
+                "bn_pool_fwd: NULL pointer");
+  BDBNN_REQUIRE(!pack || ((C & 31) == 0 && mask_bits && xb), "bn_pool_fwd: packing needs C %% 32 == 0 and all pack outputs");
+  cudaStream_t st = cudaStream_t(stream);
+  const int C4 = C / 4;
+  const int64_t n_pix = int64_t(N) * H * W;
+  BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
+  BDBNN_CUDA(cudaMemsetAsync(ymax_bits, 0, size_t(C) * sizeof(uint32_t), st));
+  bn_reduce_kernel<false><<<bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+      reinterpret_cast<const float4*>(y), nullptr, nullptr, nullptr, n_pix, C4, sums_ws, ymax_bits);
+  rc = check_launch("bn_reduce_kernel<fwd>");
+  if (rc) return rc;
+  float* a = ab_ws;
+  float* b = ab_ws + C;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_ws, n_pix, C, eps, gamma, beta, mean, invstd, a, b,
+                                                       running_mean, running_var, momentum);
+  rc = check_launch("bn_finalize_kernel");
+  if (rc) return rc;
+  const int64_t total = int64_t(N) * Ho * Wo * C4;
+  const int grid = bn_grid(total, C4);
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  if (pack) {
+    bn_pool_fwd_kernel<true><<<grid, kBnThreads, 0, st>>>(
+        y4, a, b, N, H, W, C4, Ho, Wo, k, stride, pad, total, reinterpret_cast<float4*>(z),
+        reinterpret_cast<float4*>(y_sel), reinterpret_cast<uint32_t*>(idx), sign_bits, mask_bits,
+        reinterpret_cast<uint2*>(xb), reinterpret_cast<uint32_t*>(xb_fp8), fmt == BDBNN_FMT_FP16 ? 0x3C00u : 0x3F80u);
+  } else {
+    bn_pool_fwd_kernel<false><<<grid, kBnThreads, 0, st>>>(
+        y4, a, b, N, H, W, C4, Ho, Wo, k, stride, pad, total, reinterpret_cast<float4*>(z),
+        reinterpret_cast<float4*>(y_sel), reinterpret_cast<uint32_t*>(idx), nullptr, nullptr, nullptr, nullptr, 0u);
+  }
+  return check_launch("bn_pool_fwd_kernel");
+}
+
+extern "C" int bdbnn_bn_pool_bwd(const float* g_pool, const uint8_t* idx, const float* y, const float* y_sel,
+                                 const float* mean, const float* invstd, const float* gamma, const float* ones,
+                                 const uint32_t* ymax_bits, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
+                                 int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, double* sums_ws,
+                                 uint32_t* gmax_bits, float* consts_ws, float* dgamma, float* dbeta,
+                                 uint32_t* amax_scratch, float* gy, void* stream) {
+  int rc = pool_geom_ok(N, H, W, C, k, stride, pad, Ho, Wo);
+  if (rc) return rc;
+  BDBNN_REQUIRE(g_pool && idx && y && y_sel && mean && invstd && gamma && ones && ymax_bits && sums_ws && gmax_bits &&
+                    consts_ws && dgamma && dbeta && amax_scratch && gy,
+                "bn_pool_bwd: NULL pointer");
+  cudaStream_t st = cudaStream_t(stream);
+  const int C4 = C / 4;
+  const int64_t n_pool = int64_t(N) * Ho * Wo, n_full = int64_t(N) * H * W;
+  BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
+  BDBNN_CUDA(cudaMemsetAsync(gmax_bits, 0, size_t(C) * sizeof(uint32_t), st));
+  bn_reduce_kernel<true><<<bn_grid(n_pool * C4 / 8, C4, 3), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+      reinterpret_cast<const float4*>(g_pool), reinterpret_cast<const float4*>(y_sel), mean, invstd, n_pool, C4,
+      sums_ws, gmax_bits);
+  rc = check_launch("bn_reduce_kernel<bwd,pool>");
+  if (rc) return rc;
+  // means are over the FULL-resolution element count; gscale = 1 (`ones`)
+  bn_bwd_bound_kernel<<<1, 256, 0, st>>>(sums_ws, gmax_bits, ymax_bits, n_full, C, mean, invstd, gamma, ones,
+                                         reinterpret_cast<float4*>(consts_ws), dgamma, dbeta, amax_scratch);
+  rc = check_launch("bn_bwd_bound_kernel");
+  if (rc) return rc;
+  const int64_t total = n_full * C4;
+  bn_pool_bwd_kernel<<<bn_grid(total, C4), kBnThreads, 0, st>>>(
+      reinterpret_cast<const float4*>(g_pool), reinterpret_cast<const uint32_t*>(idx),
+      reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(consts_ws), N, H, W, C4, Ho, Wo, k, stride,
+      pad, total, reinterpret_cast<float4*>(gy));
+  return check_launch("bn_pool_bwd_kernel");
 }

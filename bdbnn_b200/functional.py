@@ -625,3 +625,83 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
     if zs is not None:
         z._bdbnn_pack = (zs, zm, zb, fmt, zb8)
     return z
+
+
+class _StemBNPool(torch.autograd.Function):
+    """z = maxpool(BN_train(y)) for the stem (csrc/bn.cu): the 4x larger BN output is never written; the
+    first binary conv's packs are emitted with z."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad):
+        _require_cuda(y, "stem_bn_pool")
+        ctx.set_materialize_grads(False)
+        L = _lib.lib()
+        n, c, h, w = y.shape
+        if c % 4:
+            raise RuntimeError("stem_bn_pool: channel count must be a multiple of 4")
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        dev = y.device
+        yc = _nhwc(y.detach())
+        fmt = grad_mode()[3]
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        sums = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+        ymax = torch.empty((c,), **i32)
+        mean, invstd, ab = torch.empty((c,), **f32), torch.empty((c,), **f32), torch.empty((2 * c,), **f32)
+        z = torch.empty((n, c, ho, wo), memory_format=torch.channels_last, **f32)
+        ysel = torch.empty((n, ho, wo, c), **f32)
+        idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=dev)
+        pack = c % 32 == 0
+        zs = torch.empty((n, ho, wo, c // 32), **i32) if pack else None
+        zm = torch.empty((n, ho, wo, c // 32), **i32) if pack else None
+        zb = torch.empty((n, ho, wo, c), dtype=torch.int16, device=dev) if pack else None
+        zb8 = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=dev) if (pack and fwd8_enabled()) else None
+        nbytes = 4 * n * h * w * c * 2 + (4 + 4 + 1 + (3.25 if pack else 0)) * n * ho * wo * c
+        with _timed("stem_bn_pool_fwd", f"N{n}_{h}x{w}_c{c}", nbytes):
+            _lib.check(L.bdbnn_bn_pool_fwd(_p(yc), _p(gamma.detach()), _p(beta.detach()), n, h, w, c, k, stride, pad, ho,
+                                           wo, float(eps), float(momentum), _p(running_mean), _p(running_var),
+                                           _p(sums), _p(ymax), _p(mean), _p(invstd), _p(ab), _p(z), _p(ysel), _p(idx),
+                                           _p(zs), _p(zm), _p(zb), _p(zb8), fmt, _stream()), "bn_pool_fwd")
+        _lib.count(3)
+        ctx.geom = (n, h, w, c, k, stride, pad, ho, wo)
+        ctx.save_for_backward(yc, ysel, idx, mean, invstd, gamma.detach(), ymax)
+        outs = (z, zs, zm, zb, zb8)
+        nd = [t for t in outs[1:] if t is not None]
+        if nd:
+            ctx.mark_non_differentiable(*nd)
+        return outs
+
+    @staticmethod
+    def backward(ctx, gz, *_unused):
+        if gz is None:
+            return (None,) * 10
+        L = _lib.lib()
+        yc, ysel, idx, mean, invstd, gamma, ymax = ctx.saved_tensors
+        n, h, w, c, k, stride, pad, ho, wo = ctx.geom
+        dev = gz.device
+        g = _nhwc(gz)
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        sums = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+        gmax, amax = torch.empty((c,), **i32), torch.empty((1,), **i32)
+        consts = torch.empty((4 * c,), **f32)
+        dgamma, dbeta = torch.empty((c,), **f32), torch.empty((c,), **f32)
+        ones = torch.ones((c,), **f32)
+        gy = torch.empty((n, c, h, w), memory_format=torch.channels_last, **f32)
+        nbytes = 8 * n * ho * wo * c + (4 + 4) * n * h * w * c + 5 * n * ho * wo * c
+        with _timed("stem_bn_pool_bwd", f"N{n}_{h}x{w}_c{c}", nbytes):
+            _lib.check(L.bdbnn_bn_pool_bwd(_p(g), _p(idx), _p(yc), _p(ysel), _p(mean), _p(invstd), _p(gamma), _p(ones),
+                                           _p(ymax), n, h, w, c, k, stride, pad, ho, wo, _p(sums), _p(gmax), _p(consts),
+                                           _p(dgamma), _p(dbeta), _p(amax), _p(gy), _stream()), "bn_pool_bwd")
+        _lib.count(3)
+        return (gy if ctx.needs_input_grad[0] else None, dgamma if ctx.needs_input_grad[1] else None,
+                dbeta if ctx.needs_input_grad[2] else None, None, None, None, None, None, None, None)
+
+
+def stem_bn_pool(y, gamma, beta, running_mean, running_var, momentum, eps, kernel_size, stride, padding):
+    """maxpool(BN_train(y)); the result carries `_bdbnn_pack` for the first binary conv."""
+    z, zs, zm, zb, zb8 = _StemBNPool.apply(y, gamma, beta, running_mean, running_var, momentum, eps,
+                                           int(kernel_size), int(stride), int(padding))
+    if zs is not None:
+        z._bdbnn_pack = (zs, zm, zb, grad_mode()[3], zb8)
+    return z

@@ -82,8 +82,20 @@ class ResNetImageNet(nn.Module):
             layers.append(BasicBlock(planes, planes, conv_cls=conv_cls))
         return nn.Sequential(*layers)
 
+    def _stem(self, x):
+        y = self.conv1(x)
+        bn, mp = self.bn1, self.maxpool
+        if (y.is_cuda and bn.training and F_.fuse_enabled() and isinstance(mp, MaxPool2dNHWC) and bn.affine and
+                bn.track_running_stats and bn.momentum is not None and y.dtype == torch.float32 and
+                y.shape[1] % 4 == 0):
+            z = F_.stem_bn_pool(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps,
+                                mp.kernel_size, mp.stride, mp.padding)
+            bn.num_batches_tracked.add_(1)
+            return z
+        return mp(bn(y))
+
     def forward(self, x):
-        x = self.maxpool(self.bn1(self.conv1(x)))
+        x = self._stem(x)
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 

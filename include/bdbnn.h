@@ -215,6 +215,26 @@ BDBNN_API int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* me
                       int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits, float* consts_ws,
                       float* dgamma, float* dbeta, uint32_t* amax_bits, uint16_t* gys, void* stream);
 
+/* ---- stem: BatchNorm(train) + MaxPool fused (the BN output is never written) -----------------------
+ * bn_pool_fwd: y fp32 NHWC [N,H,W,C] (stem conv output) -> z = maxpool_k,s,p(gamma*(y-mean)*invstd+beta)
+ *              [N,Ho,Wo,C], idx = winning tap per output element (1 byte), y_sel = y at the winner;
+ *              optional packs of z as in bdbnn_bn_fwd.  Scratch as bdbnn_bn_fwd.
+ * bn_pool_bwd: g_pool = grad of z -> gy = grad of y [N,H,W,C] (BN backward with the pooled gradient
+ *              scattered to the winners), dgamma, dbeta.  `ones` = float[C] of 1.0 (unit gradient scale);
+ *              scratch: sums_ws double[2C], gmax_bits u32[C], consts_ws float[4C], amax_scratch u32[1]. */
+BDBNN_API int bdbnn_bn_pool_fwd(const float* y, const float* gamma, const float* beta, int32_t N, int32_t H, int32_t W,
+                      int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, float eps,
+                      float momentum, float* running_mean, float* running_var, double* sums_ws,
+                      uint32_t* ymax_bits, float* mean, float* invstd, float* ab_ws, float* z, float* y_sel,
+                      uint8_t* idx, uint32_t* sign_bits, uint32_t* mask_bits, uint16_t* xb, uint8_t* xb_fp8,
+                      int32_t fmt, void* stream);
+BDBNN_API int bdbnn_bn_pool_bwd(const float* g_pool, const uint8_t* idx, const float* y, const float* y_sel,
+                      const float* mean, const float* invstd, const float* gamma, const float* ones,
+                      const uint32_t* ymax_bits, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
+                      int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, double* sums_ws, uint32_t* gmax_bits,
+                      float* consts_ws, float* dgamma, float* dbeta, uint32_t* amax_scratch, float* gy,
+                      void* stream);
+
 /* ---- NHWC max-pool (stem of the ImageNet shells; torch.nn.MaxPool2d semantics) --------------------
  * Caller side of the path (the ops either side of the binary convs).  x,y,gy,gx fp32
  * NHWC, C % 4 == 0; idx = winning tap (r*k+s) per output element, one byte each [N,Ho,Wo,C].

@@ -233,3 +233,37 @@ def test_fused_unit_identity_shortcut_adds_in_dgrad_epilogue(mode, monkeypatch):
     torch.testing.assert_close(z.detach().cpu().double(), zr.detach(), rtol=2e-5, atol=2e-5)
     scale = xr.grad.abs().max().item()
     assert (xd.grad.cpu().double() - xr.grad).abs().max().item() <= GRAD_TOL[mode] * 2 * scale
+
+
+@pytest.mark.parametrize("geom", [(2, 64, 16, 16, 3, 2, 1), (3, 32, 9, 11, 3, 2, 1), (2, 8, 8, 8, 2, 2, 0)])
+def test_stem_bn_pool_fused_vs_torch(geom):
+    """maxpool(BN_train(y)) fused (BN output never materialised) vs nn.BatchNorm2d + nn.MaxPool2d in fp64."""
+    import torch.nn as nn
+    from bdbnn_b200.functional import stem_bn_pool
+    n, c, h, w, k, s, p = geom
+    g = torch.Generator().manual_seed(41 + sum(geom))
+    y = torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3
+    bn = nn.BatchNorm2d(c).double()
+    bn.weight.data = (torch.rand(c, generator=g) + 0.5).double() * torch.where(torch.arange(c) % 5 == 0, -1.0, 1.0).double()
+    bn.bias.data = torch.randn(c, generator=g).double() * 0.3
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    yr = y.double().requires_grad_(True)
+    zr = nn.functional.max_pool2d(bn(yr), k, s, p)
+    gz = torch.randn(zr.shape, generator=g, dtype=torch.float64)
+    zr.backward(gz)
+    yd = y.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gam = bn.weight.detach().float().cuda().requires_grad_(True)
+    bet = bn.bias.detach().float().cuda().requires_grad_(True)
+    rm, rv = rm0.float().cuda(), rv0.float().cuda()
+    z = stem_bn_pool(yd, gam, bet, rm, rv, 0.1, bn.eps, k, s, p)
+    z.backward(gz.float().cuda())
+    torch.testing.assert_close(z.detach().cpu().double(), zr.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(rm.cpu().double(), bn.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv.cpu().double(), bn.running_var, rtol=1e-5, atol=1e-6)
+    for name, got, ref in (("gy", yd.grad, yr.grad), ("dgamma", gam.grad, bn.weight.grad), ("dbeta", bet.grad, bn.bias.grad)):
+        scale = ref.abs().max().item() + 1e-30
+        assert (got.cpu().double() - ref).abs().max().item() <= 2e-5 * scale, name
+    if c % 32 == 0:
+        zs, zm, zb, fmt, zb8 = z._bdbnn_pack
+        assert torch.equal(zs.cpu().to(torch.int64) & 0xFFFFFFFF, B.pack_bits_nhwc(z.detach().cpu()))
+        assert torch.equal(zm.cpu().to(torch.int64) & 0xFFFFFFFF, B.pack_mask_nhwc(z.detach().cpu()))
