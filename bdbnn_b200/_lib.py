@@ -32,6 +32,7 @@ SIGNATURES = {
     "bdbnn_act_pack": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P]),
     "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "bdbnn_bits_to_fp8": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "bdbnn_ede_scale": (c_int, [_P, _P, _P, _P, c_int64, _P]),
     "bdbnn_binconv_fwd_tc8": (c_int, [_P, _P, _P, _P, _SH, _P]),
     "bdbnn_binconv_fwd_xnor": (c_int, [_P, _P, _P, _P, _SH, _P]),
     "bdbnn_binconv_fwd_tc": (c_int, [_P, _P, c_int, _P, _P, _SH, _P]),

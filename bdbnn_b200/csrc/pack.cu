@@ -327,3 +327,46 @@ extern "C" int bdbnn_bits_to_fp8(const uint32_t* sign_bits, int64_t n_pix, int32
                                                                          reinterpret_cast<uint4*>(xb_fp8));
   return check_launch("bits_to_fp8_kernel");
 }
+
+// ---- EDE backward factor (train.py:409-415, utils/utils.py:8-14) ------------------------------
+// g[i] *= k * t * (1 - tanh(t * v[i])^2): the soft-sign derivative that replaces the hard-tanh STE
+// indicator when the training loop has assigned .k/.t.  k and t stay on the device (1-element
+// tensors written by the caller each epoch), so nothing here forces a host sync.
+namespace bdbnn {
+__global__ void __launch_bounds__(256)
+ede_scale_kernel(float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ kp,
+                 const float* __restrict__ tp, int64_t n) {
+  const float k = __ldg(kp), t = __ldg(tp), kt = k * t;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  float4* g4 = reinterpret_cast<float4*>(g);
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = g4[i];
+    const float4 b = __ldg(v4 + i);
+    float th;
+    th = tanhf(t * b.x); a.x *= kt * (1.0f - th * th);
+    th = tanhf(t * b.y); a.y *= kt * (1.0f - th * th);
+    th = tanhf(t * b.z); a.z *= kt * (1.0f - th * th);
+    th = tanhf(t * b.w); a.w *= kt * (1.0f - th * th);
+    g4[i] = a;
+  }
+  for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float th = tanhf(t * __ldg(v + i));
+    g[i] *= kt * (1.0f - th * th);
+  }
+}
+}  // namespace bdbnn
+
+extern "C" int bdbnn_ede_scale(float* g, const float* v, const float* k, const float* t, int64_t n, void* stream) {
+  BDBNN_REQUIRE(n >= 0, "ede_scale: negative n");
+  if (n == 0) return BDBNN_OK;
+  BDBNN_REQUIRE(g && v && k && t, "ede_scale: NULL pointer");
+  BDBNN_REQUIRE(((uintptr_t(g) | uintptr_t(v)) & 15) == 0, "ede_scale: g and v must be 16-byte aligned");
+  int64_t blocks = ((n >> 2) + 255) / 256;
+  const int64_t cap = int64_t(bdbnn::num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  bdbnn::ede_scale_kernel<<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(g, v, k, t, n);
+  return bdbnn::check_launch("ede_scale_kernel");
+}

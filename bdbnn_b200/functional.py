@@ -145,7 +145,7 @@ class _BinConv2d(torch.autograd.Function):
     Saved for backward: bits only (plus the bf16 +-1 copy on the tensor-core path) — never fp32 x."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, padding, impl):
+    def forward(ctx, x, weight, stride, padding, impl, ede_k=None, ede_t=None):
         _require_cuda(x, "binconv2d(x)")
         _require_cuda(weight, "binconv2d(weight)")
         L = _lib.lib()
@@ -206,6 +206,16 @@ class _BinConv2d(torch.autograd.Function):
         ctx.gmode = (gname, gcode, ghalves)
         ctx.x_shape = tuple(x.shape)
         ctx.w_shape = tuple(weight.shape)
+        ctx.ede = ede_k is not None
+        if ctx.ede:
+            # EDE backward (train.py:409-415): soft-sign derivative needs the real values, and the
+            # dgrad/wgrad kernels run with all-ones masks.
+            _require_cuda(ede_k, "binconv2d(k)")
+            _require_cuda(ede_t, "binconv2d(t)")
+            mask_bits = torch.full_like(mask_bits, -1)
+            wmask = torch.full_like(wmask, -1)
+            ctx.ede_saved = (xc, w, ede_k.detach().reshape(-1)[:1].float().contiguous(),
+                             ede_t.detach().reshape(-1)[:1].float().contiguous())
         if tc:
             ctx.save_for_backward(sign_bits, mask_bits, wsign, wmask, alpha, xb, wt, gscale, inv_gscale)
         else:
@@ -273,12 +283,24 @@ class _BinConv2d(torch.autograd.Function):
                     _lib.check(L.bdbnn_binconv_wgrad(_p(g), _p(sign_bits), _p(wmask), _p(gw),
                                                      ctypes.byref(sh), st), "binconv_wgrad")
                 _lib.count(1)
-        return gx, gw, None, None, None
+        if ctx.ede:
+            xv, wv, ek, et = ctx.ede_saved
+            for gbuf, vbuf in ((gx, xv), (gw, wv)):
+                if gbuf is not None:
+                    with _timed("ede_scale", key, 12 * gbuf.numel()):
+                        _lib.check(L.bdbnn_ede_scale(_p(gbuf), _p(vbuf), _p(ek), _p(et), gbuf.numel(), st),
+                                   "ede_scale")
+                    _lib.count(1)
+        return gx, gw, None, None, None, None, None
 
 
-def binconv2d(x, weight, stride=1, padding=1, impl=None):
+def binconv2d(x, weight, stride=1, padding=1, impl=None, ede=None):
     """1W/1A binarised conv2d. x [N,Cin,H,W] fp32 CUDA (any strides; NHWC is copy-free),
-    weight [Cout,Cin,kh,kw] fp32. Returns [N,Cout,Ho,Wo] fp32 (channels_last strides)."""
+    weight [Cout,Cin,kh,kw] fp32. Returns [N,Cout,Ho,Wo] fp32 (channels_last strides).
+    `ede=(k, t)` (1-element CUDA tensors) switches both STE derivatives from the hard-tanh
+    indicator to k*t*(1 - tanh(t*v)^2) (the reference's --ede recipe, train.py:409-415)."""
+    if ede is not None:
+        return _BinConv2d.apply(x, weight, int(stride), int(padding), impl, ede[0], ede[1])
     return _BinConv2d.apply(x, weight, int(stride), int(padding), impl)
 
 

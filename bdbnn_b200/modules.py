@@ -36,12 +36,43 @@ class BinarizeConv2d(nn.Conv2d):
         if self.dilation != (1, 1) or self.groups != 1:
             raise ValueError("BinarizeConv2d supports dilation=1, groups=1 only")
         self.impl = impl
-        # EDE attributes the reference writes every epoch onto every nn.Conv2d (train.py:409-415)
-        self.k = torch.tensor([1.0])
-        self.t = torch.tensor([1.0])
+        # EDE attributes the reference writes every epoch onto every nn.Conv2d (train.py:409-415).
+        # Plain attributes here: only HardBinaryConv_cifar gives them a meaning.
+        self._ede_k = None
+        self._ede_t = None
+
+    # `.k` / `.t`: readable defaults, and assignment (what `--ede` does each epoch) is recorded.
+    @property
+    def k(self):
+        return self._ede_k if self._ede_k is not None else torch.tensor([1.0])
+
+    @k.setter
+    def k(self, value):
+        self._ede_k = value
+
+    @property
+    def t(self):
+        return self._ede_t if self._ede_t is not None else torch.tensor([1.0])
+
+    @t.setter
+    def t(self, value):
+        self._ede_t = value
+
+    #: classes that honour an assigned (k, t) pair in their backward set this to True
+    supports_ede = False
+
+    @property
+    def ede_active(self):
+        return self.supports_ede and self._ede_k is not None and self._ede_t is not None
+
+    def _ede(self, x):
+        if not self.ede_active:
+            return None
+        k, t = torch.as_tensor(self._ede_k), torch.as_tensor(self._ede_t)
+        return (k.to(x.device, torch.float32), t.to(x.device, torch.float32))
 
     def forward(self, x):
-        return binconv2d(x, self.weight, self.stride[0], self.padding[0], self.impl)
+        return binconv2d(x, self.weight, self.stride[0], self.padding[0], self.impl, self._ede(x))
 
     def extra_repr(self):
         return super().extra_repr() + f", binarized=1W/1A, impl={self.impl or 'auto'}"
@@ -63,7 +94,13 @@ class HardBinaryConv_react(BinarizeConv2d):
 
 
 class HardBinaryConv_cifar(BinarizeConv2d):
-    """CIFAR binary conv (train.py:32,392); carries the EDE `.k/.t` tensors (train.py:412-415)."""
+    """CIFAR binary conv (train.py:32,392); carries the EDE `.k/.t` tensors (train.py:412-415).
+
+    Until the training loop assigns `.k` and `.t` the backward is the hard-tanh STE of DESIGN.md §2;
+    once both are assigned (the reference's `--ede`, schedule utils/utils.py:8-14) both STE
+    derivatives become k*t*(1 - tanh(t*v)^2) (v = x for the activation, v = W for the weight)."""
+
+    supports_ede = True
 
     def __init__(self, in_chn, out_chn, kernel_size=3, stride=1, padding=1, **kw):
         super().__init__(in_chn, out_chn, kernel_size, stride, padding, **kw)

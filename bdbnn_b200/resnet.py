@@ -22,8 +22,8 @@ def _fused_unit(x, conv, bn, residual):
         return None
     if not (bn.affine and bn.track_running_stats and bn.momentum is not None and F_.fuse_enabled()):
         return None
-    if conv.impl == "xnor" or x.dtype != torch.float32:
-        return None
+    if conv.impl == "xnor" or x.dtype != torch.float32 or conv.ede_active:
+        return None                       # EDE backward needs fp32 x: module chain
     if not F_.unit_supported(x.shape, conv.weight.shape, conv.stride[0], conv.padding[0]):
         return None
     z = F_.conv_bn_add(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.momentum,

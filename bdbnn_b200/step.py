@@ -73,6 +73,30 @@ def select_hooked_weights(model, cfg: StepConfig):
     return hooked
 
 
+def cpt_tk(epoch, tot_epochs, t_min=1e-2, t_max=1e1):
+    """EDE schedule (utils/utils.py:8-14): t = 10^(lg t_min + (lg t_max - lg t_min)*epoch/tot) in fp32,
+    k = max(1/t, 1).  Returns 1-element fp32 tensors (t, k) like the reference."""
+    lo = torch.log10(torch.tensor(t_min).float())
+    hi = torch.log10(torch.tensor(t_max).float())
+    t = torch.tensor([torch.pow(torch.tensor(10.0), lo + (hi - lo) / tot_epochs * epoch)]).float()
+    k = torch.maximum(1 / t, torch.tensor(1.0)).float()
+    return t, k
+
+
+def apply_ede(model, epoch, tot_epochs, device=None):
+    """Per-epoch EDE update of train.py:409-415: every nn.Conv2d gets `.k` / `.t` on the device.
+    HardBinaryConv_cifar then switches its backward to k*t*(1 - tanh(t*v)^2)."""
+    t, k = cpt_tk(epoch, tot_epochs)
+    if device is None:
+        device = next(model.parameters()).device
+    t, k = t.to(device), k.to(device)
+    for m in model.modules():
+        if isinstance(m, nn.Conv2d):
+            m.k = k
+            m.t = t
+    return t, k
+
+
 def accuracy(output, target, topk=(1,)):
     """utils/utils.py:72-85 (device tensors, no sync)."""
     with torch.no_grad():

@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--workload", default="ce", choices=["ce", "kurt_kd"],
                     help="ce = BASELINE configs[1]; kurt_kd = configs[2] (kurtosis + KD, fp32 teacher)")
     ap.add_argument("--conv-impl", default=None, choices=[None, "auto", "xnor", "tc"])
+    ap.add_argument("--ede", action="store_true",
+                    help="EDE backward (train.py:409-415) at epoch 40/120; acts on HardBinaryConv_cifar (resnet20)")
     ap.add_argument("--cpu-batch", type=int, default=32, help="bounded CPU sample: images per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -193,6 +195,9 @@ def cpu_reference_run(args, steps, warmup, batch):
     torch.manual_seed(0)
     ishape, ncls, dataset = shapes(args.model, batch)
     model = build_model(args.model, ref=True)
+    if getattr(args, "ede", False):
+        from bdbnn_b200.step import apply_ede
+        apply_ede(model, 40, 120, device="cpu")
     teacher = None
     cfg = step_config(args.workload)
     if cfg.teacher_student:
@@ -231,7 +236,7 @@ def main():
     batch = args.batch or (128 if args.model == "resnet20" else 256)
     workload = (f"{args.model} 1W/1A synthetic {'32x32' if args.model == 'resnet20' else '224x224'} "
                 f"batch {batch}/GPU, {'CE' if args.workload == 'ce' else 'CE+kurtosis+KD(fp32 teacher)'}"
-                f" full train step")
+                f"{' +EDE backward' if args.ede else ''} full train step")
 
     if args.impl == "reference":
         if rank != 0:
@@ -269,6 +274,9 @@ def main():
     torch.manual_seed(0)
     ishape, ncls, dataset = shapes(args.model, batch)
     model = build_model(args.model, args.conv_impl).to(dev).to(memory_format=torch.channels_last)
+    if args.ede:
+        from bdbnn_b200.step import apply_ede
+        apply_ede(model, 40, 120)
     cfg = step_config(args.workload)
     teacher = None
     if cfg.teacher_student:

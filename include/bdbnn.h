@@ -96,6 +96,12 @@ BDBNN_API int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int32
 /* sign bits -> fp8 e4m3 +-1 bytes [n_pix][C] (0x38 = +1, 0xB8 = -1), C % 32 == 0: operand of fwd_tc8. */
 BDBNN_API int bdbnn_bits_to_fp8(const uint32_t* sign_bits, int64_t n_pix, int32_t C, uint8_t* xb_fp8, void* stream);
 
+/* ---- EDE backward factor: g[i] *= k*t*(1 - tanh(t*v[i])^2), k,t 1-element DEVICE floats ---------
+ * The soft-sign derivative the reference's --ede recipe uses instead of the hard-tanh indicator
+ * (train.py:409-415 assigns module.k/.t each epoch; schedule utils/utils.py:8-14).  Applied to
+ * gx (v = x) and gW (v = W) after the dgrad/wgrad kernels ran with all-ones masks. */
+BDBNN_API int bdbnn_ede_scale(float* g, const float* v, const float* k, const float* t, int64_t n, void* stream);
+
 /* ---- binary conv forward, XNOR-popcount (bit-serial, CUDA cores) -------------------------------
  * y[n,ho,wo,o] = alpha[o] * sum_{valid taps} (Cin - 2*popc(xbits ^ wbits)); zero padding
  * contributes 0.  Replaces F.conv2d on +-1 fp32 tensors inside HardBinaryConv*.forward

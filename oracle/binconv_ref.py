@@ -15,6 +15,12 @@ Spec (Bi-Real-Net `HardBinaryConv` lineage, which the class names follow):
   Wb        = alpha[o] * sign(W)      d Wb / d W  := 1[|W| <= 1]        (clamp STE, no alpha factor)
   y         = conv2d(xb, Wb, stride, zero padding)        (padded taps contribute 0)
 
+EDE variant (reference: `--ede`, train.py:409-415 assigns module.k / module.t from
+utils/utils.py:8-14 `cpt_tk`; IR-Net's "error decay estimator" the flag is named after):
+  d sign(v) / d v := k * t * (1 - tanh(t*v)^2)     for both x and W, replacing the two indicators.
+The schedule (cpt_tk) IS pinned by the reference (tests/golden/cpt_tk_cases.pt); the derivative form is
+authored like the rest of this file.
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
 this module.
 """
@@ -58,6 +64,56 @@ def binconv_backward(x, weight, gy, stride=1, padding=1):
     return gx_b * ste_mask(x), gw_b * ste_mask(weight)
 
 
+def ede_factor(v, k, t):
+    """k * t * (1 - tanh(t*v)^2): soft-sign derivative of the EDE backward."""
+    k = torch.as_tensor(k, dtype=v.dtype).reshape(())
+    t = torch.as_tensor(t, dtype=v.dtype).reshape(())
+    return k * t * (1.0 - torch.tanh(t * v) ** 2)
+
+
+def binconv_backward_ede(x, weight, gy, k, t, stride=1, padding=1):
+    """Closed-form backward with the EDE derivative in place of both STE indicators."""
+    alpha = weight_alpha(weight)
+    xb = sign_pm1(x)
+    wb = sign_pm1(weight) * alpha.view(-1, 1, 1, 1)
+    gx_b = torch.nn.grad.conv2d_input(x.shape, wb, gy, stride=stride, padding=padding)
+    gw_b = torch.nn.grad.conv2d_weight(xb, weight.shape, gy, stride=stride, padding=padding)
+    return gx_b * ede_factor(x, k, t), gw_b * ede_factor(weight, k, t)
+
+
+def cpt_tk(epoch, tot_epochs, t_min=1e-2, t_max=1e1):
+    """(t, k) of the EDE schedule, restating utils/utils.py:8-14: t = 10^(lg Tmin + (lg Tmax - lg Tmin) *
+    epoch / tot_epochs) in fp32, k = max(1/t, 1)."""
+    lo, hi = torch.log10(torch.tensor(t_min).float()), torch.log10(torch.tensor(t_max).float())
+    t = torch.tensor([torch.pow(torch.tensor(10.0), lo + (hi - lo) / tot_epochs * epoch)]).float()
+    k = torch.maximum(1 / t, torch.tensor(1.0)).float()
+    return t, k
+
+
+class _SignEDE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, k, t):
+        ctx.save_for_backward(v, k, t)
+        return sign_pm1(v)
+
+    @staticmethod
+    def backward(ctx, g):
+        v, k, t = ctx.saved_tensors
+        return g * ede_factor(v, k, t), None, None
+
+
+def binconv2d_ref_ede(x, weight, k, t, stride=1, padding=1):
+    """Autograd version of the EDE variant."""
+    alpha = weight_alpha(weight).detach()
+    k = torch.as_tensor(k, dtype=x.dtype)
+    t = torch.as_tensor(t, dtype=x.dtype)
+    xb = _SignEDE.apply(x, k, t)
+    # alpha multiplies the value only: route the weight gradient around it (no alpha factor, as in the STE spec)
+    wsgn = _SignEDE.apply(weight, k, t)
+    wb = (wsgn * alpha.view(-1, 1, 1, 1)).detach() - wsgn.detach() + wsgn
+    return F.conv2d(xb, wb, None, stride, padding)
+
+
 class _SignSTE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, v):
@@ -85,11 +141,22 @@ class RefBinarizeConv2d(nn.Conv2d):
 
     def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=False, **kw):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, bias=False)
-        self.k = torch.tensor([1.0])
-        self.t = torch.tensor([1.0])
+        self.k = None      # assigned by the training loop under --ede (train.py:412-415)
+        self.t = None
+        self.supports_ede = False
 
     def forward(self, x):
+        if self.supports_ede and self.k is not None and self.t is not None:
+            return binconv2d_ref_ede(x, self.weight, self.k, self.t, self.stride[0], self.padding[0])
         return binconv2d_ref(x, self.weight, self.stride[0], self.padding[0])
+
+
+class RefBinarizeConv2dCifar(RefBinarizeConv2d):
+    """Oracle twin of HardBinaryConv_cifar: honours an assigned (.k, .t) pair (EDE backward)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.supports_ede = True
 
 
 # ---- bit-level restatement of what the packed kernels compute (numpy-free, small sizes only) --------

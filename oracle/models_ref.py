@@ -7,7 +7,7 @@ import torch.nn as nn
 from bdbnn_b200 import resnet as _resnet
 from bdbnn_b200.losses import matched_weight_pairs
 
-from .binconv_ref import RefBinarizeConv2d
+from .binconv_ref import RefBinarizeConv2d, RefBinarizeConv2dCifar
 from . import losses_ref
 
 
@@ -20,7 +20,7 @@ def resnet34_ref(**kw):
 
 
 def resnet20_ref(**kw):
-    return _resnet.ResNetCifar(3, conv_cls=RefBinarizeConv2d, **kw)
+    return _resnet.ResNetCifar(3, conv_cls=RefBinarizeConv2dCifar, **kw)
 
 
 class RefOps:

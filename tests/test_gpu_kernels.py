@@ -329,3 +329,54 @@ def test_bits_to_fp8():
     out = torch.zeros((3, 5, 7, 64), dtype=torch.uint8, device="cuda")
     _lib.check(L.bdbnn_bits_to_fp8(_p(bits), 3 * 5 * 7, 64, _p(out), _stream()), "bits_to_fp8")
     assert torch.equal(out.view(torch.float8_e4m3fn).float().cpu(), B.sign_pm1(x).permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("impl,shape,tol", [("xnor", (2, 16, 9, 8, 24, 3, 1, 1), 2e-5),
+                                            ("xnor", (2, 32, 8, 8, 32, 3, 2, 1), 2e-5),
+                                            ("tc", (4, 64, 8, 8, 64, 3, 1, 1), 1.5e-3)])
+@pytest.mark.parametrize("kt", [(1.0, 1.0), (3.1623, 0.3162), (1.0, 9.4406)])
+def test_ede_backward_vs_oracle(impl, shape, tol, kt):
+    """EDE backward (train.py:409-415): forward unchanged, both STE indicators replaced by
+    k*t*(1 - tanh(t*v)^2); k/t stay device tensors."""
+    from bdbnn_b200.functional import binconv2d
+    n, cin, h, w, cout, ks, stride, pad = shape
+    g = torch.Generator().manual_seed(11 + sum(shape))
+    x = torch.randn(n, cin, h, w, generator=g) * 1.2
+    wt = torch.randn(cout, cin, ks, ks, generator=g) * 0.8
+    k, t = torch.tensor([kt[0]]), torch.tensor([kt[1]])
+    xd = _nhwc(x).requires_grad_(True)
+    wd = wt.cuda().requires_grad_(True)
+    y = binconv2d(xd, wd, stride, pad, impl, (k.cuda(), t.cuda()))
+    y0 = binconv2d(xd.detach(), wd.detach(), stride, pad, impl)
+    assert torch.equal(y.detach(), y0)                               # forward is not touched by EDE
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy.cuda())
+    gx_ref, gw_ref = B.binconv_backward_ede(x.double(), wt.double(), gy.double(), k.double(), t.double(), stride, pad)
+    for got, ref in ((xd.grad.cpu(), gx_ref), (wd.grad.cpu(), gw_ref)):
+        scale = ref.abs().max().item() + 1e-30
+        assert (got.double() - ref).abs().max().item() <= tol * scale
+
+
+def test_ede_module_cifar_follows_assigned_k_t():
+    """HardBinaryConv_cifar switches to the EDE backward once the loop assigned .k/.t; the oracle
+    module does the same; HardBinaryConv ignores the attributes."""
+    from bdbnn_b200 import HardBinaryConv, HardBinaryConv_cifar
+    from bdbnn_b200.step import apply_ede
+    torch.manual_seed(3)
+    x = torch.randn(2, 16, 10, 10) * 1.3
+    for cls, reacts in ((HardBinaryConv_cifar, True), (HardBinaryConv, False)):
+        conv = cls(16, 32, 3, 1, 1).cuda()
+        ref = B.RefBinarizeConv2d(16, 32, 3, 1, 1)
+        ref.load_state_dict(conv.state_dict())
+        ref.supports_ede = reacts
+        t, k = apply_ede(conv, 30, 120)
+        ref.k, ref.t = k.cpu(), t.cpu()
+        xd = _nhwc(x).requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        y, yr = conv(xd), ref(xr)
+        gy = torch.randn_like(yr)
+        y.backward(gy.cuda())
+        yr.backward(gy)
+        torch.testing.assert_close(y.detach().cpu(), yr.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=2e-4, atol=1e-5)
+        torch.testing.assert_close(conv.weight.grad.cpu(), ref.weight.grad, rtol=2e-4, atol=1e-4)

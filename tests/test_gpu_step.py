@@ -12,8 +12,8 @@ def _grads(m):
     return {n: p.grad.detach().cpu().clone() for n, p in m.named_parameters()}
 
 
-@pytest.mark.parametrize("ts", [False, True])
-def test_resnet20_step_matches_cpu_oracle(ts):
+@pytest.mark.parametrize("ts,ede", [(False, False), (True, False), (False, True)])
+def test_resnet20_step_matches_cpu_oracle(ts, ede):
     import torchvision
     from bdbnn_b200 import _lib
     from bdbnn_b200.resnet import resnet20
@@ -38,6 +38,11 @@ def test_resnet20_step_matches_cpu_oracle(ts):
         teacher_gpu = teacher_gpu.cuda().to(memory_format=torch.channels_last).eval()
         for p in teacher_gpu.parameters():
             p.requires_grad = False
+    if ede:                                           # train.py:409-415 at epoch 40 of 120
+        from bdbnn_b200.step import apply_ede
+        t, k = apply_ede(gpu, 40, 120)
+        apply_ede(ref, 40, 120, device="cpu")
+        assert all(m.ede_active for m in gpu.modules() if hasattr(m, "ede_active"))
     cfg = StepConfig(w_kurtosis=True, teacher_student=ts, beta=200.0, alpha=0.9)
     # lr=0: compare gradients of one step without the update moving the weights
     s_ref = TrainStep(ref, make_optimizer(ref, "cifar10", lr=0.0), cfg, teacher=teacher_ref, ops=RefOps)

@@ -154,3 +154,19 @@ def test_gloo_world2_gradient_allreduce(tmp_path):
     (g0, p0), (g1, p1) = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2)]
     assert torch.equal(g0, g1) and torch.equal(p0, p1)     # averaged grads and updated params identical
     assert g0.abs().sum() > 0
+
+
+def test_ede_attributes_and_activation_rule():
+    """train.py:412-415 assigns .k/.t onto every nn.Conv2d; only the cifar class reacts, and only
+    after both were assigned."""
+    import torch.nn as nn
+    from bdbnn_b200.modules import HardBinaryConv, HardBinaryConv_cifar
+    from bdbnn_b200.step import apply_ede
+    c, h = HardBinaryConv_cifar(16, 16), HardBinaryConv(16, 16)
+    assert isinstance(c, nn.Conv2d) and not c.ede_active and not h.ede_active
+    assert float(c.k) == 1.0 and float(c.t) == 1.0                 # readable defaults
+    net = nn.Sequential(c, h, nn.Conv2d(16, 16, 1))
+    t, k = apply_ede(net, 5, 10, device="cpu")
+    assert c.ede_active and not h.ede_active
+    assert c.k is k and c.t is t and net[2].k is k
+    assert "k" not in c.state_dict() and "_ede_k" not in c.state_dict()

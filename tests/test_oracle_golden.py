@@ -121,3 +121,30 @@ def test_sign_and_mask_edge_values():
 def test_cpt_tk_fixture_shape(golden_dir):
     for c in _load(golden_dir, "cpt_tk_cases.pt"):
         assert c["t"].shape == (1,) and c["k"].numel() == 1
+
+
+def test_cpt_tk_oracle_and_host_match_reference_fixture(golden_dir):
+    """EDE schedule: oracle restatement and the product host function reproduce the reference's
+    utils/utils.py:8-14 outputs bit for bit."""
+    from bdbnn_b200.step import cpt_tk as host_tk
+    for c in _load(golden_dir, "cpt_tk_cases.pt"):
+        for fn in (B.cpt_tk, host_tk):
+            t, k = fn(c["epoch"], c["tot"])
+            assert torch.equal(t.reshape(-1), c["t"].reshape(-1))
+            assert torch.equal(k.reshape(-1), c["k"].reshape(-1))
+
+
+def test_ede_autograd_matches_closed_form():
+    torch.manual_seed(5)
+    x = torch.randn(2, 8, 6, 6, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(4, 8, 3, 3, dtype=torch.float64) * 0.7).requires_grad_()
+    gy = torch.randn(2, 4, 3, 3, dtype=torch.float64)
+    k, t = torch.tensor([3.1623]), torch.tensor([0.3162])
+    y = B.binconv2d_ref_ede(x, w, k, t, 2, 1)
+    torch.testing.assert_close(y, B.binconv_forward(x.detach(), w.detach(), 2, 1))    # forward unchanged
+    y.backward(gy)
+    gx, gw = B.binconv_backward_ede(x.detach(), w.detach(), gy, k, t, 2, 1)
+    torch.testing.assert_close(x.grad, gx)
+    torch.testing.assert_close(w.grad, gw)
+    # k*t*(1 - tanh^2) at k=t=1 is 1 - tanh(v)^2
+    torch.testing.assert_close(B.ede_factor(torch.tensor([0.5]), 1.0, 1.0), 1 - torch.tanh(torch.tensor([0.5])) ** 2)
