@@ -33,6 +33,12 @@ SIGNATURES = {
     "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "bdbnn_bits_to_fp8": (c_int, [_P, c_int64, c_int, _P, _P]),
     "bdbnn_ede_scale": (c_int, [_P, _P, _P, _P, c_int64, _P]),
+    "bdbnn_stem_supported": (c_int, [c_int, c_int, c_int]),
+    "bdbnn_stem_xw_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "bdbnn_stem_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "bdbnn_stem_pack": (c_int, [_P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
+    "bdbnn_stem_conv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "bdbnn_stem_conv_wgrad": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "bdbnn_binconv_fwd_tc8": (c_int, [_P, _P, _P, _P, _SH, _P]),
     "bdbnn_binconv_fwd_xnor": (c_int, [_P, _P, _P, _P, _SH, _P]),
     "bdbnn_binconv_fwd_tc": (c_int, [_P, _P, c_int, _P, _P, _SH, _P]),

@@ -273,6 +273,27 @@ inline int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W,
   return BDBNN_OK;
 }
 
+// Overlapping-window view of a zero-padded 16-bit NHWC image (stem conv, stem.cu): element
+// (j, wo, hp, n) lives at base + n*img_stride + hp*row_stride + wo*win_stride + 2*j (bytes), i.e. window
+// `wo` of a padded row is the KB consecutive values starting win_stride bytes after window wo-1 —
+// consecutive windows overlap; TMA only needs every stride to be a multiple of 16 bytes.
+// Box [BNI][BH (every hstep-th row)][BW][KB].
+inline int make_window_map(CUtensorMap* map, const void* base, int N, int HP, int WO, int KB,
+                           uint64_t win_stride, uint64_t row_stride, uint64_t img_stride, int BW, int BH,
+                           int BNI, int hstep) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return BDBNN_ERR_CUDA; }
+  cuuint64_t dims[4] = {cuuint64_t(KB), cuuint64_t(WO), cuuint64_t(HP), cuuint64_t(N)};
+  cuuint64_t strides[3] = {win_stride, row_stride, img_stride};
+  cuuint32_t box[4] = {cuuint32_t(KB), cuuint32_t(BW), cuuint32_t(BH * hstep), cuuint32_t(BNI)};
+  cuuint32_t estr[4] = {1, 1, cuuint32_t(hstep), 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KB * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(window) failed: %d", int(r)); return BDBNN_ERR_CUDA; }
+  return BDBNN_OK;
+}
+
 // bf16 K-major weight matrix [rows][cols] -> 2-D map, box [BN rows][KB cols].
 inline int make_weight_map(CUtensorMap* map, const void* base, int rows, int cols, int KB, int BN, int esize = 2) {
   EncodeTiledFn enc = encode_tiled_fn();
@@ -301,7 +322,36 @@ struct TcConvLaunch {
   int fmt;                       // operand format (BDBNN_FMT_*); -1 = fp8 e4m3 bytes (forward only)
   const uint32_t* amax_bits;     // FP16S gradient: device word with max|A|; epilogue multiplies by 2^-e
   const float* add;              // dgrad: optional tensor added to the result (shortcut gradient), or NULL
+  // stem conv: A is an overlapping-window view (make_window_map) instead of a dense NHWC tensor
+  int win;                       // 0 = dense NHWC
+  uint64_t win_stride, win_row_stride, win_img_stride;
 };
+
+// Geometry of the stem's packed input (stem.cu): fp16 [N][HP][WP][4] zero-padded by 3 on every side,
+// windows of 8 pixels (32 values) every 2 pixels.
+struct StemGeom {
+  int N, H, W, Ho, Wo, HP, WP;
+  uint64_t win_stride, row_stride, img_stride;   // bytes
+};
+inline bool stem_geom(int N, int H, int W, StemGeom* g) {
+  if (N < 1 || H < 7 || W < 7) return false;
+  g->N = N; g->H = H; g->W = W;
+  g->Ho = (H + 6 - 7) / 2 + 1; g->Wo = (W + 6 - 7) / 2 + 1;
+  if (g->Wo > kTileM || g->Wo < 1) return false;
+  g->HP = H + 6;
+  int wp = W + 6 > 2 * g->Wo + 6 ? W + 6 : 2 * g->Wo + 6;
+  g->WP = (wp + 7) & ~7;
+  g->win_stride = 16;                               // 2 pixels x 4 halves x 2 bytes
+  g->row_stride = uint64_t(g->WP) * 8;
+  g->img_stride = g->row_stride * uint64_t(g->HP);
+  return true;
+}
+constexpr int kStemCout = 64, kStemTaps = 7, kStemWin = 32;
+int launch_stem_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, float* y, const StemGeom& g,
+                    cudaStream_t st);
+size_t stem_wgrad_workspace_bytes(const StemGeom& g);
+int launch_stem_wgrad(const uint16_t* gys, const uint16_t* xw, float* ws, size_t ws_bytes, int* ksplit_out,
+                      const StemGeom& g, cudaStream_t st);
 
 // Persistent multi-accumulator kernel (tc_conv2.cu). Returns BDBNN_ERR_UNSUPPORTED if the geometry
 // does not qualify (caller falls back to the one-tile-per-CTA kernel in tc_conv.cu).

@@ -246,7 +246,7 @@ template <int MODE>
 static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   // Persistent multi-accumulator kernel first (tc_conv2.cu); BDBNN_TC_V2=0 forces the simple kernel.
   static const int v2_env = [] { const char* e = getenv("BDBNN_TC_V2"); return e ? atoi(e) : 1; }();
-  if (v2_env) {
+  if (v2_env && !L.win) {
     const int rc2 = launch_tc_conv2(L, MODE, st);
     if (rc2 != BDBNN_ERR_UNSUPPORTED) return rc2;
   }
@@ -282,7 +282,7 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   p.fmt = L.fmt; p.amax_bits = L.amax_bits; p.add = L.add;
   // Halo mode (stride-1 launches with >128-pixel images and 64-channel K blocks): see TcConvParams.
   static const int halo_env = [] { const char* e = getenv("BDBNN_TC_HALO"); return e ? atoi(e) : 1; }();
-  if (halo_env > 0 && L.in_step == 1 && p.KB == 64 && L.OH * L.OW > kTileM && p.n_taps > 0) {
+  if (halo_env > 0 && !L.win && L.in_step == 1 && p.KB == 64 && L.OH * L.OW > kTileM && p.n_taps > 0) {
     int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
     for (int i = 0; i < p.n_taps; ++i) {
       dh0 = min(dh0, int(p.tap_dh[i])); dh1 = max(dh1, int(p.tap_dh[i]));
@@ -313,9 +313,14 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   const size_t smem = size_t(stages) * stage_bytes + (p.halo ? 2u * size_t(p.patch_bytes) : 0u) + 1024;
 
   CUtensorMap tmA, tmB;
-  int rc = p.halo ? make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.PW, p.PH, 1, 1)
-                  : make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, p.KB, p.BW, p.BH, p.BNI,
-                                 L.in_step);
+  int rc;
+  if (L.win)   // stem: overlapping windows, row step in_step, window step 1
+    rc = make_window_map(&tmA, L.A, L.NIMG, L.IH, L.IW, p.KB, L.win_stride, L.win_row_stride, L.win_img_stride,
+                         p.BW, p.BH, p.BNI, L.in_step);
+  else
+    rc = p.halo ? make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.PW, p.PH, 1, 1)
+                : make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, p.KB, p.BW, p.BH, p.BNI,
+                               L.in_step);
   if (rc) return rc;
   rc = make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, p.KB, p.BN);
   if (rc) return rc;
@@ -324,6 +329,23 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   dim3 grid(unsigned(p.tiles_h * tiles_n_eff), unsigned(L.Nout / p.BN));
   kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   return check_launch("tc_conv_kernel");
+}
+
+// Stem conv forward (7x7 / stride 2 / pad 3 on 3 channels) as a 7-tap implicit GEMM over the packed
+// window view: tap r reads window row 2*oh + r, K = 32 values (8 pixels x 4 halves) per tap.
+int launch_stem_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, float* y, const StemGeom& g,
+                    cudaStream_t st) {
+  TcConvLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.A = xw; L.IH = g.HP; L.IW = g.Wo; L.Kc = kStemWin; L.a_halves = 1; L.in_step = 2;
+  L.win = 1; L.win_stride = g.win_stride; L.win_row_stride = g.row_stride; L.win_img_stride = g.img_stride;
+  L.B = wf; L.b_taps = kStemTaps; L.Nout = kStemCout;
+  L.NIMG = g.N; L.OH = g.Ho; L.OW = g.Wo;
+  for (int r = 0; r < kStemTaps; ++r) { L.dh[r] = int8_t(r); L.dw[r] = 0; L.tb[r] = uint8_t(r); }
+  L.n_taps = kStemTaps;
+  L.out_step = 1; L.OHf = g.Ho; L.OWf = g.Wo;
+  L.alpha = alpha; L.out = y; L.fmt = BDBNN_FMT_FP16;
+  return launch_tc_conv<0>(L, st);
 }
 
 }  // namespace bdbnn

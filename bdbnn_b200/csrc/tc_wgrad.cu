@@ -41,6 +41,8 @@ struct TcWgradParams {
   int32_t n_kboxes, kboxes_per_cta;
   int32_t Cin, Cout, kh, kw, pad, stride;
   int32_t g_halves;              // 1: gys = bf16(g); 2: gys = [hi | lo] split, both accumulated
+  int32_t UW;                    // unit width in channels: 64 (128-byte rows, SWIZZLE_128B) or 32 (stem
+                                 // windows: 64-byte rows, SWIZZLE_64B); an M tile is 128/UW units
   int32_t chunks_per_tap;        // Cin / 64
   int32_t n_units, G;            // (tap, chunk) units; M tiles (accumulators) per CTA
   int32_t BN;                    // N tile (output channels per CTA)
@@ -59,13 +61,14 @@ struct TcWgradParams {
     }                                                                                            \
   } while (0)
 
-__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes) {
+// row_bytes 128: SWIZZLE_128B atoms of 8 K rows x 64 MN elements; row_bytes 64: SWIZZLE_64B, 8 x 32.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t row_bytes = 128u) {
   uint64_t d = 0;
   d |= uint64_t((saddr & 0x3FFFFu) >> 4);
-  d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;   // LBO: stride between 64-element MN chunks
-  d |= uint64_t(1024u >> 4) << 32;                   // SBO: stride between 8-row K groups
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;   // LBO: stride between MN chunks (one swizzle row each)
+  d |= uint64_t((8u * row_bytes) >> 4) << 32;        // SBO: stride between 8-row K groups
   d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;                            // SWIZZLE_128B
+  d |= uint64_t(row_bytes == 128u ? 2u : 4u) << 61;  // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
@@ -82,7 +85,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int mt0 = blockIdx.y * p.G;                               // first M tile of this CTA
-  const int n_mtiles = (p.n_units + 1) / 2;
+  const int upt = kTileM / p.UW;                                  // units per M tile (2 or 4)
+  const uint32_t a_row = uint32_t(p.UW) * 2u;                     // bytes per A row
+  const int n_mtiles = (p.n_units + upt - 1) / upt;
   const int g_cta = min(p.G, n_mtiles - mt0);
   const int nb_chunks = p.BN / 64;                                // 64-channel chunks of the N tile
   const int nb_boxes = nb_chunks * p.g_halves;                    // hi (and lo) boxes of gys
@@ -94,8 +99,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint32_t tmem_cols = 32;
   while (tmem_cols < uint32_t(p.G * p.BN)) tmem_cols <<= 1;
 
-  if (threadIdx.x < g_cta * 2) {
-    int u = mt0 * 2 + threadIdx.x;
+  if (threadIdx.x < g_cta * upt) {
+    int u = mt0 * upt + threadIdx.x;
     bool dup = false;
     if (u >= p.n_units) { u = p.n_units - 1; dup = true; }        // odd unit count: rows ignored
     const int t = u / p.chunks_per_tap, j = u - t * p.chunks_per_tap;
@@ -121,7 +126,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   // Zero every row TMA never writes (A rows >= rows_a, B rows >= rows_b): they are read as K rows.
   {
     uint8_t* base_generic = smem_raw + (tiles_base - smem_u32(smem_raw));
-    const int a_tail = int(p.a_box_bytes / 16) - p.rows_a * 8;
+    const int a_w16 = int(a_row / 16u);                            // 16-byte words per A row
+    const int a_tail = int(p.a_box_bytes / 16) - p.rows_a * a_w16;
     const int b_tail = int(p.b_box_bytes / 16) - p.rows_b * 8;
     const int per_stage = p.n_a_boxes * a_tail + nb_boxes * b_tail;
     const int total = p.stages * per_stage;
@@ -131,7 +137,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint8_t* dst;
       if (r < p.n_a_boxes * a_tail) {
         const int b = r / a_tail, w = r - b * a_tail;
-        dst = base_generic + size_t(s) * stage_bytes + size_t(b) * p.a_box_bytes + size_t(p.rows_a) * 128u +
+        dst = base_generic + size_t(s) * stage_bytes + size_t(b) * p.a_box_bytes + size_t(p.rows_a) * a_row +
               size_t(w) * 16u;
       } else {
         r -= p.n_a_boxes * a_tail;
@@ -155,8 +161,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   if (warp == 4) {
     if (lane == 0) {
-      const int n_a_loads = p.halo ? p.n_a_boxes : g_cta * 2;
-      const uint32_t tx = (uint32_t(n_a_loads) * uint32_t(p.rows_a) + uint32_t(nb_boxes) * uint32_t(p.rows_b)) * 128u;
+      const int n_a_loads = p.halo ? p.n_a_boxes : g_cta * upt;
+      const uint32_t tx = uint32_t(n_a_loads) * uint32_t(p.rows_a) * a_row +
+                          uint32_t(nb_boxes) * uint32_t(p.rows_b) * 128u;
       int it = 0, tr_n = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
         const int stage = it % p.stages;
@@ -173,8 +180,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int j = 0; j < p.n_a_boxes; ++j)
             tma_load_4d(dst0 + j * p.a_box_bytes, &tmX, fb, j * 64, p.dw_min, h0 + p.dh_min, n0);
         } else {
-          for (int i = 0; i < g_cta * 2; ++i) {
-            int u = mt0 * 2 + i;
+          for (int i = 0; i < g_cta * upt; ++i) {
+            int u = mt0 * upt + i;
             if (u >= p.n_units) u = p.n_units - 1;
             const int t = u / p.chunks_per_tap, j = u - t * p.chunks_per_tap;
             const int r = t / p.kw, s = t - r * p.kw;
@@ -203,18 +210,19 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t a0 = tiles_base + stage * stage_bytes;
         const uint32_t b0 = a0 + a_bytes;
         for (int g = 0; g < g_cta; ++g) {
-          const uint32_t ua = unit_off[2 * g], ub = unit_off[2 * g + 1];
-          const uint64_t ad0 = make_mnmajor_desc(a0 + ua, ub - ua);
+          const uint32_t ua = unit_off[upt * g], ub = unit_off[upt * g + 1];
+          const uint64_t ad0 = make_mnmajor_desc(a0 + ua, ub - ua, a_row);
+          const uint32_t a_kstep = a_row;                           // 16 K rows x a_row bytes, >> 4
           const uint32_t a_lo0 = uint32_t(ad0), a_hi = uint32_t(ad0 >> 32);
           const uint32_t acc = tmem_d + uint32_t(g * p.BN);
           for (int hf = 0; hf < p.g_halves; ++hf) {
             const uint64_t bd0 = make_mnmajor_desc(b0 + hf * nb_chunks * p.b_box_bytes, p.b_box_bytes);
             const uint32_t b_lo0 = uint32_t(bd0), b_hi = uint32_t(bd0 >> 32);
-            // +2048 bytes (16 pixel rows) per K step = +128 in the address field of the low word
+            // 16 pixel rows per K step: +2048 B (128-byte rows) = +128 in the low word's address field
             umma_bf16_split(acc, a_lo0, a_hi, b_lo0, b_hi, idesc, (it > 0 || hf > 0) ? 1u : 0u);
 #pragma unroll 4
             for (int k = 1; k < k_steps; ++k)
-              umma_bf16_split(acc, a_lo0 + uint32_t(k) * 128u, a_hi, b_lo0 + uint32_t(k) * 128u, b_hi, idesc, 1u);
+              umma_bf16_split(acc, a_lo0 + uint32_t(k) * a_kstep, a_hi, b_lo0 + uint32_t(k) * 128u, b_hi, idesc, 1u);
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));
@@ -231,10 +239,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     BDBNN_WTR(2, 1);
     const uint32_t lane_base = tmem_d + (uint32_t(warp * 32) << 16);
     for (int g = 0; g < g_cta; ++g) {
-      const int u = (mt0 + g) * 2 + (m >> 6);
+      const int u = (mt0 + g) * upt + m / p.UW;
       const bool valid = u < p.n_units;
-      float* wrow = p.ws + int64_t(blockIdx.x) * (int64_t(p.n_units) * 64 * p.Cout) +
-                    (int64_t(u) * 64 + (m & 63)) * p.Cout + nn0;           // slice, row (t*Cin + c)
+      float* wrow = p.ws + int64_t(blockIdx.x) * (int64_t(p.n_units) * p.UW * p.Cout) +
+                    (int64_t(u) * p.UW + (m % p.UW)) * p.Cout + nn0;       // slice, row (t*Cin + c)
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(lane_base + uint32_t(g * p.BN + c0), v);
@@ -311,6 +319,7 @@ static WgradPlan plan_wgrad(const bdbnn_conv_shape* s, int halves) {
   p.OW = s->Wo; p.OH = s->Ho; p.NIMG = s->N;
   p.Cin = s->Cin; p.Cout = s->Cout; p.kh = s->kh; p.kw = s->kw; p.pad = s->pad; p.stride = s->stride;
   p.g_halves = halves;
+  p.UW = 64;
   p.chunks_per_tap = s->Cin / 64;
   p.n_units = T * p.chunks_per_tap;
   const int n_mtiles = (p.n_units + 1) / 2;
@@ -396,6 +405,84 @@ static WgradPlan plan_wgrad(const bdbnn_conv_shape* s, int halves) {
 }
 
 bool wgrad_tc_ok(const bdbnn_conv_shape* s) { return s && plan_wgrad(s, 2).ok; }
+
+// ---- stem conv weight gradient ------------------------------------------------------------------
+// D[(r, j), o] = sum_pix xw[window(pix) of row 2*oh + r][j] * gys[pix, o]: 7 units (rows r of the 7x7
+// filter) of 32 window values (8 pixels x 4 halves; j = s*4 + c), box mode, one K stage per output row
+// group.  Both M tiles (units 0-3, 4-6 + one duplicate) live in every CTA, so gys is fetched once.
+static WgradPlan plan_stem_wgrad(const StemGeom& g) {
+  WgradPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  TcWgradParams& p = pl.p;
+  p.OW = g.Wo; p.OH = g.Ho; p.NIMG = g.N;
+  p.Cin = kStemWin; p.Cout = kStemCout; p.kh = kStemTaps; p.kw = 1; p.pad = 0; p.stride = 2;
+  p.g_halves = 1;
+  p.UW = kStemWin;
+  p.chunks_per_tap = 1;
+  p.n_units = kStemTaps;
+  p.BN = kStemCout;
+  p.G = 2;
+  p.stages = 3;
+  p.BW = g.Wo;
+  // K stage: BH output rows (or BNI whole images) of Wo pixels, <= 128 rows
+  if (g.Ho * g.Wo <= kTileM) {
+    p.BH = g.Ho;
+    p.BNI = kTileM / (g.Ho * g.Wo);
+    if (p.BNI > g.N) p.BNI = g.N;
+  } else {
+    p.BH = kTileM / g.Wo;
+    p.BNI = 1;
+  }
+  p.rows_a = p.rows_b = p.BNI * p.BH * p.BW;
+  p.k_stage = (p.rows_a + 15) & ~15;
+  p.a_box_bytes = (uint32_t(p.k_stage) * 64u + 1023u) & ~1023u;
+  p.b_box_bytes = uint32_t(p.k_stage) * 128u;
+  p.n_a_boxes = p.G * (kTileM / p.UW);
+  p.tiles_h = (g.Ho + p.BH - 1) / p.BH;
+  p.n_kboxes = p.tiles_h * ((g.N + p.BNI - 1) / p.BNI);
+  pl.mgroups = 1;
+  pl.ntiles = 1;
+  int ks = num_sms();
+  pl.ks_cap = ks;
+  if (ks > p.n_kboxes) ks = p.n_kboxes;
+  p.kboxes_per_cta = (p.n_kboxes + ks - 1) / ks;
+  pl.ksplit = (p.n_kboxes + p.kboxes_per_cta - 1) / p.kboxes_per_cta;
+  const size_t stage_bytes = size_t(p.n_a_boxes) * p.a_box_bytes + p.b_box_bytes;
+  p.stages = int((226u * 1024u) / stage_bytes);
+  if (p.stages > 4) p.stages = 4;
+  pl.smem = size_t(p.stages) * stage_bytes + 1024;
+  pl.ok = p.stages >= 2 && pl.smem <= 227u * 1024u;
+  return pl;
+}
+
+size_t stem_wgrad_workspace_bytes(const StemGeom& g) {
+  const WgradPlan pl = plan_stem_wgrad(g);
+  return pl.ok ? size_t(pl.ks_cap) * kStemTaps * kStemWin * kStemCout * sizeof(float) : 0;
+}
+
+int launch_stem_wgrad(const uint16_t* gys, const uint16_t* xw, float* ws, size_t ws_bytes, int* ksplit_out,
+                      const StemGeom& g, cudaStream_t st) {
+  WgradPlan pl = plan_stem_wgrad(g);
+  if (!pl.ok) { set_error("stem_conv_wgrad: geometry not supported"); return BDBNN_ERR_UNSUPPORTED; }
+  if (ws_bytes < stem_wgrad_workspace_bytes(g)) {
+    set_error("stem_conv_wgrad: workspace %zu B too small", ws_bytes);
+    return BDBNN_ERR_WORKSPACE;
+  }
+  pl.p.fmt = BDBNN_FMT_FP16;
+  pl.p.ws = ws;
+  pl.p.trace = get_tc_trace();
+  CUtensorMap tmX, tmG;
+  int rc = make_window_map(&tmX, xw, g.N, g.HP, g.Wo, kStemWin, g.win_stride, g.row_stride, g.img_stride, pl.p.BW,
+                           pl.p.BH, pl.p.BNI, 2);
+  if (rc) return rc;
+  rc = make_act_map(&tmG, gys, g.N, g.Ho, g.Wo, kStemCout, 64, pl.p.BW, pl.p.BH, pl.p.BNI);
+  if (rc) return rc;
+  BDBNN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+  dim3 grid(unsigned(pl.ksplit), 1, 1);
+  tc_wgrad_kernel<<<grid, kTcThreads, pl.smem, st>>>(tmX, tmG, pl.p);
+  *ksplit_out = pl.ksplit;
+  return check_launch("tc_wgrad_kernel(stem)");
+}
 
 }  // namespace bdbnn
 

@@ -720,6 +720,90 @@ class _StemBNPool(torch.autograd.Function):
                 dbeta if ctx.needs_input_grad[2] else None, None, None, None, None, None, None, None)
 
 
+_STEM_ENV = "BDBNN_STEM_TC"
+
+
+def stem_tc_enabled():
+    return os.environ.get(_STEM_ENV, "1") != "0"
+
+
+def stem_conv_supported(x, weight, stride, padding):
+    """tcgen05 stem: fp32 CUDA [N,3,H,W] (dense NCHW or channels_last) x [64,3,7,7], stride 2, pad 3,
+    output width <= 128, and no gradient w.r.t. the images."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
+        return False
+    if tuple(weight.shape) != (64, 3, 7, 7) or tuple(stride) != (2, 2) or tuple(padding) != (3, 3):
+        return False
+    if x.requires_grad and torch.is_grad_enabled():
+        return False
+    return bool(_lib.lib().bdbnn_stem_supported(x.shape[0], x.shape[2], x.shape[3]))
+
+
+class _StemConv(torch.autograd.Function):
+    """y = conv2d(x, W, stride 2, pad 3) for the 3 -> 64 channel 7x7 stem (csrc/stem.cu).
+    forward : stem_pack (amax, fp16 window image, fp16 weights) -> stem_conv_fwd (tcgen05, 7-tap implicit GEMM)
+    backward: grad_pack (fp16 x 2^e) -> stem_conv_wgrad (tcgen05, split-K) ; no input gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        L = _lib.lib()
+        dev = x.device
+        n, _, h, w = x.shape
+        xd = x.detach()
+        if not (xd.is_contiguous() or xd.is_contiguous(memory_format=torch.channels_last)):
+            xd = xd.contiguous()
+        wd = weight.detach().contiguous()
+        st = _stream()
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        xw = torch.empty((int(L.bdbnn_stem_xw_bytes(n, h, w)) // 2,), dtype=torch.int16, device=dev)
+        x_amax = torch.empty((1,), dtype=torch.int32, device=dev)
+        wf = torch.empty((64, 7, 32), dtype=torch.int16, device=dev)
+        alpha = torch.empty((64,), dtype=torch.float32, device=dev)
+        key = f"stem_N{n}_{h}x{w}"
+        with _timed("stem_pack", key, 4 * xd.numel() * 2 + xw.numel() * 2):
+            _lib.check(L.bdbnn_stem_pack(_p(xd), n, h, w, xd.stride(0), xd.stride(1), xd.stride(2), xd.stride(3),
+                                         _p(wd), _p(xw), _p(x_amax), _p(wf), _p(alpha), st), "stem_pack")
+        y = torch.empty((n, 64, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        with _timed("stem_conv_fwd", key, xw.numel() * 2 + 4 * y.numel()):
+            _lib.check(L.bdbnn_stem_conv_fwd(_p(xw), _p(wf), _p(alpha), _p(y), n, h, w, st), "stem_conv_fwd")
+        _lib.count(5)
+        ctx.geom = (n, h, w, ho, wo)
+        ctx.save_for_backward(xw, x_amax)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.needs_input_grad[1]:
+            return None, None
+        L = _lib.lib()
+        n, h, w, ho, wo = ctx.geom
+        xw, x_amax = ctx.saved_tensors
+        dev = gy.device
+        st = _stream()
+        g = _nhwc(gy)
+        key = f"stem_N{n}_{h}x{w}"
+        ones = torch.ones((64,), dtype=torch.float32, device=dev)
+        gys = torch.empty((n, ho, wo, 64), dtype=torch.int16, device=dev)
+        g_amax = torch.empty((1,), dtype=torch.int32, device=dev)
+        with _timed("stem_grad_pack", key, 8 * g.numel() + 2 * g.numel()):
+            _lib.check(L.bdbnn_grad_pack(_p(g), _p(ones), n * ho * wo, 64, 3, _p(g_amax), _p(gys), st), "grad_pack")
+        gw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dev)
+        nbytes = int(L.bdbnn_stem_wgrad_workspace_bytes(n, h, w))
+        ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+        with _timed("stem_conv_wgrad", key, 2 * g.numel() + xw.numel() * 2):
+            _lib.check(L.bdbnn_stem_conv_wgrad(_p(gys), _p(g_amax), _p(xw), _p(x_amax), _p(gw), n, h, w,
+                                               _p(ws), nbytes, st), "stem_conv_wgrad")
+        _lib.count(4)
+        return None, gw
+
+
+def stem_conv(x, weight):
+    """7x7 / stride-2 / pad-3 stem convolution on tcgen05 (see stem_conv_supported)."""
+    _require_cuda(x, "stem_conv(x)")
+    _require_cuda(weight, "stem_conv(weight)")
+    return _StemConv.apply(x, weight)
+
+
 def stem_bn_pool(y, gamma, beta, running_mean, running_var, momentum, eps, kernel_size, stride, padding):
     """maxpool(BN_train(y)); the result carries `_bdbnn_pack` for the first binary conv."""
     z, zs, zm, zb, zb8 = _StemBNPool.apply(y, gamma, beta, running_mean, running_var, momentum, eps,

@@ -83,7 +83,12 @@ class ResNetImageNet(nn.Module):
         return nn.Sequential(*layers)
 
     def _stem(self, x):
-        y = self.conv1(x)
+        c1 = self.conv1
+        if (type(c1) is nn.Conv2d and c1.bias is None and F_.stem_tc_enabled() and
+                F_.stem_conv_supported(x, c1.weight, c1.stride, c1.padding)):
+            y = F_.stem_conv(x, c1.weight)        # tcgen05 stem (csrc/stem.cu); BDBNN_STEM_TC=0 -> cuDNN
+        else:
+            y = c1(x)
         bn, mp = self.bn1, self.maxpool
         if (y.is_cuda and bn.training and F_.fuse_enabled() and isinstance(mp, MaxPool2dNHWC) and bn.affine and
                 bn.track_running_stats and bn.momentum is not None and y.dtype == torch.float32 and

@@ -252,6 +252,29 @@ BDBNN_API int bdbnn_maxpool_bwd(const float* gy, const uint8_t* idx, float* gx, 
                       int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t Ho, int32_t Wo,
                       void* stream);
 
+/* ---- stem convolution: 7x7 / stride 2 / pad 3, 3 -> 64 channels, fp32 in / fp32 out, on tcgen05 ------
+ * Replaces the fp32 nn.Conv2d `conv1` of the torchvision-style ResNet the reference trains
+ * (model(images), train.py:492,602; its weight gradient under loss.backward(), train.py:528,650), which
+ * cuDNN runs on TF32 tensor cores.  Operands here are fp16 after a per-call power-of-two scale
+ * (11-bit significands like TF32, fp32 accumulation); see bdbnn_b200/csrc/stem.cu.
+ *   stem_pack      : x (any dense NCHW / channels_last strides, in elements) -> xw fp16 [N][H+6][WP][4]
+ *                    (bdbnn_stem_xw_bytes), x_amax_bits (1 word), wf fp16 [64][7][32], alpha[64]
+ *   stem_conv_fwd  : y[N][Ho][Wo][64] fp32 NHWC = conv(x, W)
+ *   stem_conv_wgrad: gW[64][3][7][7] from gys = fp16(gy * 2^e) [N][Ho][Wo][64] (bdbnn_grad_pack, FP16S,
+ *                    gscale = 1) and the saved xw; workspace of bdbnn_stem_wgrad_workspace_bytes.
+ * Supported when (W-1)/2 + 1 <= 128 (bdbnn_stem_supported). */
+BDBNN_API int bdbnn_stem_supported(int32_t N, int32_t H, int32_t W);
+BDBNN_API size_t bdbnn_stem_xw_bytes(int32_t N, int32_t H, int32_t W);
+BDBNN_API size_t bdbnn_stem_wgrad_workspace_bytes(int32_t N, int32_t H, int32_t W);
+BDBNN_API int bdbnn_stem_pack(const float* x, int32_t N, int32_t H, int32_t W, int64_t sN, int64_t sC, int64_t sH,
+                    int64_t sW, const float* weight, uint16_t* xw, uint32_t* x_amax_bits, uint16_t* wf,
+                    float* alpha, void* stream);
+BDBNN_API int bdbnn_stem_conv_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, float* y, int32_t N,
+                        int32_t H, int32_t W, void* stream);
+BDBNN_API int bdbnn_stem_conv_wgrad(const uint16_t* gys, const uint32_t* g_amax_bits, const uint16_t* xw,
+                          const uint32_t* x_amax_bits, float* gW, int32_t N, int32_t H, int32_t W,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -267,3 +267,50 @@ def test_stem_bn_pool_fused_vs_torch(geom):
         zs, zm, zb, fmt, zb8 = z._bdbnn_pack
         assert torch.equal(zs.cpu().to(torch.int64) & 0xFFFFFFFF, B.pack_bits_nhwc(z.detach().cpu()))
         assert torch.equal(zm.cpu().to(torch.int64) & 0xFFFFFFFF, B.pack_mask_nhwc(z.detach().cpu()))
+
+
+@pytest.mark.parametrize("geom,layout", [((2, 32, 32), "nchw"), ((3, 33, 47), "nhwc"), ((5, 16, 16), "nchw"),
+                                         ((2, 224, 224), "nhwc"), ((1, 64, 255), "nchw")])
+def test_stem_conv_tc_vs_fp64_conv(geom, layout):
+    """7x7/2 stem conv on tcgen05 (fp16 operands with power-of-two scales = TF32-class significands, fp32
+    accumulate) vs an fp64 convolution: forward and weight gradient within 2e-3 of max|ref|
+    (cuDNN's TF32 stem, which the reference runs, has the same operand rounding)."""
+    from bdbnn_b200 import functional as F_
+    n, h, w = geom
+    g = torch.Generator().manual_seed(41 + h + w)
+    x = torch.randn(n, 3, h, w, generator=g) * 1.7 + 0.3
+    wt = torch.randn(64, 3, 7, 7, generator=g) * 0.05
+    xd = x.cuda()
+    if layout == "nhwc":
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    wd = wt.cuda().requires_grad_(True)
+    assert F_.stem_conv_supported(xd, wd, (2, 2), (3, 3))
+    y = F_.stem_conv(xd, wd)
+    xr, wr = x.double(), wt.double().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, None, 2, 3)
+    assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last)
+    scale = yr.abs().max().item()
+    assert (y.detach().cpu().double() - yr.detach()).abs().max().item() <= 2e-3 * scale
+    gy = torch.randn(yr.shape, generator=g)
+    y.backward(gy.cuda().contiguous(memory_format=torch.channels_last))
+    yr.backward(gy.double())
+    gscale = wr.grad.abs().max().item()
+    assert (wd.grad.cpu().double() - wr.grad).abs().max().item() <= 2e-3 * gscale
+    # scale invariance of the power-of-two operand scaling: x * 2^9, W * 2^-7 -> y * 4 exactly
+    y2 = F_.stem_conv(xd * 512.0, wd.detach() / 128.0)
+    assert torch.equal(y2, y.detach() * 4.0)
+
+
+def test_stem_conv_module_path_and_fallback(monkeypatch):
+    """ResNetImageNet._stem takes the tcgen05 stem by default and cuDNN with BDBNN_STEM_TC=0; both agree."""
+    from bdbnn_b200 import _lib
+    from bdbnn_b200.resnet import resnet18
+    torch.manual_seed(0)
+    net = resnet18().cuda().to(memory_format=torch.channels_last).train()
+    x = torch.randn(4, 3, 64, 64).cuda().contiguous(memory_format=torch.channels_last)
+    n0 = _lib.launch_count()
+    a = net._stem(x)
+    assert _lib.launch_count() - n0 >= 5
+    monkeypatch.setenv("BDBNN_STEM_TC", "0")
+    b = net._stem(x)
+    assert (a - b).abs().max().item() <= 5e-3 * b.abs().max().item()
