@@ -12,6 +12,8 @@
 // Per element: forward 4 + 12(+2.25) bytes instead of 12 (BN) + 12 (add) + 6.25 (pack);
 //              backward 8 + 10 bytes instead of ~20 (BN bwd) + 4 (amax) + 6 (pack).
 // All tensors fp32 NHWC [n_pix][C], C % 4 == 0 (packing: C % 32 == 0).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace bdbnn {
@@ -164,7 +166,8 @@ __global__ void bn_bwd_bound_kernel(const double* __restrict__ sums, const uint3
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ gscale,
                                     float4* __restrict__ consts, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, uint32_t* __restrict__ amax_bits) {
+                                    float* __restrict__ dbeta, uint32_t* __restrict__ amax_bits,
+                                    float gz_mult = 1.0f) {
   __shared__ float red[32];
   float bound = 0.f;
   const double n = double(n_pix);
@@ -177,7 +180,8 @@ __global__ void bn_bwd_bound_kernel(const double* __restrict__ sums, const uint3
     const float A = gamma[c] * is * gscale[c];
     consts[c] = make_float4(m1, m2 * is, mu, A);
     const float ymax = __uint_as_float(ymax_bits[c]), gmax = __uint_as_float(gmax_bits[c]);
-    bound = fmaxf(bound, fabsf(A) * (gmax + fabsf(m1) + (ymax + fabsf(mu)) * is * fabsf(m2)));
+    // gz_mult: how many gradient values can land on one position (pooled stem: windows per pixel)
+    bound = fmaxf(bound, fabsf(A) * (gz_mult * gmax + fabsf(m1) + (ymax + fabsf(mu)) * is * fabsf(m2)));
   }
   bound = warp_max(bound);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bound;
@@ -408,10 +412,15 @@ bn_pool_fwd_kernel(const float4* __restrict__ y, const float* __restrict__ a, co
 
 // gy[n,h,w,c] = A*(gz - m1 - (y-mean)*m2'),  gz = sum of g_pool over the windows won by (h,w);
 // consts[c] = {m1, m2*invstd, mean, A} from bn_bwd_bound_kernel (gscale = 1).
+// HALF: write gys = fp16(gy * 2^e) (e from the bound in amax_bits: the stem conv's wgrad operand, so the
+// 4-byte gradient of the largest activation of the step is never written) instead of fp32 gy.
+template <bool HALF>
 __global__ void __launch_bounds__(kBnThreads)
 bn_pool_bwd_kernel(const float4* __restrict__ gpool, const uint32_t* __restrict__ idx, const float4* __restrict__ y,
                    const float4* __restrict__ consts, int N, int H, int W, int C4, int Ho, int Wo, int k, int s,
-                   int p, int64_t total, float4* __restrict__ gy) {
+                   int p, int64_t total, float4* __restrict__ gy, const uint32_t* __restrict__ amax_bits,
+                   uint2* __restrict__ gys) {
+  const float up = HALF ? amax_pow2_scale(__ldg(amax_bits), false) : 1.0f;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;     // multiple of C4
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c = int(i % C4);
@@ -446,7 +455,12 @@ bn_pool_bwd_kernel(const float4* __restrict__ gpool, const uint32_t* __restrict_
     o.y = (gz.y - k1.x - (v.y - k1.z) * k1.y) * k1.w;
     o.z = (gz.z - k2.x - (v.z - k2.z) * k2.y) * k2.w;
     o.w = (gz.w - k3.x - (v.w - k3.z) * k3.y) * k3.w;
-    gy[i] = o;
+    if (HALF) {
+      const __half2 h0 = __floats2half2_rn(o.x * up, o.y * up), h1 = __floats2half2_rn(o.z * up, o.w * up);
+      gys[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    } else {
+      gy[i] = o;
+    }
   }
 }
 
@@ -510,11 +524,11 @@ extern "C" int bdbnn_bn_pool_bwd(const float* g_pool, const uint8_t* idx, const 
                                  const uint32_t* ymax_bits, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
                                  int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, double* sums_ws,
                                  uint32_t* gmax_bits, float* consts_ws, float* dgamma, float* dbeta,
-                                 uint32_t* amax_scratch, float* gy, void* stream) {
+                                 uint32_t* amax_scratch, float* gy, uint16_t* gys, void* stream) {
   int rc = pool_geom_ok(N, H, W, C, k, stride, pad, Ho, Wo);
   if (rc) return rc;
   BDBNN_REQUIRE(g_pool && idx && y && y_sel && mean && invstd && gamma && ones && ymax_bits && sums_ws && gmax_bits &&
-                    consts_ws && dgamma && dbeta && amax_scratch && gy,
+                    consts_ws && dgamma && dbeta && amax_scratch && (gy || gys),
                 "bn_pool_bwd: NULL pointer");
   cudaStream_t st = cudaStream_t(stream);
   const int C4 = C / 4;
@@ -527,14 +541,22 @@ extern "C" int bdbnn_bn_pool_bwd(const float* g_pool, const uint8_t* idx, const 
   rc = check_launch("bn_reduce_kernel<bwd,pool>");
   if (rc) return rc;
   // means are over the FULL-resolution element count; gscale = 1 (`ones`)
+  const int per_dim = (k + stride - 1) / stride;          // pooling windows covering one position, per axis
   bn_bwd_bound_kernel<<<1, 256, 0, st>>>(sums_ws, gmax_bits, ymax_bits, n_full, C, mean, invstd, gamma, ones,
-                                         reinterpret_cast<float4*>(consts_ws), dgamma, dbeta, amax_scratch);
+                                         reinterpret_cast<float4*>(consts_ws), dgamma, dbeta, amax_scratch,
+                                         float(per_dim * per_dim));
   rc = check_launch("bn_bwd_bound_kernel");
   if (rc) return rc;
   const int64_t total = n_full * C4;
-  bn_pool_bwd_kernel<<<bn_grid(total, C4), kBnThreads, 0, st>>>(
-      reinterpret_cast<const float4*>(g_pool), reinterpret_cast<const uint32_t*>(idx),
-      reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(consts_ws), N, H, W, C4, Ho, Wo, k, stride,
-      pad, total, reinterpret_cast<float4*>(gy));
+  if (gys != nullptr)
+    bn_pool_bwd_kernel<true><<<bn_grid(total, C4), kBnThreads, 0, st>>>(
+        reinterpret_cast<const float4*>(g_pool), reinterpret_cast<const uint32_t*>(idx),
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(consts_ws), N, H, W, C4, Ho, Wo, k,
+        stride, pad, total, nullptr, amax_scratch, reinterpret_cast<uint2*>(gys));
+  else
+    bn_pool_bwd_kernel<false><<<bn_grid(total, C4), kBnThreads, 0, st>>>(
+        reinterpret_cast<const float4*>(g_pool), reinterpret_cast<const uint32_t*>(idx),
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(consts_ws), N, H, W, C4, Ho, Wo, k,
+        stride, pad, total, reinterpret_cast<float4*>(gy), nullptr, nullptr);
   return check_launch("bn_pool_bwd_kernel");
 }

@@ -246,7 +246,7 @@ template <int MODE>
 static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   // Persistent multi-accumulator kernel first (tc_conv2.cu); BDBNN_TC_V2=0 forces the simple kernel.
   static const int v2_env = [] { const char* e = getenv("BDBNN_TC_V2"); return e ? atoi(e) : 1; }();
-  if (v2_env && !L.win) {
+  if (v2_env) {
     const int rc2 = launch_tc_conv2(L, MODE, st);
     if (rc2 != BDBNN_ERR_UNSUPPORTED) return rc2;
   }

@@ -222,8 +222,11 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (f8) {
                   for (int k = 0; k < k_steps; ++k)
                     umma_f8_split(acc, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc, (!first || k > 0) ? 1u : 0u);
-                } else {
+                } else if (p.row_bytes == 128) {
                   umma_bf16_k4(acc, a_lo, b_lo, desc_hi, idesc, first ? 0u : 1u);
+                } else {
+                  for (int k = 0; k < k_steps; ++k)
+                    umma_bf16_split(acc, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc, (!first || k > 0) ? 1u : 0u);
                 }
               }
             }
@@ -358,10 +361,12 @@ long long* get_tc_trace() { return g_trace; }
 
 // mode: 0 = alpha epilogue (forward), 1 = STE-mask epilogue (dgrad)
 int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
-  if (L.Kc % 64 != 0 || L.n_taps <= 0) return BDBNN_ERR_UNSUPPORTED;
+  if (L.n_taps <= 0) return BDBNN_ERR_UNSUPPORTED;
+  if (L.win ? (L.Kc != 32 || L.fmt < 0) : (L.Kc % 64 != 0)) return BDBNN_ERR_UNSUPPORTED;
   const bool f8 = L.fmt < 0;
   const int esize = f8 ? 1 : 2;
-  const int kb_elems = f8 ? (L.Kc % 128 == 0 ? 128 : 64) : 64;
+  // K block: 64 16-bit channels (128-byte rows); fp8: 128 or 64 bytes; stem windows: 32 halves (64-byte rows)
+  const int kb_elems = L.win ? 32 : (f8 ? (L.Kc % 128 == 0 ? 128 : 64) : 64);
   const uint32_t row_bytes = uint32_t(kb_elems * esize);
   if (L.Nout != 64 && L.Nout % 128 != 0) return BDBNN_ERR_UNSUPPORTED;
   TcConv2Params p;
@@ -442,7 +447,11 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
     p.n_mtiles = p.tiles_h * ((L.NIMG + p.BNI - 1) / p.BNI);
     p.n_supers = (p.n_mtiles + p.TS - 1) / p.TS;
     p.stage_bytes = (p.b_bytes + uint32_t(p.TS) * kTileM * row_bytes + 1023u) & ~1023u;
-    rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, kb_elems, p.BW, p.BH, p.BNI, L.in_step, esize);
+    if (L.win)
+      rc = make_window_map(&tmA, L.A, L.NIMG, L.IH, L.IW, kb_elems, L.win_stride, L.win_row_stride, L.win_img_stride,
+                           p.BW, p.BH, p.BNI, L.in_step);
+    else
+      rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, kb_elems, p.BW, p.BH, p.BNI, L.in_step, esize);
   }
   if (rc) return rc;
   rc = make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, kb_elems, p.BN, esize);

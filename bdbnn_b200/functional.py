@@ -649,6 +649,67 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
     return z
 
 
+def _bn_pool_fwd_impl(yc, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad):
+    """bn_pool_fwd launch sequence on an NHWC-contiguous y. Returns (outs, saved, geom)."""
+    L = _lib.lib()
+    n, c, h, w = yc.shape
+    if c % 4:
+        raise RuntimeError("stem_bn_pool: channel count must be a multiple of 4")
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    dev = yc.device
+    fmt = grad_mode()[3]
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    sums = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+    ymax = torch.empty((c,), **i32)
+    mean, invstd, ab = torch.empty((c,), **f32), torch.empty((c,), **f32), torch.empty((2 * c,), **f32)
+    z = torch.empty((n, c, ho, wo), memory_format=torch.channels_last, **f32)
+    ysel = torch.empty((n, ho, wo, c), **f32)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=dev)
+    pack = c % 32 == 0
+    zs = torch.empty((n, ho, wo, c // 32), **i32) if pack else None
+    zm = torch.empty((n, ho, wo, c // 32), **i32) if pack else None
+    zb = torch.empty((n, ho, wo, c), dtype=torch.int16, device=dev) if pack else None
+    zb8 = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=dev) if (pack and fwd8_enabled()) else None
+    nbytes = 4 * n * h * w * c * 2 + (4 + 4 + 1 + (3.25 if pack else 0)) * n * ho * wo * c
+    with _timed("stem_bn_pool_fwd", f"N{n}_{h}x{w}_c{c}", nbytes):
+        _lib.check(L.bdbnn_bn_pool_fwd(_p(yc), _p(gamma.detach()), _p(beta.detach()), n, h, w, c, k, stride, pad, ho,
+                                       wo, float(eps), float(momentum), _p(running_mean), _p(running_var),
+                                       _p(sums), _p(ymax), _p(mean), _p(invstd), _p(ab), _p(z), _p(ysel), _p(idx),
+                                       _p(zs), _p(zm), _p(zb), _p(zb8), fmt, _stream()), "bn_pool_fwd")
+    _lib.count(3)
+    return (z, zs, zm, zb, zb8), (yc, ysel, idx, mean, invstd, gamma.detach(), ymax), (n, h, w, c, k, stride, pad, ho, wo)
+
+
+def _bn_pool_bwd_impl(gz, saved, geom, half):
+    """bn_pool_bwd launch sequence. half=False -> (gy fp32 NCHW-shaped channels_last, dgamma, dbeta);
+    half=True -> ((gys fp16 x 2^e [N,H,W,C], amax word), dgamma, dbeta): the fp32 gradient is never written."""
+    L = _lib.lib()
+    yc, ysel, idx, mean, invstd, gamma, ymax = saved
+    n, h, w, c, k, stride, pad, ho, wo = geom
+    dev = gz.device
+    g = _nhwc(gz)
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    sums = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+    gmax, amax = torch.empty((c,), **i32), torch.empty((1,), **i32)
+    consts = torch.empty((4 * c,), **f32)
+    dgamma, dbeta = torch.empty((c,), **f32), torch.empty((c,), **f32)
+    ones = torch.ones((c,), **f32)
+    gy = gys = None
+    if half:
+        gys = torch.empty((n, h, w, c), dtype=torch.int16, device=dev)
+    else:
+        gy = torch.empty((n, c, h, w), memory_format=torch.channels_last, **f32)
+    nbytes = 8 * n * ho * wo * c + (4 + (2 if half else 4)) * n * h * w * c + 5 * n * ho * wo * c
+    with _timed("stem_bn_pool_bwd", f"N{n}_{h}x{w}_c{c}", nbytes):
+        _lib.check(L.bdbnn_bn_pool_bwd(_p(g), _p(idx), _p(yc), _p(ysel), _p(mean), _p(invstd), _p(gamma), _p(ones),
+                                       _p(ymax), n, h, w, c, k, stride, pad, ho, wo, _p(sums), _p(gmax), _p(consts),
+                                       _p(dgamma), _p(dbeta), _p(amax), _p(gy), _p(gys), _stream()), "bn_pool_bwd")
+    _lib.count(3)
+    return ((gys, amax) if half else gy), dgamma, dbeta
+
+
 class _StemBNPool(torch.autograd.Function):
     """z = maxpool(BN_train(y)) for the stem (csrc/bn.cu): the 4x larger BN output is never written; the
     first binary conv's packs are emitted with z."""
@@ -657,37 +718,9 @@ class _StemBNPool(torch.autograd.Function):
     def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad):
         _require_cuda(y, "stem_bn_pool")
         ctx.set_materialize_grads(False)
-        L = _lib.lib()
-        n, c, h, w = y.shape
-        if c % 4:
-            raise RuntimeError("stem_bn_pool: channel count must be a multiple of 4")
-        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
-        dev = y.device
-        yc = _nhwc(y.detach())
-        fmt = grad_mode()[3]
-        i32 = dict(dtype=torch.int32, device=dev)
-        f32 = dict(dtype=torch.float32, device=dev)
-        sums = torch.empty((2 * c,), dtype=torch.float64, device=dev)
-        ymax = torch.empty((c,), **i32)
-        mean, invstd, ab = torch.empty((c,), **f32), torch.empty((c,), **f32), torch.empty((2 * c,), **f32)
-        z = torch.empty((n, c, ho, wo), memory_format=torch.channels_last, **f32)
-        ysel = torch.empty((n, ho, wo, c), **f32)
-        idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=dev)
-        pack = c % 32 == 0
-        zs = torch.empty((n, ho, wo, c // 32), **i32) if pack else None
-        zm = torch.empty((n, ho, wo, c // 32), **i32) if pack else None
-        zb = torch.empty((n, ho, wo, c), dtype=torch.int16, device=dev) if pack else None
-        zb8 = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=dev) if (pack and fwd8_enabled()) else None
-        nbytes = 4 * n * h * w * c * 2 + (4 + 4 + 1 + (3.25 if pack else 0)) * n * ho * wo * c
-        with _timed("stem_bn_pool_fwd", f"N{n}_{h}x{w}_c{c}", nbytes):
-            _lib.check(L.bdbnn_bn_pool_fwd(_p(yc), _p(gamma.detach()), _p(beta.detach()), n, h, w, c, k, stride, pad, ho,
-                                           wo, float(eps), float(momentum), _p(running_mean), _p(running_var),
-                                           _p(sums), _p(ymax), _p(mean), _p(invstd), _p(ab), _p(z), _p(ysel), _p(idx),
-                                           _p(zs), _p(zm), _p(zb), _p(zb8), fmt, _stream()), "bn_pool_fwd")
-        _lib.count(3)
-        ctx.geom = (n, h, w, c, k, stride, pad, ho, wo)
-        ctx.save_for_backward(yc, ysel, idx, mean, invstd, gamma.detach(), ymax)
-        outs = (z, zs, zm, zb, zb8)
+        outs, saved, ctx.geom = _bn_pool_fwd_impl(_nhwc(y.detach()), gamma, beta, running_mean, running_var,
+                                                  momentum, eps, k, stride, pad)
+        ctx.save_for_backward(*saved)
         nd = [t for t in outs[1:] if t is not None]
         if nd:
             ctx.mark_non_differentiable(*nd)
@@ -697,25 +730,7 @@ class _StemBNPool(torch.autograd.Function):
     def backward(ctx, gz, *_unused):
         if gz is None:
             return (None,) * 10
-        L = _lib.lib()
-        yc, ysel, idx, mean, invstd, gamma, ymax = ctx.saved_tensors
-        n, h, w, c, k, stride, pad, ho, wo = ctx.geom
-        dev = gz.device
-        g = _nhwc(gz)
-        i32 = dict(dtype=torch.int32, device=dev)
-        f32 = dict(dtype=torch.float32, device=dev)
-        sums = torch.empty((2 * c,), dtype=torch.float64, device=dev)
-        gmax, amax = torch.empty((c,), **i32), torch.empty((1,), **i32)
-        consts = torch.empty((4 * c,), **f32)
-        dgamma, dbeta = torch.empty((c,), **f32), torch.empty((c,), **f32)
-        ones = torch.ones((c,), **f32)
-        gy = torch.empty((n, c, h, w), memory_format=torch.channels_last, **f32)
-        nbytes = 8 * n * ho * wo * c + (4 + 4) * n * h * w * c + 5 * n * ho * wo * c
-        with _timed("stem_bn_pool_bwd", f"N{n}_{h}x{w}_c{c}", nbytes):
-            _lib.check(L.bdbnn_bn_pool_bwd(_p(g), _p(idx), _p(yc), _p(ysel), _p(mean), _p(invstd), _p(gamma), _p(ones),
-                                           _p(ymax), n, h, w, c, k, stride, pad, ho, wo, _p(sums), _p(gmax), _p(consts),
-                                           _p(dgamma), _p(dbeta), _p(amax), _p(gy), _stream()), "bn_pool_bwd")
-        _lib.count(3)
+        gy, dgamma, dbeta = _bn_pool_bwd_impl(gz, ctx.saved_tensors, ctx.geom, half=False)
         return (gy if ctx.needs_input_grad[0] else None, dgamma if ctx.needs_input_grad[1] else None,
                 dbeta if ctx.needs_input_grad[2] else None, None, None, None, None, None, None, None)
 
@@ -739,6 +754,45 @@ def stem_conv_supported(x, weight, stride, padding):
     return bool(_lib.lib().bdbnn_stem_supported(x.shape[0], x.shape[2], x.shape[3]))
 
 
+def _stem_conv_fwd_impl(x, weight):
+    """stem_pack -> stem_conv_fwd. Returns (y fp32 channels_last, xw, x_amax)."""
+    L = _lib.lib()
+    dev = x.device
+    n, _, h, w = x.shape
+    xd = x.detach()
+    if not (xd.is_contiguous() or xd.is_contiguous(memory_format=torch.channels_last)):
+        xd = xd.contiguous()
+    wd = weight.detach().contiguous()
+    st = _stream()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    xw = torch.empty((int(L.bdbnn_stem_xw_bytes(n, h, w)) // 2,), dtype=torch.int16, device=dev)
+    x_amax = torch.empty((1,), dtype=torch.int32, device=dev)
+    wf = torch.empty((64, 7, 32), dtype=torch.int16, device=dev)
+    alpha = torch.empty((64,), dtype=torch.float32, device=dev)
+    key = f"stem_N{n}_{h}x{w}"
+    with _timed("stem_pack", key, 4 * xd.numel() * 2 + xw.numel() * 2):
+        _lib.check(L.bdbnn_stem_pack(_p(xd), n, h, w, xd.stride(0), xd.stride(1), xd.stride(2), xd.stride(3),
+                                     _p(wd), _p(xw), _p(x_amax), _p(wf), _p(alpha), st), "stem_pack")
+    y = torch.empty((n, 64, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+    with _timed("stem_conv_fwd", key, xw.numel() * 2 + 4 * y.numel()):
+        _lib.check(L.bdbnn_stem_conv_fwd(_p(xw), _p(wf), _p(alpha), _p(y), n, h, w, st), "stem_conv_fwd")
+    _lib.count(5)
+    return y, xw, x_amax
+
+
+def _stem_wgrad_impl(gys, g_amax, xw, x_amax, n, h, w):
+    L = _lib.lib()
+    dev = gys.device
+    gw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dev)
+    nbytes = int(L.bdbnn_stem_wgrad_workspace_bytes(n, h, w))
+    ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+    with _timed("stem_conv_wgrad", f"stem_N{n}_{h}x{w}", 2 * gys.numel() + xw.numel() * 2):
+        _lib.check(L.bdbnn_stem_conv_wgrad(_p(gys), _p(g_amax), _p(xw), _p(x_amax), _p(gw), n, h, w,
+                                           _p(ws), nbytes, _stream()), "stem_conv_wgrad")
+    _lib.count(2)
+    return gw
+
+
 class _StemConv(torch.autograd.Function):
     """y = conv2d(x, W, stride 2, pad 3) for the 3 -> 64 channel 7x7 stem (csrc/stem.cu).
     forward : stem_pack (amax, fp16 window image, fp16 weights) -> stem_conv_fwd (tcgen05, 7-tap implicit GEMM)
@@ -746,28 +800,8 @@ class _StemConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight):
-        L = _lib.lib()
-        dev = x.device
-        n, _, h, w = x.shape
-        xd = x.detach()
-        if not (xd.is_contiguous() or xd.is_contiguous(memory_format=torch.channels_last)):
-            xd = xd.contiguous()
-        wd = weight.detach().contiguous()
-        st = _stream()
-        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-        xw = torch.empty((int(L.bdbnn_stem_xw_bytes(n, h, w)) // 2,), dtype=torch.int16, device=dev)
-        x_amax = torch.empty((1,), dtype=torch.int32, device=dev)
-        wf = torch.empty((64, 7, 32), dtype=torch.int16, device=dev)
-        alpha = torch.empty((64,), dtype=torch.float32, device=dev)
-        key = f"stem_N{n}_{h}x{w}"
-        with _timed("stem_pack", key, 4 * xd.numel() * 2 + xw.numel() * 2):
-            _lib.check(L.bdbnn_stem_pack(_p(xd), n, h, w, xd.stride(0), xd.stride(1), xd.stride(2), xd.stride(3),
-                                         _p(wd), _p(xw), _p(x_amax), _p(wf), _p(alpha), st), "stem_pack")
-        y = torch.empty((n, 64, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
-        with _timed("stem_conv_fwd", key, xw.numel() * 2 + 4 * y.numel()):
-            _lib.check(L.bdbnn_stem_conv_fwd(_p(xw), _p(wf), _p(alpha), _p(y), n, h, w, st), "stem_conv_fwd")
-        _lib.count(5)
-        ctx.geom = (n, h, w, ho, wo)
+        y, xw, x_amax = _stem_conv_fwd_impl(x, weight)
+        ctx.geom = (x.shape[0], x.shape[2], x.shape[3], y.shape[2], y.shape[3])
         ctx.save_for_backward(xw, x_amax)
         return y
 
@@ -779,22 +813,52 @@ class _StemConv(torch.autograd.Function):
         n, h, w, ho, wo = ctx.geom
         xw, x_amax = ctx.saved_tensors
         dev = gy.device
-        st = _stream()
         g = _nhwc(gy)
-        key = f"stem_N{n}_{h}x{w}"
         ones = torch.ones((64,), dtype=torch.float32, device=dev)
         gys = torch.empty((n, ho, wo, 64), dtype=torch.int16, device=dev)
         g_amax = torch.empty((1,), dtype=torch.int32, device=dev)
-        with _timed("stem_grad_pack", key, 8 * g.numel() + 2 * g.numel()):
-            _lib.check(L.bdbnn_grad_pack(_p(g), _p(ones), n * ho * wo, 64, 3, _p(g_amax), _p(gys), st), "grad_pack")
-        gw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dev)
-        nbytes = int(L.bdbnn_stem_wgrad_workspace_bytes(n, h, w))
-        ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
-        with _timed("stem_conv_wgrad", key, 2 * g.numel() + xw.numel() * 2):
-            _lib.check(L.bdbnn_stem_conv_wgrad(_p(gys), _p(g_amax), _p(xw), _p(x_amax), _p(gw), n, h, w,
-                                               _p(ws), nbytes, st), "stem_conv_wgrad")
-        _lib.count(4)
-        return None, gw
+        with _timed("stem_grad_pack", f"stem_N{n}_{h}x{w}", 8 * g.numel() + 2 * g.numel()):
+            _lib.check(L.bdbnn_grad_pack(_p(g), _p(ones), n * ho * wo, 64, 3, _p(g_amax), _p(gys), _stream()),
+                       "grad_pack")
+        _lib.count(2)
+        return None, _stem_wgrad_impl(gys, g_amax, xw, x_amax, n, h, w)
+
+
+class _StemFused(torch.autograd.Function):
+    """z = maxpool(BN_train(conv7x7/2(x, W))) as ONE autograd node: the conv output's gradient goes from
+    bn_pool_bwd to stem_conv_wgrad as the fp16 operand only (no fp32 gradient of the 112x112x64 tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad):
+        ctx.set_materialize_grads(False)
+        y, xw, x_amax = _stem_conv_fwd_impl(x, weight)
+        outs, saved, ctx.geom = _bn_pool_fwd_impl(y, gamma, beta, running_mean, running_var, momentum, eps, k,
+                                                  stride, pad)
+        ctx.xgeom = (x.shape[0], x.shape[2], x.shape[3])
+        ctx.save_for_backward(xw, x_amax, *saved)
+        nd = [t for t in outs[1:] if t is not None]
+        if nd:
+            ctx.mark_non_differentiable(*nd)
+        return outs
+
+    @staticmethod
+    def backward(ctx, gz, *_unused):
+        if gz is None:
+            return (None,) * 11
+        xw, x_amax = ctx.saved_tensors[:2]
+        (gys, g_amax), dgamma, dbeta = _bn_pool_bwd_impl(gz, ctx.saved_tensors[2:], ctx.geom, half=True)
+        gw = _stem_wgrad_impl(gys, g_amax, xw, x_amax, *ctx.xgeom) if ctx.needs_input_grad[1] else None
+        return (None, gw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
+                None, None, None, None, None, None, None)
+
+
+def stem_conv_bn_pool(x, weight, gamma, beta, running_mean, running_var, momentum, eps, kernel_size, stride, padding):
+    """maxpool(BN_train(stem_conv(x))); the result carries `_bdbnn_pack` for the first binary conv."""
+    z, zs, zm, zb, zb8 = _StemFused.apply(x, weight, gamma, beta, running_mean, running_var, momentum, eps,
+                                          int(kernel_size), int(stride), int(padding))
+    if zs is not None:
+        z._bdbnn_pack = (zs, zm, zb, grad_mode()[3], zb8)
+    return z
 
 
 def stem_conv(x, weight):

@@ -83,16 +83,19 @@ class ResNetImageNet(nn.Module):
         return nn.Sequential(*layers)
 
     def _stem(self, x):
-        c1 = self.conv1
-        if (type(c1) is nn.Conv2d and c1.bias is None and F_.stem_tc_enabled() and
-                F_.stem_conv_supported(x, c1.weight, c1.stride, c1.padding)):
-            y = F_.stem_conv(x, c1.weight)        # tcgen05 stem (csrc/stem.cu); BDBNN_STEM_TC=0 -> cuDNN
-        else:
-            y = c1(x)
-        bn, mp = self.bn1, self.maxpool
-        if (y.is_cuda and bn.training and F_.fuse_enabled() and isinstance(mp, MaxPool2dNHWC) and bn.affine and
-                bn.track_running_stats and bn.momentum is not None and y.dtype == torch.float32 and
-                y.shape[1] % 4 == 0):
+        c1, bn, mp = self.conv1, self.bn1, self.maxpool
+        tc_stem = (type(c1) is nn.Conv2d and c1.bias is None and F_.stem_tc_enabled() and
+                   F_.stem_conv_supported(x, c1.weight, c1.stride, c1.padding))   # BDBNN_STEM_TC=0 -> cuDNN
+        fuse = (x.is_cuda and bn.training and F_.fuse_enabled() and isinstance(mp, MaxPool2dNHWC) and bn.affine and
+                bn.track_running_stats and bn.momentum is not None and x.dtype == torch.float32 and
+                c1.out_channels % 4 == 0)
+        if tc_stem and fuse:
+            z = F_.stem_conv_bn_pool(x, c1.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum,
+                                     bn.eps, mp.kernel_size, mp.stride, mp.padding)
+            bn.num_batches_tracked.add_(1)
+            return z
+        y = F_.stem_conv(x, c1.weight) if tc_stem else c1(x)
+        if fuse:
             z = F_.stem_bn_pool(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps,
                                 mp.kernel_size, mp.stride, mp.padding)
             bn.num_batches_tracked.add_(1)

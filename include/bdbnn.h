@@ -227,7 +227,10 @@ BDBNN_API int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* me
  *              optional packs of z as in bdbnn_bn_fwd.  Scratch as bdbnn_bn_fwd.
  * bn_pool_bwd: g_pool = grad of z -> gy = grad of y [N,H,W,C] (BN backward with the pooled gradient
  *              scattered to the winners), dgamma, dbeta.  `ones` = float[C] of 1.0 (unit gradient scale);
- *              scratch: sums_ws double[2C], gmax_bits u32[C], consts_ws float[4C], amax_scratch u32[1]. */
+ *              scratch: sums_ws double[2C], gmax_bits u32[C], consts_ws float[4C], amax_scratch u32[1].
+ *              If `gys` is non-NULL the gradient is written ONLY as gys = fp16(gy * 2^e) [N,H,W,C] with
+ *              amax_scratch holding the bound e was derived from (FP16S operand of bdbnn_stem_conv_wgrad);
+ *              gy may then be NULL. */
 BDBNN_API int bdbnn_bn_pool_fwd(const float* y, const float* gamma, const float* beta, int32_t N, int32_t H, int32_t W,
                       int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, float eps,
                       float momentum, float* running_mean, float* running_var, double* sums_ws,
@@ -239,7 +242,7 @@ BDBNN_API int bdbnn_bn_pool_bwd(const float* g_pool, const uint8_t* idx, const f
                       const uint32_t* ymax_bits, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
                       int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, double* sums_ws, uint32_t* gmax_bits,
                       float* consts_ws, float* dgamma, float* dbeta, uint32_t* amax_scratch, float* gy,
-                      void* stream);
+                      uint16_t* gys, void* stream);
 
 /* ---- NHWC max-pool (stem of the ImageNet shells; torch.nn.MaxPool2d semantics) --------------------
  * Caller side of the path (the ops either side of the binary convs).  x,y,gy,gx fp32

@@ -314,3 +314,53 @@ def test_stem_conv_module_path_and_fallback(monkeypatch):
     monkeypatch.setenv("BDBNN_STEM_TC", "0")
     b = net._stem(x)
     assert (a - b).abs().max().item() <= 5e-3 * b.abs().max().item()
+
+
+@pytest.mark.parametrize("geom", [(4, 64, 64), (2, 224, 224), (3, 38, 50)])
+def test_stem_fused_conv_bn_pool(geom):
+    """One-node stem (conv -> BN(train) -> maxpool, gradient handed to the wgrad as fp16 only) vs the two-node
+    path on the same kernels (identical forward; weight gradient within fp16-rounding distance) and vs an
+    fp64 torch stem."""
+    import torch.nn as nn
+    from bdbnn_b200 import functional as F_
+    n, h, w = geom
+    g = torch.Generator().manual_seed(97 + h)
+    x = torch.randn(n, 3, h, w, generator=g)
+    wt = torch.randn(64, 3, 7, 7, generator=g) * 0.06
+    gam = torch.rand(64, generator=g) + 0.5
+    bet = torch.randn(64, generator=g) * 0.2
+    xd = x.cuda().contiguous(memory_format=torch.channels_last)
+
+    def run(fused):
+        wd = wt.cuda().requires_grad_(True)
+        gd, bd = gam.cuda().requires_grad_(True), bet.cuda().requires_grad_(True)
+        rm, rv = torch.zeros(64).cuda(), torch.ones(64).cuda()
+        if fused:
+            z = F_.stem_conv_bn_pool(xd, wd, gd, bd, rm, rv, 0.1, 1e-5, 3, 2, 1)
+        else:
+            z = F_.stem_bn_pool(F_.stem_conv(xd, wd), gd, bd, rm, rv, 0.1, 1e-5, 3, 2, 1)
+        gz = torch.randn(z.shape, generator=torch.Generator().manual_seed(5)).cuda()
+        z.backward(gz.contiguous(memory_format=torch.channels_last))
+        return z.detach(), wd.grad, gd.grad, bd.grad, rm, rv, gz
+
+    zf, gwf, ggf, gbf, rmf, rvf, gz = run(True)
+    zu, gwu, ggu, gbu, rmu, rvu, _ = run(False)
+    # same kernels; the BN statistics are summed with fp64 atomics, so the last bits may differ run to run
+    for a, b in ((zf, zu), (rmf, rmu), (rvf, rvu), (ggf, ggu), (gbf, gbu)):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+    assert (gwf - gwu).abs().max().item() <= 2e-3 * gwu.abs().max().item()
+    assert hasattr(zf, "shape") and zf.shape == (n, 64, ((h - 1) // 2) // 2 + 1, ((w - 1) // 2) // 2 + 1)
+    # fp64 torch BN + max-pool + conv weight gradient, evaluated on the GPU conv's own output y (pooling
+    # winners are discrete: an fp64 conv would flip a few near-ties and move whole gradient entries)
+    y = F_.stem_conv(xd, wt.cuda()).cpu().double().requires_grad_(True)
+    bn = nn.BatchNorm2d(64).double()
+    bn.weight.data, bn.bias.data = gam.double(), bet.double()
+    zr = nn.functional.max_pool2d(bn(y), 3, 2, 1)
+    zr.backward(gz.cpu().double())
+    gw_ref = torch.nn.grad.conv2d_weight(x.double(), (64, 3, 7, 7), y.grad, stride=2, padding=3)
+    torch.testing.assert_close(zf.cpu().double(), zr.detach(), rtol=1e-5, atol=1e-5)
+    assert (gwf.cpu().double() - gw_ref).abs().max().item() <= 2e-3 * gw_ref.abs().max().item()
+    assert (ggf.cpu().double() - bn.weight.grad).abs().max().item() <= 2e-5 * bn.weight.grad.abs().max().item()
+    # and the conv itself against an fp64 conv (TF32-class operands)
+    yr = nn.functional.conv2d(x.double(), wt.double(), None, 2, 3)
+    assert (y.detach() - yr).abs().max().item() <= 2e-3 * yr.abs().max().item()
