@@ -37,11 +37,11 @@ SIGNATURES = {
     "bdbnn_stem_xw_bytes": (c_size_t, [c_int, c_int, c_int]),
     "bdbnn_stem_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "bdbnn_stem_pack": (c_int, [_P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
-    "bdbnn_stem_conv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "bdbnn_stem_conv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "bdbnn_stem_conv_wgrad": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
-    "bdbnn_binconv_fwd_tc8": (c_int, [_P, _P, _P, _P, _SH, _P]),
+    "bdbnn_binconv_fwd_tc8": (c_int, [_P, _P, _P, _P, _SH, _P, _P, _P]),
     "bdbnn_binconv_fwd_xnor": (c_int, [_P, _P, _P, _P, _SH, _P]),
-    "bdbnn_binconv_fwd_tc": (c_int, [_P, _P, c_int, _P, _P, _SH, _P]),
+    "bdbnn_binconv_fwd_tc": (c_int, [_P, _P, c_int, _P, _P, _SH, _P, _P, _P]),
     "bdbnn_binconv_dgrad": (c_int, [_P, _P, _P, _P, _P, _SH, _P]),
     "bdbnn_binconv_wgrad": (c_int, [_P, _P, _P, _P, _SH, _P]),
     "bdbnn_grad_pack": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
@@ -53,9 +53,9 @@ SIGNATURES = {
     "bdbnn_kd_logits_fwd_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
     "bdbnn_kd_layer_multi_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P]),
     "bdbnn_kd_layer_multi_bwd": (c_int, [_P, _P, c_int, _P, _P, c_int, _P]),
-    "bdbnn_bn_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, ctypes.c_float, ctypes.c_float] + [_P] * 12 + [c_int, _P]),
+    "bdbnn_bn_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, ctypes.c_float, ctypes.c_float] + [_P] * 12 + [c_int, c_int, _P]),
     "bdbnn_bn_bwd_pack": (c_int, [_P] * 7 + [c_int64, c_int, c_int] + [_P] * 8),
-    "bdbnn_bn_pool_fwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [ctypes.c_float, ctypes.c_float] + [_P] * 14 + [c_int, _P]),
+    "bdbnn_bn_pool_fwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [ctypes.c_float, ctypes.c_float] + [_P] * 14 + [c_int, c_int, _P]),
     "bdbnn_bn_pool_bwd": (c_int, [_P] * 9 + [c_int] * 9 + [_P] * 9),
     "bdbnn_maxpool_fwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [_P]),
     "bdbnn_maxpool_bwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [_P]),

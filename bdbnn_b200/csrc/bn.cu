@@ -243,6 +243,16 @@ static int bn_grid(int64_t work, int C4, int per_sm = 8) {
   return int(blocks);
 }
 
+// Forward statistics pass (also the fallback of conv kernels without a statistics epilogue).
+int bn_stats_launch(const float* y, int64_t n_pix, int C, double* sums, uint32_t* ymax, cudaStream_t st) {
+  BDBNN_REQUIRE(C > 0 && (C & 3) == 0 && C <= 4096, "bn_stats: C must be a multiple of 4, <= 4096");
+  const int C4 = C / 4;
+  bn_reduce_kernel<false><<<bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3), kBnThreads,
+                            size_t(3 * C) * sizeof(float), st>>>(reinterpret_cast<const float4*>(y), nullptr, nullptr,
+                                                                 nullptr, n_pix, C4, sums, ymax);
+  return check_launch("bn_reduce_kernel<fwd>");
+}
+
 }  // namespace bdbnn
 
 using namespace bdbnn;
@@ -258,7 +268,7 @@ extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* 
                             int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
                             float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean,
                             float* invstd, float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits,
-                            uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, void* stream) {
+                            uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, int32_t stats_ready, void* stream) {
   const bool pack = sign_bits != nullptr;
   int rc = bn_dims_ok(n_pix, C, pack);
   if (rc) return rc;
@@ -267,12 +277,12 @@ extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* 
   BDBNN_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_fwd: running stats come in pairs");
   cudaStream_t st = cudaStream_t(stream);
   const int C4 = C / 4;
-  BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
-  BDBNN_CUDA(cudaMemsetAsync(ymax_bits, 0, size_t(C) * sizeof(uint32_t), st));
-  bn_reduce_kernel<false><<<bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
-      reinterpret_cast<const float4*>(y), nullptr, nullptr, nullptr, n_pix, C4, sums_ws, ymax_bits);
-  rc = check_launch("bn_reduce_kernel<fwd>");
-  if (rc) return rc;
+  if (!stats_ready) {          // else: sums_ws / ymax_bits were filled by the conv's epilogue
+    BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
+    BDBNN_CUDA(cudaMemsetAsync(ymax_bits, 0, size_t(C) * sizeof(uint32_t), st));
+    rc = bn_stats_launch(y, n_pix, C, sums_ws, ymax_bits, st);
+    if (rc) return rc;
+  }
   float* a = ab_ws;
   float* b = ab_ws + C;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_ws, n_pix, C, eps, gamma, beta, mean, invstd, a, b,
@@ -464,6 +474,77 @@ bn_pool_bwd_kernel(const float4* __restrict__ gpool, const uint32_t* __restrict_
   }
 }
 
+// Same result for the 3x3 / stride-2 / pad-1 pool (the stem's), restructured so that one thread owns a 2x2
+// block of input positions (rows 2a, 2a+1; columns 2b, 2b+1) of one channel quad: the four positions are
+// covered by the same four pooling windows (a..a+1, b..b+1), so each window's winner word and gradient
+// are loaded once for four outputs (the generic kernel re-reads them 2.25x per output on average) and
+// the index arithmetic is per block, not per element.  Windows are visited in the generic kernel's
+// order, so the sums are bit-identical.  blockDim.x must be a multiple of C4.
+template <bool HALF>
+__global__ void __launch_bounds__(kBnThreads)
+bn_pool_bwd_k3s2_kernel(const float4* __restrict__ gpool, const uint32_t* __restrict__ idx,
+                        const float4* __restrict__ y, const float4* __restrict__ consts, int H, int W, int C4,
+                        int Ho, int Wo, int HB, int WB, float4* __restrict__ gy,
+                        const uint32_t* __restrict__ amax_bits, uint2* __restrict__ gys) {
+  const float up = HALF ? amax_pow2_scale(__ldg(amax_bits), false) : 1.0f;
+  const int c = threadIdx.x % C4;
+  const float4 k0 = consts[c * 4 + 0], k1 = consts[c * 4 + 1], k2 = consts[c * 4 + 2], k3 = consts[c * 4 + 3];
+  const int n = blockIdx.x / HB, a = blockIdx.x - n * HB;
+  const int h0 = 2 * a, h1 = 2 * a + 1;
+  const int per_row = WB * C4;
+  for (int j = threadIdx.x; j < per_row; j += blockDim.x) {
+    const int b = j / C4;
+    const int w0 = 2 * b, w1 = 2 * b + 1;
+    // windows (a,b) (a,b+1) (a+1,b) (a+1,b+1)
+    float4 g[4];
+    uint32_t wd[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ho = a + (q >> 1), wo = b + (q & 1);
+      if (ho < Ho && wo < Wo) {
+        const int64_t o = ((int64_t(n) * Ho + ho) * Wo + wo) * C4 + c;
+        wd[q] = __ldg(idx + o);
+        g[q] = __ldg(gpool + o);
+      } else {
+        wd[q] = 0xffffffffu;                      // tap 255 never matches
+        g[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    auto pick = [&](float4& acc, int q, uint32_t tap) {
+      const uint32_t w4 = wd[q];
+      if ((w4 & 0xffu) == tap) acc.x += g[q].x;
+      if (((w4 >> 8) & 0xffu) == tap) acc.y += g[q].y;
+      if (((w4 >> 16) & 0xffu) == tap) acc.z += g[q].z;
+      if ((w4 >> 24) == tap) acc.w += g[q].w;
+    };
+    float4 z00 = make_float4(0.f, 0.f, 0.f, 0.f), z01 = z00, z10 = z00, z11 = z00;
+    pick(z00, 0, 4u);                                             // (2a  , 2b  ): centre of window (a,b)
+    pick(z01, 0, 5u); pick(z01, 1, 3u);                           // (2a  , 2b+1)
+    pick(z10, 0, 7u); pick(z10, 2, 1u);                           // (2a+1, 2b  )
+    pick(z11, 0, 8u); pick(z11, 1, 6u); pick(z11, 2, 2u); pick(z11, 3, 0u);
+    auto emit = [&](int h, int w, const float4& gz) {
+      if (h >= H || w >= W) return;
+      const int64_t i = ((int64_t(n) * H + h) * W + w) * C4 + c;
+      const float4 v = __ldcs(y + i);
+      float4 o;
+      o.x = (gz.x - k0.x - (v.x - k0.z) * k0.y) * k0.w;
+      o.y = (gz.y - k1.x - (v.y - k1.z) * k1.y) * k1.w;
+      o.z = (gz.z - k2.x - (v.z - k2.z) * k2.y) * k2.w;
+      o.w = (gz.w - k3.x - (v.w - k3.z) * k3.y) * k3.w;
+      if (HALF) {
+        const __half2 p0 = __floats2half2_rn(o.x * up, o.y * up), p1 = __floats2half2_rn(o.z * up, o.w * up);
+        gys[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+      } else {
+        gy[i] = o;
+      }
+    };
+    emit(h0, w0, z00);
+    emit(h0, w1, z01);
+    emit(h1, w0, z10);
+    emit(h1, w1, z11);
+  }
+}
+
 }  // namespace bdbnn
 
 using namespace bdbnn;
@@ -481,7 +562,7 @@ extern "C" int bdbnn_bn_pool_fwd(const float* y, const float* gamma, const float
                                  int32_t Wo, float eps, float momentum, float* running_mean, float* running_var,
                                  double* sums_ws, uint32_t* ymax_bits, float* mean, float* invstd, float* ab_ws,
                                  float* z, float* y_sel, uint8_t* idx, uint32_t* sign_bits, uint32_t* mask_bits,
-                                 uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, void* stream) {
+                                 uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, int32_t stats_ready, void* stream) {
   int rc = pool_geom_ok(N, H, W, C, k, stride, pad, Ho, Wo);
   if (rc) return rc;
   const bool pack = sign_bits != nullptr;
@@ -491,12 +572,12 @@ extern "C" int bdbnn_bn_pool_fwd(const float* y, const float* gamma, const float
   cudaStream_t st = cudaStream_t(stream);
   const int C4 = C / 4;
   const int64_t n_pix = int64_t(N) * H * W;
-  BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
-  BDBNN_CUDA(cudaMemsetAsync(ymax_bits, 0, size_t(C) * sizeof(uint32_t), st));
-  bn_reduce_kernel<false><<<bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
-      reinterpret_cast<const float4*>(y), nullptr, nullptr, nullptr, n_pix, C4, sums_ws, ymax_bits);
-  rc = check_launch("bn_reduce_kernel<fwd>");
-  if (rc) return rc;
+  if (!stats_ready) {
+    BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
+    BDBNN_CUDA(cudaMemsetAsync(ymax_bits, 0, size_t(C) * sizeof(uint32_t), st));
+    rc = bn_stats_launch(y, n_pix, C, sums_ws, ymax_bits, st);
+    if (rc) return rc;
+  }
   float* a = ab_ws;
   float* b = ab_ws + C;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_ws, n_pix, C, eps, gamma, beta, mean, invstd, a, b,
@@ -548,6 +629,22 @@ extern "C" int bdbnn_bn_pool_bwd(const float* g_pool, const uint8_t* idx, const 
   rc = check_launch("bn_bwd_bound_kernel");
   if (rc) return rc;
   const int64_t total = n_full * C4;
+  if (k == 3 && stride == 2 && pad == 1 && C4 <= kBnThreads) {
+    const int HB = (H + 1) / 2, WB = (W + 1) / 2;
+    const int threads = (kBnThreads / C4) * C4;
+    const unsigned grid = unsigned(N) * unsigned(HB);
+    if (gys != nullptr)
+      bn_pool_bwd_k3s2_kernel<true><<<grid, threads, 0, st>>>(
+          reinterpret_cast<const float4*>(g_pool), reinterpret_cast<const uint32_t*>(idx),
+          reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(consts_ws), H, W, C4, Ho, Wo, HB, WB,
+          nullptr, amax_scratch, reinterpret_cast<uint2*>(gys));
+    else
+      bn_pool_bwd_k3s2_kernel<false><<<grid, threads, 0, st>>>(
+          reinterpret_cast<const float4*>(g_pool), reinterpret_cast<const uint32_t*>(idx),
+          reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(consts_ws), H, W, C4, Ho, Wo, HB, WB,
+          reinterpret_cast<float4*>(gy), nullptr, nullptr);
+    return check_launch("bn_pool_bwd_k3s2_kernel");
+  }
   if (gys != nullptr)
     bn_pool_bwd_kernel<true><<<bn_grid(total, C4), kBnThreads, 0, st>>>(
         reinterpret_cast<const float4*>(g_pool), reinterpret_cast<const uint32_t*>(idx),

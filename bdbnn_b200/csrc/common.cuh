@@ -78,6 +78,9 @@ __host__ __device__ inline float amax_pow2_scale(uint32_t amax_bits, bool invers
 #endif
 }
 
+// bn.cu: sum y, sum y^2, max|y| per channel of an NHWC fp32 tensor into (pre-zeroed) sums / ymax.
+int bn_stats_launch(const float* y, int64_t n_pix, int C, double* sums, uint32_t* ymax, cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -164,11 +164,12 @@ extern "C" int bdbnn_stem_pack(const float* x, int32_t N, int32_t H, int32_t W, 
 }
 
 extern "C" int bdbnn_stem_conv_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, float* y, int32_t N,
-                                   int32_t H, int32_t W, void* stream) {
+                                   int32_t H, int32_t W, double* bn_sums, uint32_t* bn_ymax, void* stream) {
   StemGeom g;
   BDBNN_REQUIRE(stem_geom(N, H, W, &g), "stem_conv_fwd: geometry not supported");
   BDBNN_REQUIRE(xw && wf && alpha && y, "stem_conv_fwd: NULL pointer");
-  return launch_stem_fwd(xw, wf, alpha, y, g, cudaStream_t(stream));
+  BDBNN_REQUIRE((bn_sums == nullptr) == (bn_ymax == nullptr), "stem_conv_fwd: bn_sums and bn_ymax go together");
+  return launch_stem_fwd(xw, wf, alpha, y, g, bn_sums, bn_ymax, cudaStream_t(stream));
 }
 
 extern "C" int bdbnn_stem_conv_wgrad(const uint16_t* gys, const uint32_t* g_amax_bits, const uint16_t* xw,

@@ -322,6 +322,10 @@ struct TcConvLaunch {
   int fmt;                       // operand format (BDBNN_FMT_*); -1 = fp8 e4m3 bytes (forward only)
   const uint32_t* amax_bits;     // FP16S gradient: device word with max|A|; epilogue multiplies by 2^-e
   const float* add;              // dgrad: optional tensor added to the result (shortcut gradient), or NULL
+  // forward only: per-output-channel BatchNorm statistics of the result, accumulated by the epilogue
+  // (sum y, sum y^2 as doubles [2*Nout]; max|y| bits [Nout]); NULL = off.  Zeroed by the caller.
+  double* bn_sums;
+  uint32_t* bn_ymax;
   // stem conv: A is an overlapping-window view (make_window_map) instead of a dense NHWC tensor
   int win;                       // 0 = dense NHWC
   uint64_t win_stride, win_row_stride, win_img_stride;
@@ -348,7 +352,14 @@ inline bool stem_geom(int N, int H, int W, StemGeom* g) {
 }
 constexpr int kStemCout = 64, kStemTaps = 7, kStemWin = 32;
 int launch_stem_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, float* y, const StemGeom& g,
-                    cudaStream_t st);
+                    double* bn_sums, uint32_t* bn_ymax, cudaStream_t st);
+// zero the statistics buffers of a conv launch (no-op when off)
+inline int bn_stats_zero(double* sums, uint32_t* ymax, int C, cudaStream_t st) {
+  if (!sums) return BDBNN_OK;
+  BDBNN_CUDA(cudaMemsetAsync(sums, 0, size_t(2 * C) * sizeof(double), st));
+  BDBNN_CUDA(cudaMemsetAsync(ymax, 0, size_t(C) * sizeof(uint32_t), st));
+  return BDBNN_OK;
+}
 size_t stem_wgrad_workspace_bytes(const StemGeom& g);
 int launch_stem_wgrad(const uint16_t* gys, const uint16_t* xw, float* ws, size_t ws_bytes, int* ksplit_out,
                       const StemGeom& g, cudaStream_t st);

@@ -328,13 +328,18 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   BDBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   dim3 grid(unsigned(p.tiles_h * tiles_n_eff), unsigned(L.Nout / p.BN));
   kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
-  return check_launch("tc_conv_kernel");
+  rc = check_launch("tc_conv_kernel");
+  if (rc) return rc;
+  // this kernel has no statistics epilogue: one extra pass over the result when they were asked for
+  if (MODE == 0 && L.bn_sums != nullptr)
+    return bn_stats_launch(L.out, int64_t(L.NIMG) * L.OHf * L.OWf, L.Nout, L.bn_sums, L.bn_ymax, st);
+  return BDBNN_OK;
 }
 
 // Stem conv forward (7x7 / stride 2 / pad 3 on 3 channels) as a 7-tap implicit GEMM over the packed
 // window view: tap r reads window row 2*oh + r, K = 32 values (8 pixels x 4 halves) per tap.
 int launch_stem_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, float* y, const StemGeom& g,
-                    cudaStream_t st) {
+                    double* bn_sums, uint32_t* bn_ymax, cudaStream_t st) {
   TcConvLaunch L;
   memset(&L, 0, sizeof(L));
   L.A = xw; L.IH = g.HP; L.IW = g.Wo; L.Kc = kStemWin; L.a_halves = 1; L.in_step = 2;
@@ -345,6 +350,9 @@ int launch_stem_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, 
   L.n_taps = kStemTaps;
   L.out_step = 1; L.OHf = g.Ho; L.OWf = g.Wo;
   L.alpha = alpha; L.out = y; L.fmt = BDBNN_FMT_FP16;
+  L.bn_sums = bn_sums; L.bn_ymax = bn_ymax;
+  int rc = bn_stats_zero(bn_sums, bn_ymax, kStemCout, st);
+  if (rc) return rc;
   return launch_tc_conv<0>(L, st);
 }
 
@@ -366,7 +374,8 @@ extern "C" int bdbnn_tc_supported(const bdbnn_conv_shape* s) {
 }
 
 extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, int32_t fmt,
-                                    const float* alpha, float* y, const bdbnn_conv_shape* s, void* stream) {
+                                    const float* alpha, float* y, const bdbnn_conv_shape* s, double* bn_sums,
+                                    uint32_t* bn_ymax, void* stream) {
   BDBNN_REQUIRE(fmt == BDBNN_FMT_FP16 || fmt == BDBNN_FMT_BF16, "binconv_fwd_tc: bad operand format");
   int rc = validate_shape(s);
   if (rc) return rc;
@@ -385,11 +394,16 @@ extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_
   L.n_taps = s->kh * s->kw;
   L.out_step = 1; L.OHf = s->Ho; L.OWf = s->Wo;
   L.alpha = alpha; L.out = y; L.fmt = fmt;
+  BDBNN_REQUIRE((bn_sums == nullptr) == (bn_ymax == nullptr), "binconv_fwd_tc: bn_sums and bn_ymax go together");
+  L.bn_sums = bn_sums; L.bn_ymax = bn_ymax;
+  rc = bn_stats_zero(bn_sums, bn_ymax, s->Cout, cudaStream_t(stream));
+  if (rc) return rc;
   return launch_tc_conv<0>(L, cudaStream_t(stream));
 }
 
 extern "C" int bdbnn_binconv_fwd_tc8(const uint8_t* xb_fp8, const uint8_t* wf_fp8, const float* alpha, float* y,
-                                     const bdbnn_conv_shape* s, void* stream) {
+                                     const bdbnn_conv_shape* s, double* bn_sums, uint32_t* bn_ymax,
+                                     void* stream) {
   int rc = validate_shape(s);
   if (rc) return rc;
   BDBNN_REQUIRE(xb_fp8 && wf_fp8 && alpha && y, "binconv_fwd_tc8: NULL pointer");
@@ -411,6 +425,11 @@ extern "C" int bdbnn_binconv_fwd_tc8(const uint8_t* xb_fp8, const uint8_t* wf_fp
   L.n_taps = s->kh * s->kw;
   L.out_step = 1; L.OHf = s->Ho; L.OWf = s->Wo;
   L.alpha = alpha; L.out = y; L.fmt = -1;
+  BDBNN_REQUIRE((bn_sums == nullptr) == (bn_ymax == nullptr), "binconv_fwd_tc8: bn_sums and bn_ymax go together");
+  BDBNN_REQUIRE(bn_sums == nullptr || s->Cout <= 512, "binconv_fwd_tc8: statistics need Cout <= 512");
+  L.bn_sums = bn_sums; L.bn_ymax = bn_ymax;
+  rc = bn_stats_zero(bn_sums, bn_ymax, s->Cout, cudaStream_t(stream));
+  if (rc) return rc;
   rc = launch_tc_conv2(L, 0, cudaStream_t(stream));
   if (rc == BDBNN_ERR_UNSUPPORTED) set_error("binconv_fwd_tc8: geometry not supported by the persistent kernel");
   return rc;

@@ -48,8 +48,12 @@ struct TcConv2Params {
   const float* alpha;
   const uint32_t* mask;
   float* out;
+  double* bn_sums;           // MODE 0: per-channel sum / sum of squares of the result [2*Nout] (or NULL)
+  uint32_t* bn_ymax;         // MODE 0: per-channel max|result| bits [Nout]
   long long* trace;          // optional clock64 trace of CTA 0 (bdbnn_debug_trace), else NULL
 };
+
+constexpr int kMaxStatCh = 512;   // channels the in-kernel BatchNorm statistics can hold per CTA
 
 // role r (0 producer, 1 mma, 2 epilogue) appends (event id, clock) pairs to its 2048-entry lane.
 #define BDBNN_TR(r, ev)                                                           \
@@ -98,6 +102,12 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t tap_shift_rows[kMaxTaps];   // halo: row offset of tap i inside the patch
+  // BatchNorm statistics of this CTA's output rows (MODE 0 with p.bn_sums): fp32 partials, flushed once
+  __shared__ float stat_sum[MODE == 0 ? kMaxStatCh : 1], stat_sq[MODE == 0 ? kMaxStatCh : 1];
+  __shared__ uint32_t stat_max[MODE == 0 ? kMaxStatCh : 1];
+  const bool do_stats = MODE == 0 && p.bn_sums != nullptr;
+  if (do_stats)
+    for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { stat_sum[i] = 0.f; stat_sq[i] = 0.f; stat_max[i] = 0u; }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < p.n_taps)
@@ -248,10 +258,50 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // 4 KB per-warp staging tile behind the TMA ring (generic-proxy only, never touched by TMA/UMMA)
     uint8_t* stage_warp = smem_raw + (ring_base - smem_u32(smem_raw)) + size_t(p.stages) * p.stage_bytes +
                           size_t(warp) * 4096;
+    // BatchNorm statistics: each lane keeps (sum, sum of squares, max|.|) of the 4 channels it stores for
+    // every 32-column block of the N tile, across tiles and work items, and flushes them to shared memory
+    // only when the N tile changes or the CTA is done (per-block shuffles + atomics cost 25-35 % of the
+    // forward kernels when done per 32x32 block).
+    float4 acc_s[4], acc_q[4], acc_m[4];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) acc_s[cb] = acc_q[cb] = acc_m[cb] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int acc_nn0 = -1;
+    auto flush_stats = [&]() {
+      if (!do_stats || acc_nn0 < 0) return;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        if (cb * 32 >= p.BN) break;
+        float4 ss = acc_s[cb], sq = acc_q[cb], mx = acc_m[cb];
+        // lanes cq, cq+8, cq+16, cq+24 hold the same 4 channels for different rows
+#pragma unroll
+        for (int d = 8; d <= 16; d <<= 1) {
+          ss.x += __shfl_xor_sync(0xffffffffu, ss.x, d); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, d);
+          ss.z += __shfl_xor_sync(0xffffffffu, ss.z, d); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, d);
+          sq.x += __shfl_xor_sync(0xffffffffu, sq.x, d); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, d);
+          sq.z += __shfl_xor_sync(0xffffffffu, sq.z, d); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, d);
+          mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, d)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, d));
+          mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, d)); mx.w = fmaxf(mx.w, __shfl_xor_sync(0xffffffffu, mx.w, d));
+        }
+        if (lane < 8) {
+          const int ch = acc_nn0 + cb * 32 + lane * 4;
+          atomicAdd(&stat_sum[ch], ss.x); atomicAdd(&stat_sum[ch + 1], ss.y);
+          atomicAdd(&stat_sum[ch + 2], ss.z); atomicAdd(&stat_sum[ch + 3], ss.w);
+          atomicAdd(&stat_sq[ch], sq.x); atomicAdd(&stat_sq[ch + 1], sq.y);
+          atomicAdd(&stat_sq[ch + 2], sq.z); atomicAdd(&stat_sq[ch + 3], sq.w);
+          atomicMax(&stat_max[ch], __float_as_uint(mx.x)); atomicMax(&stat_max[ch + 1], __float_as_uint(mx.y));
+          atomicMax(&stat_max[ch + 2], __float_as_uint(mx.z)); atomicMax(&stat_max[ch + 3], __float_as_uint(mx.w));
+        }
+        acc_s[cb] = acc_q[cb] = acc_m[cb] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wcount) {
       const int sup = w / p.n_ntiles, nt = w - sup * p.n_ntiles;
       const SuperGeom g = super_geom(p, sup);
       const int nn0 = nt * p.BN;
+      if (do_stats && nn0 != acc_nn0) {
+        flush_stats();
+        acc_nn0 = nn0;
+      }
       const uint32_t buf = wcount % uint32_t(p.NB);
       BDBNN_TR(2, 0);
       mbar_wait(smem_u32(&tfull_bar[buf]), (wcount / uint32_t(p.NB)) & 1u);
@@ -289,7 +339,10 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (p.dbg & 2) continue;
         // Row offsets/validity of this warp's 32 rows are exchanged by shuffle in the store phase.
         const int64_t row_off = valid ? pix * p.Nout + nn0 : int64_t(-1);
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          const int c0 = cb * 32;
+          if (c0 >= p.BN) break;
           uint32_t v[32];
           tmem_ld32(tbase + uint32_t(c0), v);
           uint32_t word = 0;
@@ -336,7 +389,16 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (MODE == 1 && p.add != nullptr) {
               o.x += addv[i].x; o.y += addv[i].y; o.z += addv[i].z; o.w += addv[i].w;
             }
-            if (offs[i] >= 0) *reinterpret_cast<float4*>(p.out + offs[i] + c0 + cq * 4) = o;
+            if (offs[i] >= 0) {
+              *reinterpret_cast<float4*>(p.out + offs[i] + c0 + cq * 4) = o;
+              if (do_stats) {
+                float4& ss = acc_s[cb]; float4& sq = acc_q[cb]; float4& mx = acc_m[cb];
+                ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
+                sq.x += o.x * o.x; sq.y += o.y * o.y; sq.z += o.z * o.z; sq.w += o.w * o.w;
+                mx.x = fmaxf(mx.x, fabsf(o.x)); mx.y = fmaxf(mx.y, fabsf(o.y));
+                mx.z = fmaxf(mx.z, fabsf(o.z)); mx.w = fmaxf(mx.w, fabsf(o.w));
+              }
+            }
           }
         }
       }
@@ -345,9 +407,20 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       BDBNN_TR(2, 2);
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
     }
+    flush_stats();
   }
   tc_fence_before();
   __syncthreads();
+  if (do_stats) {
+    // one fp64 atomic per channel per CTA; channels this CTA never touched hold zeros
+    for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) {
+      if (stat_max[i] != 0u || stat_sum[i] != 0.f || stat_sq[i] != 0.f) {
+        atomicAdd(p.bn_sums + i, double(stat_sum[i]));
+        atomicAdd(p.bn_sums + p.Nout + i, double(stat_sq[i]));
+        atomicMax(p.bn_ymax + i, stat_max[i]);
+      }
+    }
+  }
   if (warp == 5) {
     __syncwarp();
     tc_fence_after();
@@ -393,6 +466,9 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   p.NB = 512 / (p.TS * p.BN);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
   p.fmt = L.fmt; p.amax_bits = L.amax_bits; p.add = L.add;
+  p.bn_sums = (mode == 0 && L.Nout <= kMaxStatCh) ? L.bn_sums : nullptr;
+  p.bn_ymax = L.bn_ymax;
+  if (L.bn_sums && !p.bn_sums) return BDBNN_ERR_UNSUPPORTED;
   p.b_bytes = uint32_t(p.BN) * row_bytes;
 
   int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
@@ -458,7 +534,8 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   if (rc) return rc;
   const uint32_t kStaging = 4u * 4096u;   // epilogue transpose tiles
   const uint32_t fixed = (p.halo ? 2u * p.patch_bytes : 0u) + kStaging;
-  const uint32_t budget = 224u * 1024u - 1024u;
+  // 227 KB per CTA minus static shared memory (barriers; MODE 0 also holds 6 KB of BN statistics)
+  const uint32_t budget = 224u * 1024u - 1024u - (mode == 0 ? 3u * kMaxStatCh * 4u : 0u);
   if (fixed + 2u * p.stage_bytes > budget) return BDBNN_ERR_UNSUPPORTED;
   int stages = int((budget - fixed) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

@@ -190,12 +190,12 @@ class _BinConv2d(torch.autograd.Function):
                         memory_format=torch.channels_last)
         if use8:
             with _timed("binconv_fwd_tc8", key, algorithmic_bytes("fwd_tc8", sh)):
-                _lib.check(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), ctypes.byref(sh), st),
-                           "binconv_fwd_tc8")
+                _lib.check(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), ctypes.byref(sh), None, None,
+                                                   st), "binconv_fwd_tc8")
         elif tc:
             with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
-                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), st),
-                           "binconv_fwd_tc")
+                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), None, None,
+                                                  st), "binconv_fwd_tc")
         else:
             with _timed("binconv_fwd_xnor", key, algorithmic_bytes("fwd_xnor", sh)):
                 _lib.check(L.bdbnn_binconv_fwd_xnor(_p(sign_bits), _p(wsign), _p(alpha), _p(y),
@@ -479,6 +479,10 @@ def fwd8_enabled():
     return os.environ.get(_FWD8_ENV, "1") != "0"
 
 
+def conv_stats_enabled():
+    return os.environ.get("BDBNN_CONV_STATS", "1") != "0"
+
+
 def fuse_enabled():
     return os.environ.get(_FUSE_ENV, "1") != "0"
 
@@ -536,14 +540,19 @@ class _ConvBNAddUnit(torch.autograd.Function):
                                        _p(wf8), _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
         y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
                         memory_format=torch.channels_last)
+        # BN batch statistics of y are accumulated by the conv kernel's epilogue (BDBNN_CONV_STATS=0: separate pass)
+        sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
+        ymax = torch.empty((cout,), **i32)
+        in_conv = conv_stats_enabled() and cout <= 512
+        s_ptr, m_ptr = (_p(sums), _p(ymax)) if in_conv else (None, None)
         if use8:
             with _timed("binconv_fwd_tc8", key, algorithmic_bytes("fwd_tc8", sh)):
-                _lib.check(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), ctypes.byref(sh), st),
-                           "binconv_fwd_tc8")
+                _lib.check(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), ctypes.byref(sh), s_ptr, m_ptr,
+                                                   st), "binconv_fwd_tc8")
         else:
             with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
-                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), st),
-                           "binconv_fwd_tc")
+                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), s_ptr, m_ptr,
+                                                  st), "binconv_fwd_tc")
         _lib.count(3)
         n_pix = n * sh.Ho * sh.Wo
         if res_is_x:            # identity shortcut: the residual IS the conv input (one autograd edge)
@@ -551,8 +560,6 @@ class _ConvBNAddUnit(torch.autograd.Function):
         else:
             rc = _nhwc(residual.detach()) if residual is not None else None
         z = torch.empty_like(y)
-        sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
-        ymax = torch.empty((cout,), **i32)
         mean = torch.empty((cout,), dtype=torch.float32, device=dev)
         invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
         ab = torch.empty((2 * cout,), dtype=torch.float32, device=dev)
@@ -561,11 +568,12 @@ class _ConvBNAddUnit(torch.autograd.Function):
         zm = torch.empty((n, sh.Ho, sh.Wo, cout // 32), **i32) if pack else None
         zb = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.int16, device=dev) if pack else None
         zb8 = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.uint8, device=dev) if (pack and fwd8_enabled()) else None
-        with _timed("bn_fwd", key, (4 + 12 + (2.25 if pack else 0) + (1 if zb8 is not None else 0)) * n_pix * cout):
+        with _timed("bn_fwd", key, ((0 if in_conv else 4) + 12 + (2.25 if pack else 0) +
+                                    (1 if zb8 is not None else 0)) * n_pix * cout):
             _lib.check(L.bdbnn_bn_fwd(_p(y), _p(rc), _p(gamma.detach()), _p(beta.detach()), n_pix, cout, float(eps),
                                       float(momentum), _p(running_mean), _p(running_var), _p(sums), _p(ymax),
-                                      _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm), _p(zb), _p(zb8), fmt, st),
-                       "bn_fwd")
+                                      _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm), _p(zb), _p(zb8), fmt,
+                                      1 if in_conv else 0, st), "bn_fwd")
         _lib.count(3)
         ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
         ctx.shapes = (tuple(x.shape), tuple(weight.shape))
@@ -649,8 +657,9 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
     return z
 
 
-def _bn_pool_fwd_impl(yc, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad):
-    """bn_pool_fwd launch sequence on an NHWC-contiguous y. Returns (outs, saved, geom)."""
+def _bn_pool_fwd_impl(yc, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad, stats=None):
+    """bn_pool_fwd launch sequence on an NHWC-contiguous y. Returns (outs, saved, geom).
+    stats = (sums, ymax) already filled by the conv that produced y, or None."""
     L = _lib.lib()
     n, c, h, w = yc.shape
     if c % 4:
@@ -660,8 +669,11 @@ def _bn_pool_fwd_impl(yc, gamma, beta, running_mean, running_var, momentum, eps,
     fmt = grad_mode()[3]
     i32 = dict(dtype=torch.int32, device=dev)
     f32 = dict(dtype=torch.float32, device=dev)
-    sums = torch.empty((2 * c,), dtype=torch.float64, device=dev)
-    ymax = torch.empty((c,), **i32)
+    if stats is not None:
+        sums, ymax = stats
+    else:
+        sums = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+        ymax = torch.empty((c,), **i32)
     mean, invstd, ab = torch.empty((c,), **f32), torch.empty((c,), **f32), torch.empty((2 * c,), **f32)
     z = torch.empty((n, c, ho, wo), memory_format=torch.channels_last, **f32)
     ysel = torch.empty((n, ho, wo, c), **f32)
@@ -671,12 +683,13 @@ def _bn_pool_fwd_impl(yc, gamma, beta, running_mean, running_var, momentum, eps,
     zm = torch.empty((n, ho, wo, c // 32), **i32) if pack else None
     zb = torch.empty((n, ho, wo, c), dtype=torch.int16, device=dev) if pack else None
     zb8 = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=dev) if (pack and fwd8_enabled()) else None
-    nbytes = 4 * n * h * w * c * 2 + (4 + 4 + 1 + (3.25 if pack else 0)) * n * ho * wo * c
+    nbytes = 4 * n * h * w * c * (1 if stats is not None else 2) + (4 + 4 + 1 + (3.25 if pack else 0)) * n * ho * wo * c
     with _timed("stem_bn_pool_fwd", f"N{n}_{h}x{w}_c{c}", nbytes):
         _lib.check(L.bdbnn_bn_pool_fwd(_p(yc), _p(gamma.detach()), _p(beta.detach()), n, h, w, c, k, stride, pad, ho,
                                        wo, float(eps), float(momentum), _p(running_mean), _p(running_var),
                                        _p(sums), _p(ymax), _p(mean), _p(invstd), _p(ab), _p(z), _p(ysel), _p(idx),
-                                       _p(zs), _p(zm), _p(zb), _p(zb8), fmt, _stream()), "bn_pool_fwd")
+                                       _p(zs), _p(zm), _p(zb), _p(zb8), fmt, 1 if stats is not None else 0,
+                                       _stream()), "bn_pool_fwd")
     _lib.count(3)
     return (z, zs, zm, zb, zb8), (yc, ysel, idx, mean, invstd, gamma.detach(), ymax), (n, h, w, c, k, stride, pad, ho, wo)
 
@@ -754,8 +767,8 @@ def stem_conv_supported(x, weight, stride, padding):
     return bool(_lib.lib().bdbnn_stem_supported(x.shape[0], x.shape[2], x.shape[3]))
 
 
-def _stem_conv_fwd_impl(x, weight):
-    """stem_pack -> stem_conv_fwd. Returns (y fp32 channels_last, xw, x_amax)."""
+def _stem_conv_fwd_impl(x, weight, want_stats=False):
+    """stem_pack -> stem_conv_fwd. Returns (y fp32 channels_last, xw, x_amax[, (sums, ymax) BN statistics of y])."""
     L = _lib.lib()
     dev = x.device
     n, _, h, w = x.shape
@@ -774,9 +787,16 @@ def _stem_conv_fwd_impl(x, weight):
         _lib.check(L.bdbnn_stem_pack(_p(xd), n, h, w, xd.stride(0), xd.stride(1), xd.stride(2), xd.stride(3),
                                      _p(wd), _p(xw), _p(x_amax), _p(wf), _p(alpha), st), "stem_pack")
     y = torch.empty((n, 64, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+    stats = None
+    if want_stats and conv_stats_enabled():
+        stats = (torch.empty((128,), dtype=torch.float64, device=dev), torch.empty((64,), dtype=torch.int32, device=dev))
     with _timed("stem_conv_fwd", key, xw.numel() * 2 + 4 * y.numel()):
-        _lib.check(L.bdbnn_stem_conv_fwd(_p(xw), _p(wf), _p(alpha), _p(y), n, h, w, st), "stem_conv_fwd")
+        _lib.check(L.bdbnn_stem_conv_fwd(_p(xw), _p(wf), _p(alpha), _p(y), n, h, w,
+                                         _p(stats[0]) if stats else None, _p(stats[1]) if stats else None, st),
+                   "stem_conv_fwd")
     _lib.count(5)
+    if want_stats:
+        return y, xw, x_amax, stats
     return y, xw, x_amax
 
 
@@ -831,9 +851,9 @@ class _StemFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad):
         ctx.set_materialize_grads(False)
-        y, xw, x_amax = _stem_conv_fwd_impl(x, weight)
+        y, xw, x_amax, stats = _stem_conv_fwd_impl(x, weight, want_stats=True)
         outs, saved, ctx.geom = _bn_pool_fwd_impl(y, gamma, beta, running_mean, running_var, momentum, eps, k,
-                                                  stride, pad)
+                                                  stride, pad, stats)
         ctx.xgeom = (x.shape[0], x.shape[2], x.shape[3])
         ctx.save_for_backward(xw, x_amax, *saved)
         nd = [t for t in outs[1:] if t is not None]

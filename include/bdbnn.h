@@ -110,14 +110,19 @@ BDBNN_API int bdbnn_binconv_fwd_xnor(const uint32_t* sign_bits, const uint32_t* 
                            const float* alpha, float* y, const bdbnn_conv_shape* s, void* stream);
 
 /* ---- binary conv forward, tcgen05 implicit GEMM on +-1 bf16 operands (exact, fp32 accumulate) --
- * Same result as bdbnn_binconv_fwd_xnor.  Requires bdbnn_tc_supported(s). */
+ * Same result as bdbnn_binconv_fwd_xnor.  Requires bdbnn_tc_supported(s).
+ * bn_sums / bn_ymax (both or neither; also on fwd_tc8 and stem_conv_fwd): if non-NULL the kernel's
+ * epilogue also accumulates the BatchNorm batch statistics of y — bn_sums = double[2*Cout] (sum y, then
+ * sum y^2 per channel), bn_ymax = u32[Cout] (bits of max|y|) — so that bdbnn_bn_fwd / bdbnn_bn_pool_fwd can
+ * be called with stats_ready = 1 and skip their own pass over y.  The buffers are zeroed here. */
 BDBNN_API int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, int32_t fmt,
-                         const float* alpha, float* y, const bdbnn_conv_shape* s, void* stream);
+                         const float* alpha, float* y, const bdbnn_conv_shape* s, double* bn_sums,
+                         uint32_t* bn_ymax, void* stream);
 
 /* Same forward on fp8 (e4m3) +-1 operands: half the operand bytes and twice the K per MMA of the
  * 16-bit kernel; still exact.  Requires bdbnn_tc_supported(s) & BDBNN_TC_FWD8. */
 BDBNN_API int bdbnn_binconv_fwd_tc8(const uint8_t* xb_fp8, const uint8_t* wf_fp8, const float* alpha, float* y,
-                          const bdbnn_conv_shape* s, void* stream);
+                          const bdbnn_conv_shape* s, double* bn_sums, uint32_t* bn_ymax, void* stream);
 
 /* ---- backward: data gradient -------------------------------------------------------------------
  * gx[n,h,w,c] = mask(n,h,w,c) * sum_{t,o} gy[n,ho,wo,o] * alpha[o] * sign(W[o,c,t])
@@ -215,7 +220,7 @@ BDBNN_API int bdbnn_bn_fwd(const float* y, const float* residual, const float* g
                  int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
                  float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean, float* invstd,
                  float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits, uint16_t* xb,
-                 uint8_t* xb_fp8, int32_t fmt, void* stream);
+                 uint8_t* xb_fp8, int32_t fmt, int32_t stats_ready, void* stream);
 BDBNN_API int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* mean, const float* invstd,
                       const float* gamma, const float* gscale, const uint32_t* ymax_bits, int64_t n_pix,
                       int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits, float* consts_ws,
@@ -236,7 +241,7 @@ BDBNN_API int bdbnn_bn_pool_fwd(const float* y, const float* gamma, const float*
                       float momentum, float* running_mean, float* running_var, double* sums_ws,
                       uint32_t* ymax_bits, float* mean, float* invstd, float* ab_ws, float* z, float* y_sel,
                       uint8_t* idx, uint32_t* sign_bits, uint32_t* mask_bits, uint16_t* xb, uint8_t* xb_fp8,
-                      int32_t fmt, void* stream);
+                      int32_t fmt, int32_t stats_ready, void* stream);
 BDBNN_API int bdbnn_bn_pool_bwd(const float* g_pool, const uint8_t* idx, const float* y, const float* y_sel,
                       const float* mean, const float* invstd, const float* gamma, const float* ones,
                       const uint32_t* ymax_bits, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
@@ -273,7 +278,7 @@ BDBNN_API int bdbnn_stem_pack(const float* x, int32_t N, int32_t H, int32_t W, i
                     int64_t sW, const float* weight, uint16_t* xw, uint32_t* x_amax_bits, uint16_t* wf,
                     float* alpha, void* stream);
 BDBNN_API int bdbnn_stem_conv_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, float* y, int32_t N,
-                        int32_t H, int32_t W, void* stream);
+                        int32_t H, int32_t W, double* bn_sums, uint32_t* bn_ymax, void* stream);
 BDBNN_API int bdbnn_stem_conv_wgrad(const uint16_t* gys, const uint32_t* g_amax_bits, const uint16_t* xw,
                           const uint32_t* x_amax_bits, float* gW, int32_t N, int32_t H, int32_t W,
                           void* workspace, size_t workspace_bytes, void* stream);

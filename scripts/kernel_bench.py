@@ -88,8 +88,8 @@ def main():
             nb = int(L.bdbnn_wgrad_tc_workspace_bytes(shp))
             wsb = torch.empty(max(nb, 4) // 4, device="cuda")
             kernels.update({
-                "fwd_tc8": lambda: (ck(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), shp, st), "f8") if caps & 8 else None),
-                "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), FMT, _p(alpha), _p(y), shp, st), "f"),
+                "fwd_tc8": lambda: (ck(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), shp, None, None, st), "f8") if caps & 8 else None),
+                "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), FMT, _p(alpha), _p(y), shp, None, None, st), "f"),
                 "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, GC, _p(amax), _p(gys), st), "g"),
                 "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), GC, _p(amax), _p(wt), _p(mb), _p(None), _p(gx), shp, st), "d"),
             })

@@ -30,11 +30,11 @@ wf8 = torch.empty((cout, 9, cin), dtype=torch.uint8, device="cuda"); xb8 = torch
 L.bdbnn_weight_pack(_p(w), cout, cin, 3, 3, _p(alpha), _p(ws), _p(wm), _p(wf), _p(wt), _p(wf8), _p(gs), _p(igs), 1, st)
 L.bdbnn_bits_to_fp8(_p(sb), n * hw * hw, cin, _p(xb8), st)
 if which == "fwd8":
-    run = lambda: L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), shp, st)
+    run = lambda: L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), shp, None, None, st)
 elif which == "wgrad":
     run = lambda: L.bdbnn_binconv_wgrad_tc(_p(gys), 2, _p(None), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st)
 else:
-  run = (lambda: L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), 1, _p(alpha), _p(y), shp, st)) if which == "fwd" else \
+  run = (lambda: L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), 1, _p(alpha), _p(y), shp, None, None, st)) if which == "fwd" else \
       (lambda: L.bdbnn_binconv_dgrad_tc(_p(gys), 2, _p(None), _p(wt), _p(mb), _p(None), _p(gx), shp, st))
 run(); torch.cuda.synchronize()
 tr = torch.zeros(3 * 2048, dtype=torch.int64, device="cuda")
