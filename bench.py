@@ -87,6 +87,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None          # host-time window of the timed region (mark_begin / mark_end)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -100,7 +107,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -113,7 +120,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # the sampler is started before the warm-up (process start-up must not land in the timed region);
+        # only samples taken inside the timed window count (all of them if the window saw fewer than 2)
+        inside = [ln for ts, ln in self.lines if self.t0 is None or (self.t0 <= ts <= (self.t1 or ts) + 0.2)]
+        if len(inside) < 2:
+            inside = [ln for _, ln in self.lines][-3:]
+        for ln in inside:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -310,24 +322,26 @@ def main():
     if args.profile_mode:
         args.no_e2e = args.no_cpu_baseline = True
     n_warm = 2 if args.profile_mode else max(3, args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(n_warm):
         step(x_dev, y_dev)
     if args.profile_mode:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()          # ncu --profile-from-start off: only the timed step(s)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     KernelTimer.start()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step(x_dev, y_dev)
     e1.record()
     barrier()
+    sampler.mark_end()
     if args.profile_mode:
         torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
