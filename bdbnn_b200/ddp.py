@@ -21,7 +21,7 @@ class GradAllReduce:
     NCCL transfer of the big late-layer buckets runs under the backward of the early layers.  `__call__`
     (after backward) issues whatever is left, waits, and applies 1/world."""
 
-    def __init__(self, model, process_group=None, broadcast_params=True, n_buckets=4, overlap=True):
+    def __init__(self, model, process_group=None, broadcast_params=True, n_buckets=4, overlap=True, scale=True):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -29,6 +29,7 @@ class GradAllReduce:
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.overlap = bool(overlap) and self.world > 1
+        self.scale = bool(scale)      # False: the optimizer applies 1/world (optim.FusedAdam/FusedSGD grad_scale)
         order = list(reversed(self.params))
         target = max(1, (total + n_buckets - 1) // max(1, n_buckets))
         self.buckets = []                      # [start, end, n_params]
@@ -79,7 +80,8 @@ class GradAllReduce:
                     self._launch(b)
             for w in self._works:
                 w.wait()
-            self.flat.mul_(1.0 / self.world)
+            if self.scale:
+                self.flat.mul_(1.0 / self.world)
             self._pending = [b[2] for b in self.buckets]
             self._works = [None] * len(self.buckets)
 

@@ -387,6 +387,54 @@ def kd_logits_loss(stud_logits, teacher_logits):
     return _KDLogits.apply(stud_logits, teacher_logits)
 
 
+class _CrossEntropyTopK(torch.autograd.Function):
+    """nn.CrossEntropyLoss()(logits, target) + accuracy(topk) + running meters (csrc/step_ops.cu):
+    loss, its gradient and the two accuracies in two launches, nothing read back."""
+
+    @staticmethod
+    def forward(ctx, logits, target, k1, k2, meters):
+        _require_cuda(logits, "cross_entropy_topk(logits)")
+        if not target.is_cuda:
+            raise RuntimeError("bdbnn_b200.cross_entropy_topk(target): expected a CUDA tensor")
+        if logits.dim() != 2 or target.dim() != 1 or target.shape[0] != logits.shape[0]:
+            raise RuntimeError(f"cross_entropy_topk: expected [N,C] logits and [N] targets, got "
+                               f"{tuple(logits.shape)} {tuple(target.shape)}")
+        if target.dtype != torch.int64:
+            raise RuntimeError("cross_entropy_topk: targets must be int64 class indices")
+        L = _lib.lib()
+        z = logits.detach().contiguous()
+        t = target.contiguous()
+        n, c = z.shape
+        dev = z.device
+        row_loss = torch.empty((n,), dtype=torch.float32, device=dev)
+        row_rank = torch.empty((n,), dtype=torch.int32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        acc = torch.empty((2,), dtype=torch.float32, device=dev)
+        grad = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        _lib.check(L.bdbnn_ce_topk_fwd_bwd(_p(z), _p(t), n, c, int(k1), int(k2), _p(row_loss), _p(row_rank), _p(loss),
+                                           _p(acc), _p(grad), _p(meters), _stream()), "ce_topk_fwd_bwd")
+        _lib.count(2)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(acc)
+        return loss, acc
+
+    @staticmethod
+    def backward(ctx, gout, _gacc):
+        (grad,) = ctx.saved_tensors
+        return (grad * gout if grad is not None else None), None, None, None, None
+
+
+def cross_entropy_topk(logits, target, topk=(1, 5), meters=None):
+    """(loss, [acc_k1, acc_k2]) — mean cross-entropy (differentiable) and top-k accuracies in percent as
+    1-element tensors (utils/utils.py:72-85).  `meters`: optional float64 CUDA tensor [4] accumulating
+    {loss*N, acc_k1*N, acc_k2*N, N} on the device (train.py:520-524 without `.item()`)."""
+    if meters is not None and (meters.dtype != torch.float64 or meters.numel() != 4 or not meters.is_cuda):
+        raise RuntimeError("cross_entropy_topk: meters must be a float64 CUDA tensor of 4 elements")
+    k1, k2 = topk
+    loss, acc = _CrossEntropyTopK.apply(logits, target, k1, k2, meters)
+    return loss, [acc[0:1], acc[1:2]]
+
+
 class _KDLayerMulti(torch.autograd.Function):
     """sum_l KLDivLoss(log_target=True)(Ws_l, Wt_l) (utils/KD_loss.py:52-67) in two launches."""
 

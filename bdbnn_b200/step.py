@@ -122,6 +122,12 @@ class FusedOps:
     def kd_layer(out_s, out_t, model_s, model_t, T):
         return _losses.DistributionLoss_layer()(out_s, out_t, model_s, model_t, T)
 
+    @staticmethod
+    def ce_acc(output, target, topk, meters):
+        """criterion + accuracy + meters in two launches (train.py:493,518-524; csrc/step_ops.cu)."""
+        from .functional import cross_entropy_topk
+        return cross_entropy_topk(output, target, topk, meters)
+
 
 class TrainStep:
     """One optimisation step. `grad_sync` (optional) is called between backward and optimizer.step()
@@ -131,7 +137,10 @@ class TrainStep:
                  grad_sync=None, criterion=None):
         self.model, self.optimizer, self.cfg = model, optimizer, cfg or StepConfig()
         self.teacher, self.ops, self.grad_sync = teacher, ops, grad_sync
+        # a caller-supplied criterion is honoured as is; otherwise the ops' fused CE+accuracy (if any)
+        self._ce_acc = getattr(ops, "ce_acc", None) if criterion is None else None
         self.criterion = criterion or nn.CrossEntropyLoss()
+        self.meters = None          # device float64 {loss*N, acc1*N, acc5*N, N} (fused CE path)
         self.hooked = select_hooked_weights(model, self.cfg)
         if self.cfg.teacher_student and teacher is None:
             raise ValueError("teacher_student step needs a teacher model")
@@ -141,9 +150,33 @@ class TrainStep:
             if len(self.targets) < len(self.hooked):
                 raise ValueError("fewer kurtosis targets than hooked layers")
 
+    def _ce(self, output, target):
+        """(cross-entropy, acc1, acc5) — train.py:493/614 and :518."""
+        topk = (1, min(5, output.shape[1]))
+        if self._ce_acc is not None and output.is_cuda:
+            if self.meters is None:
+                self.meters = torch.zeros(4, dtype=torch.float64, device=output.device)
+            ce, (acc1, acc5) = self._ce_acc(output, target, topk, self.meters)
+            return ce, acc1, acc5
+        acc1, acc5 = accuracy(output, target, topk=topk)
+        return self.criterion(output, target), acc1, acc5
+
+    def averages(self):
+        """Running (loss, acc1, acc5) averages since construction / reset_meters() — one host read."""
+        if self.meters is None:
+            return None
+        m = self.meters.tolist()
+        n = max(m[3], 1.0)
+        return {"loss": m[0] / n, "acc1": m[1] / n, "acc5": m[2] / n, "samples": int(m[3])}
+
+    def reset_meters(self):
+        if self.meters is not None:
+            self.meters.zero_()
+
     def __call__(self, images, target, epoch=0):
         cfg = self.cfg
         output = self.model(images)                                               # train.py:492 / 602
+        ce, acc1, acc5 = self._ce(output, target)                                 # train.py:493/614, :518
         loss_kl = loss_kl_c = 0
         if cfg.teacher_student:
             with torch.no_grad():
@@ -155,15 +188,14 @@ class TrainStep:
                 loss_kl = self.ops.kd_layer(output, output_teacher, self.model, self.teacher,
                                             cfg.temperature) * beta               # train.py:611
             loss_kl_c = self.ops.kd_logits(output, output_teacher) * alpha        # train.py:612
-            orig_loss = self.criterion(output, target) * lam_ce                   # train.py:614
+            orig_loss = ce * lam_ce                                               # train.py:614
         else:
-            orig_loss = self.criterion(output, target)                            # train.py:493
+            orig_loss = ce                                                        # train.py:493
         kurt_reg = 0
         if cfg.w_kurtosis and cfg.kurtepoch <= epoch and self.hooked:             # train.py:498-513
             kurt_reg = self.ops.kurtosis(list(self.hooked.values()), self.targets[:len(self.hooked)],
                                          cfg.kurtosis_mode, len(self.hooked), cfg.w_lambda_kurtosis)
         loss = loss_kl + loss_kl_c + orig_loss + kurt_reg                         # train.py:515 / 636
-        acc1, acc5 = accuracy(output, target, topk=(1, min(5, output.shape[1])))  # train.py:518
         self.optimizer.zero_grad()                                                # train.py:527
         loss.backward()                                                           # train.py:528
         if self.grad_sync is not None:
@@ -177,19 +209,23 @@ class TrainStep:
 def make_optimizer(model, dataset='imagenet', lr=None, momentum=0.9, weight_decay=None, fused=None):
     """train.py:319-336. CIFAR: SGD(lr .1, m .9, wd 1e-4). ImageNet: Adam, weight decay only on
     4-D / 'conv' parameters (train.py:323-330)."""
-    if dataset in ('cifar10', 'cifar100'):
-        return torch.optim.SGD(model.parameters(), lr if lr is not None else 0.1, momentum=momentum,
-                               weight_decay=1e-4 if weight_decay is None else weight_decay)
     all_parameters = list(model.parameters())
+    on_cuda = all(p.is_cuda for p in all_parameters)
+    own = on_cuda and fused in (None, True)           # fused="torch": torch's fused kernels; False: plain torch
+    if dataset in ('cifar10', 'cifar100'):
+        kw = dict(lr=lr if lr is not None else 0.1, momentum=momentum,
+                  weight_decay=1e-4 if weight_decay is None else weight_decay)
+        if own:
+            from .optim import FusedSGD
+            return FusedSGD(all_parameters, **kw)
+        return torch.optim.SGD(all_parameters, **kw)
     weight_parameters = [p for n, p in model.named_parameters() if p.ndimension() == 4 or 'conv' in n]
     ids = {id(p) for p in weight_parameters}
     other_parameters = [p for p in all_parameters if id(p) not in ids]
-    kw = {}
-    if fused is None:
-        fused = all(p.is_cuda for p in all_parameters)
-    if fused:
-        kw["fused"] = True
-    return torch.optim.Adam(
-        [{'params': other_parameters},
-         {'params': weight_parameters, 'weight_decay': 1e-4 if weight_decay is None else weight_decay}],
-        lr=lr if lr is not None else 1e-3, **kw)
+    groups = [{'params': other_parameters},
+              {'params': weight_parameters, 'weight_decay': 1e-4 if weight_decay is None else weight_decay}]
+    if own:
+        from .optim import FusedAdam
+        return FusedAdam(groups, lr=lr if lr is not None else 1e-3)
+    kw = {"fused": True} if (fused == "torch" and on_cuda) else {}
+    return torch.optim.Adam(groups, lr=lr if lr is not None else 1e-3, **kw)

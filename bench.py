@@ -16,6 +16,7 @@ events on the launching stream inside the timed region; `cpu_baseline` = the CPU
 this box's host cores on a bounded sample.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -296,7 +297,10 @@ def main():
     opt = make_optimizer(model, dataset)
     reducer = None
     if world > 1:
-        reducer = GradAllReduce(model)
+        fold = hasattr(opt, "grad_scale")       # FusedAdam / FusedSGD apply 1/world inside the update kernel
+        if fold:
+            opt.grad_scale = 1.0 / world
+        reducer = GradAllReduce(model, scale=not fold)
         opt = FlatGradOptimizerShim(opt, reducer)
     step = TrainStep(model, opt, cfg, teacher=teacher, grad_sync=reducer)
 
@@ -335,6 +339,8 @@ def main():
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    gc.collect()
+    gc.disable()                 # a generation-2 collection inside the loop stalls the launch thread for tens of ms
     sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
@@ -342,6 +348,7 @@ def main():
     e1.record()
     barrier()
     sampler.mark_end()
+    gc.enable()
     if args.profile_mode:
         torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -384,10 +391,13 @@ def main():
 
         e2e_loop(2)
         barrier()
+        gc.collect()
+        gc.disable()
         e0.record()
         e2e_loop(args.steps)
         e1.record()
         barrier()
+        gc.enable()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         e2e = {"value": round(batch * world * args.steps / (ms_e2e / 1e3), 2), "unit": "images/sec",
                "ms_per_step": round(ms_e2e / args.steps, 3),

@@ -283,6 +283,34 @@ BDBNN_API int bdbnn_stem_conv_wgrad(const uint16_t* gys, const uint32_t* g_amax_
                           const uint32_t* x_amax_bits, float* gW, int32_t N, int32_t H, int32_t W,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- step pieces either side of the path -----------------------------
+ * ce_topk_fwd_bwd : nn.CrossEntropyLoss()(logits, target) (train.py:493, 614), its gradient
+ *                   (softmax - onehot)/N (written when grad_logits != NULL), accuracy(output, target,
+ *                   topk=(k1, k2)) in percent (train.py:518, utils/utils.py:72-85) and, when `meters` is
+ *                   non-NULL, the running AverageMeter sums {loss*N, acc_k1*N, acc_k2*N, N} as device
+ *                   doubles (train.py:520-524 without the .item() syncs).  Two launches, nothing read
+ *                   back.  logits fp32 [N,C] row-major, target int64 [N]; scratch row_loss_ws float[N],
+ *                   row_rank_ws int32[N]; loss_out float[1], acc_out float[2].
+ * optim_adam_multi: torch.optim.Adam step (train.py:331-335: betas, eps, L2 weight decay only on the
+ *                   conv-weight group) for `count` tensors in one launch per 48 tensors; p/g/m/v share
+ *                   one dense layout per tensor; `step` is the 1-based step count for the bias
+ *                   corrections; every gradient is multiplied by grad_scale first (1/world after the
+ *                   data-parallel all-reduce SUM).  Pointer / size / hyper-parameter tables are HOST arrays.
+ * optim_sgd_multi : torch.optim.SGD step with momentum (train.py:319-321; dampening 0, no nesterov);
+ *                   first_step != 0 initialises the momentum buffers with the gradient. */
+BDBNN_API int bdbnn_ce_topk_fwd_bwd(const float* logits, const int64_t* target, int32_t N, int32_t C, int32_t k1,
+                          int32_t k2, float* row_loss_ws, int32_t* row_rank_ws, float* loss_out,
+                          float* acc_out, float* grad_logits, double* meters, void* stream);
+BDBNN_API int bdbnn_optim_adam_multi(float* const* params_host, const float* const* grads_host,
+                           float* const* exp_avg_host, float* const* exp_avg_sq_host,
+                           const int64_t* numel_host, const float* weight_decay_host, const float* lr_host,
+                           int32_t count, float beta1, float beta2, float eps, int64_t step,
+                           float grad_scale, void* stream);
+BDBNN_API int bdbnn_optim_sgd_multi(float* const* params_host, const float* const* grads_host,
+                          float* const* momentum_buf_host, const int64_t* numel_host,
+                          const float* weight_decay_host, const float* lr_host, int32_t count, float momentum,
+                          int32_t first_step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,3 +170,19 @@ def test_ede_attributes_and_activation_rule():
     assert c.ede_active and not h.ede_active
     assert c.k is k and c.t is t and net[2].k is k
     assert "k" not in c.state_dict() and "_ede_k" not in c.state_dict()
+
+
+def test_make_optimizer_cpu_is_plain_torch_and_fused_rejects_cpu():
+    """No CPU path in the product optimizers: CPU models get torch's, FusedAdam on CPU tensors raises."""
+    import torch.nn as nn
+    from bdbnn_b200.optim import FusedAdam
+    from bdbnn_b200.step import make_optimizer
+    m = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4))
+    assert type(make_optimizer(m, "imagenet")).__module__.startswith("torch.optim")
+    assert type(make_optimizer(m, "cifar10")).__module__.startswith("torch.optim")
+    o = make_optimizer(m, "imagenet")
+    assert [g.get("weight_decay", 0) for g in o.param_groups] == [0, 1e-4]       # train.py:331-334
+    p = torch.zeros(3, requires_grad=True)
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FusedAdam([p]).step()
