@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256)
 weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32_t T, int32_t Cw,
                    float* __restrict__ alpha, uint32_t* __restrict__ wsign,
                    uint16_t* __restrict__ wf, uint16_t* __restrict__ wt, uint8_t* __restrict__ wf8,
-                   float* __restrict__ gscale, float* __restrict__ inv_gscale, uint16_t one16) {
+                   float* __restrict__ gscale, float* __restrict__ inv_gscale, uint16_t one16,
+                   uint32_t* __restrict__ wmask_inline, int wt_inline) {
   const int o = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int per = Cin * T;
@@ -108,7 +109,43 @@ weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32
       const uint16_t sg = (v >= 0.0f) ? one16 : uint16_t(one16 | 0x8000u);
       if (wf) wf[(int64_t(o) * T + t) * Cin + c] = sg;
       if (wf8) wf8[(int64_t(o) * T + t) * Cin + c] = (v >= 0.0f) ? uint8_t(0x38) : uint8_t(0xB8);  // e4m3 +-1
-      if (wt) wt[(int64_t(c) * T + (T - 1 - t)) * Cout + o] = live ? sg : uint16_t(0);
+      if (wt && wt_inline) wt[(int64_t(c) * T + (T - 1 - t)) * Cout + o] = live ? sg : uint16_t(0);
+    }
+  }
+  // |W| <= 1 bits of this filter's slice of the flat OIHW mask (when the slice is word-aligned)
+  if (wmask_inline != nullptr) {
+    uint32_t* mo = wmask_inline + (int64_t(o) * per >> 5);
+    for (int w = warp; w < (per >> 5); w += nwarps) {
+      const uint32_t mb = __ballot_sync(0xffffffffu, fabsf(Wo[w * 32 + lane]) <= 1.0f);
+      if (lane == 0) mo[w] = mb;
+    }
+  }
+}
+
+// dgrad operand wt[c][T-1-t][o] = alpha[o] > 0 ? sign(W[o][c][t]) : 0 as a 32x32 tile transpose: reads run along
+// (c,t) for one filter, writes run along o (the per-filter kernel's scattered 2-byte stores cost 50 us at
+// 512x512x9).  grid = (ceil(per/32), ceil(Cout/32)), block = (32, 8).
+__global__ void __launch_bounds__(256)
+weight_wt_kernel(const float* __restrict__ W, const float* __restrict__ alpha, int32_t Cout, int32_t Cin, int32_t T,
+                 uint16_t* __restrict__ wt, uint16_t one16) {
+  __shared__ uint16_t tile[32][33];
+  const int per = Cin * T;
+  const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int o = o0 + r, i = i0 + threadIdx.x;
+    uint16_t sg = 0;
+    if (o < Cout && i < per) {
+      const float v = W[int64_t(o) * per + i];
+      sg = __ldg(alpha + o) > 0.f ? ((v >= 0.0f) ? one16 : uint16_t(one16 | 0x8000u)) : uint16_t(0);
+    }
+    tile[r][threadIdx.x] = sg;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, o = o0 + threadIdx.x;
+    if (i < per && o < Cout) {
+      const int c = i / T, t = i - c * T;
+      wt[(int64_t(c) * T + (T - 1 - t)) * Cout + o] = tile[threadIdx.x][r];
     }
   }
 }
@@ -275,11 +312,22 @@ extern "C" int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int3
   BDBNN_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "weight_pack: bad dims");
   BDBNN_REQUIRE(W && alpha && wsign_bits && wmask_bits, "weight_pack: NULL pointer");
   const int32_t T = kh * kw, Cw = (Cin + 31) / 32;
+  const int per = Cin * T;
+  const bool mask_inline = (per & 31) == 0;          // each filter's mask slice is whole words
+  const bool wt_tiled = wt_bf16 != nullptr && int64_t(Cout) * per >= 32768;   // small layers: one launch less
   weight_pack_kernel<<<Cout, 256, 0, cudaStream_t(stream)>>>(W, Cout, Cin, T, Cw, alpha, wsign_bits,
                                                             wf_bf16, wt_bf16, wf_fp8, gscale, inv_gscale,
-                                                            one_bits(fmt));
+                                                            one_bits(fmt), mask_inline ? wmask_bits : nullptr,
+                                                            wt_tiled ? 0 : 1);
   int rc = check_launch("weight_pack_kernel");
   if (rc) return rc;
+  if (wt_tiled) {
+    dim3 grid(unsigned((per + 31) / 32), unsigned((Cout + 31) / 32));
+    weight_wt_kernel<<<grid, dim3(32, 8), 0, cudaStream_t(stream)>>>(W, alpha, Cout, Cin, T, wt_bf16, one_bits(fmt));
+    rc = check_launch("weight_wt_kernel");
+    if (rc) return rc;
+  }
+  if (mask_inline) return BDBNN_OK;
   const int64_t n = int64_t(Cout) * Cin * T;
   const int64_t n_words = (n + 31) / 32;
   int64_t blocks = (n_words * 32 + 255) / 256;
