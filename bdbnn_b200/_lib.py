@@ -37,6 +37,7 @@ SIGNATURES = {
     "bdbnn_optim_adam_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_float, c_int64, ctypes.c_float, _P]),
     "bdbnn_optim_sgd_multi": (c_int, [_P, _P, _P, _P, _P, _P, c_int, ctypes.c_float, c_int, ctypes.c_float, _P]),
+    "bdbnn_real_conv_pack": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int] + [_P] * 8),
     "bdbnn_stem_supported": (c_int, [c_int, c_int, c_int]),
     "bdbnn_stem_xw_bytes": (c_size_t, [c_int, c_int, c_int]),
     "bdbnn_stem_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -212,7 +212,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 16; ++j) f[j] = ((word >> j) & 1u) ? __uint_as_float(v[j]) * post : 0.0f;
           if (p.add != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.add + pix * p.Nout + nn0 + c0 + j);
+            for (int j = 0; j < 16; ++j) f[j] += p.add[pix * p.Nout + nn0 + c0 + j];   // plain load: add may alias out
           }
         }
 #pragma unroll
@@ -482,8 +482,9 @@ extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mod
     }
   if (empty_phase) {
     const size_t bytes = size_t(s->N) * s->H * s->W * s->Cin * sizeof(float);
-    if (add != nullptr) BDBNN_CUDA(cudaMemcpyAsync(gx, add, bytes, cudaMemcpyDeviceToDevice, st));
-    else BDBNN_CUDA(cudaMemsetAsync(gx, 0, bytes, st));
+    // add == gx: accumulate in place (positions no phase writes keep their value, nothing to initialise)
+    if (add != nullptr && add != gx) BDBNN_CUDA(cudaMemcpyAsync(gx, add, bytes, cudaMemcpyDeviceToDevice, st));
+    else if (add == nullptr) BDBNN_CUDA(cudaMemsetAsync(gx, 0, bytes, st));
   }
   for (int i = 0; i < n_launch; ++i) {
     rc = launch_tc_conv<1>(Ls[i], st);

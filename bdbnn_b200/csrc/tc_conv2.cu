@@ -379,7 +379,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (MODE == 1 && p.add != nullptr) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              addv[i] = offs[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.add + offs[i] + c0 + cq * 4))
+              addv[i] = offs[i] >= 0 ? *reinterpret_cast<const float4*>(p.add + offs[i] + c0 + cq * 4)   // may alias out
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll

@@ -547,8 +547,17 @@ class _ConvBNAddUnit(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride,
-                padding, xs, xm, xb, xb8, res_is_x):
+                padding, xs, xm, xb, xb8, res_is_x, sc_weight=None, sc_gamma=None, sc_beta=None, sc_rm=None,
+                sc_rv=None, sc_momentum=None, sc_eps=None, sc_stride=None):
         _require_cuda(x, "conv_bn_add(x)")
+        # optional real-valued 1x1 shortcut branch evaluated inside this node: its output is the residual,
+        # and its input gradient is added in place to this conv's (see backward)
+        ctx.n_sc = 0
+        sc_saved = ()
+        if sc_weight is not None:
+            residual, sc_saved, ctx.sc_geom = _shortcut_fwd_impl(x, sc_weight, sc_gamma, sc_beta, sc_rm, sc_rv,
+                                                                sc_momentum, sc_eps, sc_stride)
+            ctx.n_sc = len(sc_saved)
         ctx.set_materialize_grads(False)     # no zero tensors for the (integer) pack outputs in backward
         L = _lib.lib()
         sh = conv_shape(x.shape, weight.shape, stride, padding)
@@ -625,9 +634,9 @@ class _ConvBNAddUnit(torch.autograd.Function):
         _lib.count(3)
         ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
         ctx.shapes = (tuple(x.shape), tuple(weight.shape))
-        ctx.has_res = residual is not None
+        ctx.has_res = residual is not None and sc_weight is None
         ctx.res_is_x = bool(res_is_x)
-        ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale)
+        ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale, *sc_saved)
         if pack:
             if zb8 is not None:
                 ctx.mark_non_differentiable(zs, zm, zb, zb8)
@@ -639,12 +648,12 @@ class _ConvBNAddUnit(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gz, _g1, _g2, _g3, _g4):
         if gz is None:
-            return (None,) * 16
+            return (None,) * 24
         L = _lib.lib()
         sh = ctx.sh
         st = _stream()
         dev = gz.device
-        y, mean, invstd, gamma, ymax, xm, xb, wt, wmask, gscale, inv_gscale = ctx.saved_tensors
+        y, mean, invstd, gamma, ymax, xm, xb, wt, wmask, gscale, inv_gscale = ctx.saved_tensors[:11]
         gname, gcode, gh = ctx.gmode
         key = _shape_key(sh)
         g = _nhwc(gz)
@@ -682,12 +691,24 @@ class _ConvBNAddUnit(torch.autograd.Function):
                                                     ctypes.byref(sh), _p(ws), nbytes, st), "binconv_wgrad_tc")
             _lib.count(2)
         gres = gz if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        sc_gw = sc_dg = sc_db = None
+        if ctx.n_sc:
+            # shortcut branch: residual gradient = gz; its dgrad accumulates into gx in place
+            sgx, sc_gw, sc_dg, sc_db = _shortcut_bwd_impl(gz, ctx.saved_tensors[11:], ctx.sc_geom,
+                                                          ctx.needs_input_grad[0], ctx.needs_input_grad[16], acc=gx)
+            gx = sgx if sgx is not None else gx
+            sc_dg = sc_dg if ctx.needs_input_grad[17] else None
+            sc_db = sc_db if ctx.needs_input_grad[18] else None
         return (gx, gw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
-                gres, None, None, None, None, None, None, None, None, None, None, None)
+                gres, None, None, None, None, None, None, None, None, None, None, None,
+                sc_gw, sc_dg, sc_db, None, None, None, None, None)
 
 
-def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride, padding):
-    """z = BN_train(binconv2d(x, weight)) + residual on the fused kernels.  The returned tensor carries
+def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride, padding,
+                shortcut=None):
+    """z = BN_train(binconv2d(x, weight)) + residual on the fused kernels.  `shortcut` = (weight[Cout,Cin,1,1],
+    gamma, beta, running_mean, running_var, momentum, eps, stride) evaluates the real-valued 1x1 conv + BN
+    `downsample` branch of x inside the same node and uses it as the residual.  The returned tensor carries
     `_bdbnn_pack` = (sign bits, mask bits, +-1 copy, fmt) of z so that a following conv_bn_add skips its
     own activation pack; x's own `_bdbnn_pack` (if present and of the current format) is consumed."""
     fmt = grad_mode()[3]
@@ -697,12 +718,148 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
         xs, xm, xb = pk[:3]
         xb8 = pk[4] if len(pk) > 4 else None
     res_is_x = residual is x and x.shape[1] == weight.shape[0] and int(stride) == 1
-    z, zs, zm, zb, zb8 = _ConvBNAddUnit.apply(x, weight, gamma, beta, None if res_is_x else residual, running_mean,
-                                              running_var, momentum, eps, int(stride), int(padding), xs, xm, xb, xb8,
-                                              res_is_x)
+    if shortcut is not None:
+        if residual is not None:
+            raise RuntimeError("conv_bn_add: pass either residual or shortcut")
+        z, zs, zm, zb, zb8 = _ConvBNAddUnit.apply(x, weight, gamma, beta, None, running_mean, running_var, momentum,
+                                                  eps, int(stride), int(padding), xs, xm, xb, xb8, False, *shortcut)
+    else:
+        z, zs, zm, zb, zb8 = _ConvBNAddUnit.apply(x, weight, gamma, beta, None if res_is_x else residual,
+                                                  running_mean, running_var, momentum, eps, int(stride),
+                                                  int(padding), xs, xm, xb, xb8, res_is_x)
     if zs is not None:
         z._bdbnn_pack = (zs, zm, zb, fmt, zb8)
     return z
+
+
+def shortcut_tc_enabled():
+    return os.environ.get("BDBNN_SHORTCUT_TC", "1") != "0"
+
+
+def shortcut_supported(x, weight, stride):
+    """fp32 1x1 shortcut conv + BN on the tcgen05 kernels: CUDA fp32 NHWC-able x, [Cout,Cin,1,1] weight,
+    fp16s gradient mode (the operands are fp16), and all three kernels available for the 1x1 geometry."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and weight.dim() == 4):
+        return False
+    cout, cin, kh, kw = weight.shape
+    if (kh, kw) != (1, 1) or cin != x.shape[1] or grad_mode()[0] != "fp16s":
+        return False
+    n, _, h, w = x.shape
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    caps1 = int(_lib.lib().bdbnn_tc_supported(ctypes.byref(conv_shape((n, cin, ho, wo), weight.shape, 1, 0))))
+    capss = int(_lib.lib().bdbnn_tc_supported(ctypes.byref(conv_shape(x.shape, weight.shape, stride, 0))))
+    return (caps1 & 5) == 5 and bool(capss & 2) and cout % 4 == 0 and cout <= 512
+
+
+def _shortcut_fwd_impl(x, weight, gamma, beta, running_mean, running_var, momentum, eps, stride):
+    """real_conv_pack -> fwd_tc (1x1 over the packed samples, BN statistics in its epilogue) -> bn_fwd.
+    Returns (z, saved tensors, geometry)."""
+    L = _lib.lib()
+    dev = x.device
+    st = _stream()
+    n, cin, h, w = x.shape
+    cout = weight.shape[0]
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    sh1 = conv_shape((n, cin, ho, wo), weight.shape, 1, 0)        # the GEMM: 1x1 / stride 1 over the samples
+    shs = conv_shape(x.shape, weight.shape, stride, 0)            # the dgrad scatter geometry
+    key = _shape_key(shs)
+    xc = _nhwc(x.detach())
+    wd = weight.detach().contiguous()
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    xh = torch.empty((n, ho, wo, cin), dtype=torch.int16, device=dev)
+    amax2 = torch.empty((2,), **i32)
+    wf = torch.empty((cout, cin), dtype=torch.int16, device=dev)
+    wt = torch.empty((cin, cout), dtype=torch.int16, device=dev)
+    alpha, gscale, inv_gscale = torch.empty((cout,), **f32), torch.empty((cout,), **f32), torch.empty((cout,), **f32)
+    with _timed("shortcut_pack", key, 4 * n * ho * wo * cin * 2 + 2 * n * ho * wo * cin):
+        _lib.check(L.bdbnn_real_conv_pack(_p(xc), n, h, w, cin, stride, _p(wd), cout, _p(xh), _p(amax2), _p(wf),
+                                          _p(wt), _p(alpha), _p(gscale), _p(inv_gscale), st), "real_conv_pack")
+    y = torch.empty((n, cout, ho, wo), memory_format=torch.channels_last, **f32)
+    sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
+    ymax = torch.empty((cout,), **i32)
+    with _timed("shortcut_fwd_tc", key, 2 * xh.numel() + 4 * y.numel()):
+        _lib.check(L.bdbnn_binconv_fwd_tc(_p(xh), _p(wf), 0, _p(alpha), _p(y), ctypes.byref(sh1), _p(sums), _p(ymax),
+                                          st), "binconv_fwd_tc(shortcut)")
+    z = torch.empty_like(y)
+    mean, invstd, ab = torch.empty((cout,), **f32), torch.empty((cout,), **f32), torch.empty((2 * cout,), **f32)
+    n_pix = n * ho * wo
+    with _timed("shortcut_bn_fwd", key, 8 * n_pix * cout):
+        _lib.check(L.bdbnn_bn_fwd(_p(y), None, _p(gamma.detach()), _p(beta.detach()), n_pix, cout, float(eps),
+                                  float(momentum), _p(running_mean), _p(running_var), _p(sums), _p(ymax),
+                                  _p(mean), _p(invstd), _p(ab), _p(z), None, None, None, None, 0, 1, st),
+                   "bn_fwd(shortcut)")
+    _lib.count(9)
+    saved = (y, mean, invstd, gamma.detach(), ymax, xh, wt, gscale, inv_gscale)
+    return z, saved, (sh1, shs, tuple(x.shape), tuple(weight.shape))
+
+
+def _shortcut_bwd_impl(gz, saved, geom, need_x, need_w, acc=None):
+    """bn_bwd_pack -> dgrad_tc (scatter to the sampled positions) , wgrad_tc.
+    acc: an fp32 NHWC gradient of x already holding the main branch's part — the shortcut's part is added
+    in place (no zero fill, no separate add); otherwise a fresh tensor (zeros off the samples).
+    Returns (gx, gw, dgamma, dbeta)."""
+    L = _lib.lib()
+    st = _stream()
+    dev = gz.device
+    sh1, shs, x_shape, w_shape = geom
+    y, mean, invstd, gamma, ymax, xh, wt, gscale, inv_gscale = saved
+    cout, cin = w_shape[0], w_shape[1]
+    n_pix = sh1.N * sh1.Ho * sh1.Wo
+    key = _shape_key(shs)
+    g = _nhwc(gz)
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
+    gmax, amax = torch.empty((cout,), **i32), torch.empty((1,), **i32)
+    consts, dgamma, dbeta = torch.empty((4 * cout,), **f32), torch.empty((cout,), **f32), torch.empty((cout,), **f32)
+    gys = torch.empty((sh1.N, sh1.Ho, sh1.Wo, cout), dtype=torch.int16, device=dev)
+    with _timed("shortcut_bn_bwd", key, 18 * n_pix * cout):
+        _lib.check(L.bdbnn_bn_bwd_pack(_p(g), _p(y), _p(mean), _p(invstd), _p(gamma), _p(gscale), _p(ymax), n_pix,
+                                       cout, 3, _p(sums), _p(gmax), _p(consts), _p(dgamma), _p(dbeta), _p(amax),
+                                       _p(gys), st), "bn_bwd_pack(shortcut)")
+    _lib.count(3)
+    gx = gw = None
+    if need_x:
+        ones = torch.full((x_shape[0], x_shape[2], x_shape[3], (cin + 31) // 32), -1, **i32)
+        gx = acc if acc is not None else torch.empty(x_shape, memory_format=torch.channels_last, **f32)
+        with _timed("shortcut_dgrad_tc", key, 2 * gys.numel() + (4 * gx.numel() if acc is None else 8 * n_pix * cin)):
+            _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), 3, _p(amax), _p(wt), _p(ones), _p(acc), _p(gx),
+                                                ctypes.byref(shs), st), "binconv_dgrad_tc(shortcut)")
+        _lib.count(2)
+    if need_w:
+        wones = torch.full(((cout * cin + 31) // 32,), -1, **i32)
+        gw = torch.empty(w_shape, **f32)
+        nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh1)))
+        ws = torch.empty((max(nbytes, 4) // 4,), **f32)
+        with _timed("shortcut_wgrad_tc", key, 2 * gys.numel() + 2 * xh.numel()):
+            _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), 3, _p(amax), _p(xh), _p(wones), _p(inv_gscale), _p(gw),
+                                                ctypes.byref(sh1), _p(ws), nbytes, st), "binconv_wgrad_tc(shortcut)")
+        _lib.count(2)
+    return gx, gw, dgamma, dbeta
+
+
+class _RealConvBN(torch.autograd.Function):
+    """z = BN_train(conv1x1_stride_s(x, W)) for the real-valued `downsample` branch (csrc/real_conv.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, momentum, eps, stride):
+        _require_cuda(x, "shortcut_conv_bn(x)")
+        z, saved, ctx.geom = _shortcut_fwd_impl(x, weight, gamma, beta, running_mean, running_var, momentum, eps, stride)
+        ctx.save_for_backward(*saved)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        gx, gw, dgamma, dbeta = _shortcut_bwd_impl(gz, ctx.saved_tensors, ctx.geom, ctx.needs_input_grad[0],
+                                                   ctx.needs_input_grad[1])
+        return (gx, gw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
+                None, None, None, None, None)
+
+
+def shortcut_conv_bn(x, weight, gamma, beta, running_mean, running_var, momentum, eps, stride):
+    """BN_train(conv2d(x, weight[Cout,Cin,1,1], stride)) on the tcgen05 kernels (see shortcut_supported)."""
+    return _RealConvBN.apply(x, weight, gamma, beta, running_mean, running_var, momentum, eps, int(stride))
 
 
 def _bn_pool_fwd_impl(yc, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad, stats=None):

@@ -16,8 +16,9 @@ from . import functional as F_
 from .modules import BinarizeConv2d, HardBinaryConv, HardBinaryConv_cifar, MaxPool2dNHWC
 
 
-def _fused_unit(x, conv, bn, residual):
-    """BN_train(conv(x)) + residual through the fused kernels when the pair qualifies, else None."""
+def _fused_unit(x, conv, bn, residual, shortcut=None):
+    """BN_train(conv(x)) + residual through the fused kernels when the pair qualifies, else None.
+    `shortcut`: argument tuple of a qualifying `downsample` branch (see _shortcut_args) evaluated in the same node."""
     if not (x.is_cuda and bn.training and isinstance(conv, BinarizeConv2d) and isinstance(bn, nn.BatchNorm2d)):
         return None
     if not (bn.affine and bn.track_running_stats and bn.momentum is not None and F_.fuse_enabled()):
@@ -27,9 +28,25 @@ def _fused_unit(x, conv, bn, residual):
     if not F_.unit_supported(x.shape, conv.weight.shape, conv.stride[0], conv.padding[0]):
         return None
     z = F_.conv_bn_add(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.momentum,
-                       bn.eps, conv.stride[0], conv.padding[0])
+                       bn.eps, conv.stride[0], conv.padding[0], shortcut=shortcut)
     bn.num_batches_tracked.add_(1)
     return z
+
+
+def _shortcut_args(x, ds):
+    """Arguments for the tcgen05 `downsample` path — Sequential(fp32 1x1 Conv2d, BatchNorm2d) in training
+    mode on a supported geometry — or None."""
+    if not (isinstance(ds, nn.Sequential) and len(ds) == 2 and type(ds[0]) is nn.Conv2d and
+            isinstance(ds[1], nn.BatchNorm2d)):
+        return None
+    conv, bn = ds[0], ds[1]
+    if not (x.is_cuda and bn.training and bn.affine and bn.track_running_stats and bn.momentum is not None and
+            conv.bias is None and conv.kernel_size == (1, 1) and conv.padding == (0, 0) and
+            conv.stride[0] == conv.stride[1] and conv.groups == 1 and F_.fuse_enabled() and F_.shortcut_tc_enabled()):
+        return None
+    if not F_.shortcut_supported(x, conv.weight, conv.stride[0]):
+        return None
+    return (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, conv.stride[0])
 
 
 class BasicBlock(nn.Module):
@@ -44,8 +61,23 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        residual = x if self.downsample is None else self.downsample(x)
-        out = _fused_unit(x, self.conv1, self.bn1, residual)
+        out = None
+        if self.downsample is None:
+            residual = x
+        else:
+            # conv1 + bn1 + the real-valued 1x1 shortcut (conv + bn) as ONE node when everything qualifies:
+            # the shortcut's input gradient is then added in place to conv1's (no zero fill, no add kernel)
+            sc = _shortcut_args(x, self.downsample)
+            if sc is not None:
+                out = _fused_unit(x, self.conv1, self.bn1, None, shortcut=sc)
+                if out is not None:
+                    self.downsample[1].num_batches_tracked.add_(1)
+            if out is None:
+                residual = (F_.shortcut_conv_bn(x, *sc) if sc is not None else self.downsample(x))
+                if sc is not None:
+                    self.downsample[1].num_batches_tracked.add_(1)
+        if out is None:
+            out = _fused_unit(x, self.conv1, self.bn1, residual)
         if out is None:
             out = self.bn1(self.conv1(x)) + residual
         out2 = _fused_unit(out, self.conv2, self.bn2, out)

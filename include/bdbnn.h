@@ -148,7 +148,8 @@ BDBNN_API int bdbnn_binconv_wgrad(const float* gy, const uint32_t* sign_bits, co
  *            gys is shared by dgrad_tc (K-major) and wgrad_tc (MN-major).
  * dgrad_tc : gx = mask * 2^-e * conv_transpose(gys, wt) (+ add)      (sign-only weights, exact; `add`,
  *            if non-NULL, is an fp32 tensor shaped like gx — the shortcut branch's gradient — summed in
- *            the epilogue)
+ *            the epilogue; add == gx accumulates in place: with stride > 1 only the positions a tap reaches
+ *            are touched, which is how the strided 1x1 shortcut adds its gradient to the main branch's)
  * wgrad_tc : gW = wmask * inv_gscale[o] * 2^-e * sum_pix gys[pix,o]*xb[pix',c]
  * The +-1 operands (xb, wt) must be in the format matching the mode: fp16 for FP16S, bf16 otherwise.
  * wgrad_tc needs a workspace of bdbnn_wgrad_tc_workspace_bytes(s) bytes (split-K partials).
@@ -310,6 +311,18 @@ BDBNN_API int bdbnn_optim_sgd_multi(float* const* params_host, const float* cons
                           float* const* momentum_buf_host, const int64_t* numel_host,
                           const float* weight_decay_host, const float* lr_host, int32_t count, float momentum,
                           int32_t first_step, float grad_scale, void* stream);
+
+/* ---- fp32 1x1 shortcut convolution (`downsample` of the ResNet shells) on the tcgen05 kernels -----------
+ * Packing only (bdbnn_b200/csrc/real_conv.cu): xh = fp16(x[:, ::stride, ::stride, :] * 2^ex) dense NHWC
+ * [N,Ho,Wo,Cin], wf = fp16(W * 2^ew) [Cout][Cin], wt = its transpose [Cin][Cout], and the scale vectors
+ * alpha[o] = 2^-ew 2^-ex, gscale[o] = 2^-ew, inv_gscale[o] = 2^ew 2^-ex.  The convolution itself is
+ * bdbnn_binconv_fwd_tc / _dgrad_tc / _wgrad_tc run as a 1x1 stride-1 conv over xh with these vectors and
+ * all-ones STE masks (TF32-class operands, fp32 accumulate; replaces cuDNN's TF32 kernels under
+ * model(images) / loss.backward()).  x fp32 NHWC, weight fp32 [Cout][Cin] (= [Cout,Cin,1,1]);
+ * x_amax_bits: TWO words of scratch ([0] = bits of max|x| over the samples, [1] = of max|W|). */
+BDBNN_API int bdbnn_real_conv_pack(const float* x, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t stride,
+                         const float* weight, int32_t Cout, uint16_t* xh, uint32_t* x_amax_bits, uint16_t* wf,
+                         uint16_t* wt, float* alpha, float* gscale, float* inv_gscale, void* stream);
 
 #ifdef __cplusplus
 }

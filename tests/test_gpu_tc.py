@@ -364,3 +364,80 @@ def test_stem_fused_conv_bn_pool(geom):
     # and the conv itself against an fp64 conv (TF32-class operands)
     yr = nn.functional.conv2d(x.double(), wt.double(), None, 2, 3)
     assert (y.detach() - yr).abs().max().item() <= 2e-3 * yr.abs().max().item()
+
+
+@pytest.mark.parametrize("geom", [(4, 64, 128, 16, 16, 2), (2, 64, 128, 56, 56, 2), (3, 128, 256, 28, 28, 2),
+                                  (5, 256, 512, 14, 14, 2), (2, 64, 64, 9, 11, 1)])
+def test_shortcut_conv_bn_vs_fp64(geom):
+    """fp32 1x1 `downsample` conv + BN(train) on the tcgen05 kernels (fp16 operands with power-of-two scales,
+    TF32-class like the cuDNN kernels the reference runs) vs conv2d + BatchNorm2d in fp64: output, running
+    statistics and the gradients of x, W, gamma, beta."""
+    import torch.nn as nn
+    from bdbnn_b200 import functional as F_
+    n, cin, cout, h, w, stride = geom
+    g = torch.Generator().manual_seed(sum(geom))
+    x = torch.randn(n, cin, h, w, generator=g) * 1.3 + 0.2
+    wt = torch.randn(cout, cin, 1, 1, generator=g) * 0.1
+    gam, bet = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.2
+    xr, wr = x.double().requires_grad_(True), wt.double().requires_grad_(True)
+    bn = nn.BatchNorm2d(cout).double()
+    bn.weight.data, bn.bias.data = gam.double(), bet.double()
+    zr = bn(nn.functional.conv2d(xr, wr, None, stride))
+    gz = torch.randn(zr.shape, generator=g)
+    zr.backward(gz.double())
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wd = wt.cuda().requires_grad_(True)
+    gd, bd = gam.cuda().requires_grad_(True), bet.cuda().requires_grad_(True)
+    rm, rv = torch.zeros(cout).cuda(), torch.ones(cout).cuda()
+    assert F_.shortcut_supported(xd, wd, stride)
+    z = F_.shortcut_conv_bn(xd, wd, gd, bd, rm, rv, 0.1, 1e-5, stride)
+    z.backward(gz.cuda().contiguous(memory_format=torch.channels_last))
+    def close(got, ref, tol, name):
+        err = (got.detach().cpu().double() - ref).abs().max().item()
+        assert err <= tol * (ref.abs().max().item() + 1e-30), (name, err, ref.abs().max().item())
+    close(z, zr.detach(), 5e-3, "z")
+    close(rm, bn.running_mean, 2e-3, "running_mean")
+    close(rv, bn.running_var, 2e-3, "running_var")
+    close(xd.grad, xr.grad, 5e-3, "gx")
+    close(wd.grad, wr.grad, 5e-3, "gW")
+    close(gd.grad, bn.weight.grad, 5e-3, "dgamma")
+    close(bd.grad, bn.bias.grad, 1e-4, "dbeta")
+    if stride == 2:      # positions the stride skips get exactly zero gradient
+        gxc = xd.grad.cpu()
+        assert (gxc[:, :, 1::2, :] == 0).all() and (gxc[:, :, :, 1::2] == 0).all()
+
+
+@pytest.mark.parametrize("geom", [(4, 64, 128, 16, 16), (2, 64, 128, 56, 56), (3, 256, 512, 14, 14)])
+def test_unit_with_in_node_shortcut_equals_two_nodes(geom):
+    """conv1 + bn1 with the real-valued 1x1 shortcut evaluated inside the same autograd node (shortcut dgrad
+    accumulated in place into conv1's input gradient) vs the same kernels as two nodes joined by autograd."""
+    import torch.nn as nn
+    from bdbnn_b200 import HardBinaryConv
+    from bdbnn_b200 import resnet as R
+    n, cin, cout, h, w = geom
+    torch.manual_seed(sum(geom))
+    x = (torch.randn(n, cin, h, w) * 1.2).cuda().contiguous(memory_format=torch.channels_last)
+    gz = torch.randn(n, cout, h // 2, w // 2).cuda().contiguous(memory_format=torch.channels_last)
+
+    def run(one_node):
+        torch.manual_seed(1)
+        conv1, bn1 = HardBinaryConv(cin, cout, 3, 2, 1).cuda(), nn.BatchNorm2d(cout).cuda()
+        ds = nn.Sequential(nn.Conv2d(cin, cout, 1, 2, bias=False), nn.BatchNorm2d(cout)).cuda()
+        xd = x.clone().requires_grad_(True)
+        sc = R._shortcut_args(xd, ds)
+        assert sc is not None
+        if one_node:
+            out = R._fused_unit(xd, conv1, bn1, None, shortcut=sc)
+        else:
+            out = R._fused_unit(xd, conv1, bn1, R.F_.shortcut_conv_bn(xd, *sc))
+        assert out is not None
+        out.backward(gz)
+        grads = [xd.grad] + [p.grad for p in list(conv1.parameters()) + list(bn1.parameters()) + list(ds.parameters())]
+        return out.detach(), grads, ds[1].running_mean.clone()
+
+    o1, g1, rm1 = run(True)
+    o2, g2, rm2 = run(False)
+    torch.testing.assert_close(o1, o2, rtol=1e-5, atol=1e-5)       # BN statistics use fp64 atomics: last-bit noise
+    torch.testing.assert_close(rm1, rm2, rtol=1e-5, atol=1e-6)
+    for a, b in zip(g1, g2):
+        assert (a - b).abs().max().item() <= 2e-4 * b.abs().max().item() + 1e-7
