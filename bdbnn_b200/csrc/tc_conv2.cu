@@ -340,7 +340,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // Row offsets/validity of this warp's 32 rows are exchanged by shuffle in the store phase.
         const int64_t row_off = valid ? pix * p.Nout + nn0 : int64_t(-1);
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < (MODE == 1 ? 8 : 4); ++cb) {
           const int c0 = cb * 32;
           if (c0 >= p.BN) break;
           uint32_t v[32];
@@ -392,7 +392,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (offs[i] >= 0) {
               *reinterpret_cast<float4*>(p.out + offs[i] + c0 + cq * 4) = o;
               if (do_stats) {
-                float4& ss = acc_s[cb]; float4& sq = acc_q[cb]; float4& mx = acc_m[cb];
+                float4& ss = acc_s[cb & 3]; float4& sq = acc_q[cb & 3]; float4& mx = acc_m[cb & 3];
                 ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
                 sq.x += o.x * o.x; sq.y += o.y * o.y; sq.z += o.z * o.z; sq.w += o.w * o.w;
                 mx.x = fmaxf(mx.x, fabsf(o.x)); mx.y = fmaxf(mx.y, fabsf(o.y));
@@ -453,7 +453,12 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   memcpy(p.tap_b, L.tb, sizeof(p.tap_b));
   p.out_step = L.out_step; p.out_off_h = L.off_h; p.out_off_w = L.off_w; p.OHf = L.OHf; p.OWf = L.OWf;
   p.Nout = L.Nout;
-  p.BN = L.Nout >= 128 ? 128 : 64;
+  // dgrad of the wide layers (Nout = Cin >= 256): 256-wide N tiles — per K step the two M tiles fetch
+  // 2 x (4 KB A + 8 KB B) from shared memory instead of 4 x (4 + 4) KB for the same work (SS-mode MMAs are
+  // bound by that fetch, DESIGN.md section 5 finding 3).  BDBNN_TC_BN256=0 restores 128.
+  static const int bn256 = [] { const char* e = getenv("BDBNN_TC_BN256"); return e ? atoi(e) : 1; }();
+  const bool wide = bn256 && mode == 1 && !f8 && L.Nout % 256 == 0;
+  p.BN = wide ? 256 : (L.Nout >= 128 ? 128 : 64);
   p.n_ntiles = L.Nout / p.BN;
   // 512 TMEM columns = NB buffers x TS accumulators x BN columns.  BDBNN_TC_TS128 picks the BN=128 split:
   // 4 = four tiles sharing each weight stage, single buffer (epilogue exposed);
@@ -462,7 +467,7 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   // layer2 fwd 0.109 -> 0.097 ms, stride-2 fwd 0.081 -> 0.058), TS=4 wins for K >= 256 (layers 3, 4).
   static const int ts128 = [] { const char* e = getenv("BDBNN_TC_TS128"); return e ? atoi(e) : 0; }();
   const int ts_auto = (L.Kc * L.a_halves <= 128) ? 2 : 4;
-  p.TS = p.BN == 64 ? 4 : (ts128 == 4 ? 4 : (ts128 == 2 ? 2 : ts_auto));
+  p.TS = p.BN == 256 ? 2 : (p.BN == 64 ? 4 : (ts128 == 4 ? 4 : (ts128 == 2 ? 2 : ts_auto)));
   p.NB = 512 / (p.TS * p.BN);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
   p.fmt = L.fmt; p.amax_bits = L.amax_bits; p.add = L.add;
