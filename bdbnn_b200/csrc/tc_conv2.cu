@@ -262,14 +262,15 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // every 32-column block of the N tile, across tiles and work items, and flushes them to shared memory
     // only when the N tile changes or the CTA is done (per-block shuffles + atomics cost 25-35 % of the
     // forward kernels when done per 32x32 block).
-    float4 acc_s[4], acc_q[4], acc_m[4];
+    constexpr int kAcc = MODE == 0 ? 8 : 1;          // 32-column blocks of the widest N tile (256)
+    float4 acc_s[kAcc], acc_q[kAcc], acc_m[kAcc];
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) acc_s[cb] = acc_q[cb] = acc_m[cb] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int cb = 0; cb < kAcc; ++cb) acc_s[cb] = acc_q[cb] = acc_m[cb] = make_float4(0.f, 0.f, 0.f, 0.f);
     int acc_nn0 = -1;
     auto flush_stats = [&]() {
       if (!do_stats || acc_nn0 < 0) return;
 #pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
+      for (int cb = 0; cb < kAcc; ++cb) {
         if (cb * 32 >= p.BN) break;
         float4 ss = acc_s[cb], sq = acc_q[cb], mx = acc_m[cb];
         // lanes cq, cq+8, cq+16, cq+24 hold the same 4 channels for different rows
@@ -340,7 +341,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // Row offsets/validity of this warp's 32 rows are exchanged by shuffle in the store phase.
         const int64_t row_off = valid ? pix * p.Nout + nn0 : int64_t(-1);
 #pragma unroll
-        for (int cb = 0; cb < (MODE == 1 ? 8 : 4); ++cb) {
+        for (int cb = 0; cb < 8; ++cb) {
           const int c0 = cb * 32;
           if (c0 >= p.BN) break;
           uint32_t v[32];
@@ -392,7 +393,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (offs[i] >= 0) {
               *reinterpret_cast<float4*>(p.out + offs[i] + c0 + cq * 4) = o;
               if (do_stats) {
-                float4& ss = acc_s[cb & 3]; float4& sq = acc_q[cb & 3]; float4& mx = acc_m[cb & 3];
+                float4& ss = acc_s[MODE == 0 ? cb : 0]; float4& sq = acc_q[MODE == 0 ? cb : 0];
+                float4& mx = acc_m[MODE == 0 ? cb : 0];
                 ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
                 sq.x += o.x * o.x; sq.y += o.y * o.y; sq.z += o.z * o.z; sq.w += o.w * o.w;
                 mx.x = fmaxf(mx.x, fabsf(o.x)); mx.y = fmaxf(mx.y, fabsf(o.y));
@@ -456,8 +458,9 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   // dgrad of the wide layers (Nout = Cin >= 256): 256-wide N tiles — per K step the two M tiles fetch
   // 2 x (4 KB A + 8 KB B) from shared memory instead of 4 x (4 + 4) KB for the same work (SS-mode MMAs are
   // bound by that fetch, DESIGN.md section 5 finding 3).  BDBNN_TC_BN256=0 restores 128.
-  static const int bn256 = [] { const char* e = getenv("BDBNN_TC_BN256"); return e ? atoi(e) : 1; }();
-  const bool wide = bn256 && mode == 1 && !f8 && L.Nout % 256 == 0;
+  static const int bn256 = [] { const char* e = getenv("BDBNN_TC_BN256"); return e ? atoi(e) : 3; }();   // 1 dgrad, 2 fwd8, 3 both (default)
+  // forward: the fp8 layers with Cout >= 256 (bit 1 of the knob)
+  const bool wide = L.Nout % 256 == 0 && ((mode == 1 && !f8 && (bn256 & 1)) || (mode == 0 && f8 && (bn256 & 2)));
   p.BN = wide ? 256 : (L.Nout >= 128 ? 128 : 64);
   p.n_ntiles = L.Nout / p.BN;
   // 512 TMEM columns = NB buffers x TS accumulators x BN columns.  BDBNN_TC_TS128 picks the BN=128 split:
