@@ -26,7 +26,7 @@
 
 namespace bdbnn {
 
-constexpr int kMaxUnits = 2 * 5;   // units per CTA (G <= 5 M tiles)
+constexpr int kMaxUnits = 16;      // units per CTA (G <= 5 M tiles of 2 units, or 2 tiles of 8 16-wide units)
 
 struct TcWgradParams {
   int32_t OW, OH, NIMG;          // gy pixel grid
@@ -61,14 +61,14 @@ struct TcWgradParams {
     }                                                                                            \
   } while (0)
 
-// row_bytes 128: SWIZZLE_128B atoms of 8 K rows x 64 MN elements; row_bytes 64: SWIZZLE_64B, 8 x 32.
+// row_bytes 128: SWIZZLE_128B atoms of 8 K rows x 64 MN elements; 64: SWIZZLE_64B, 8 x 32; 32: SWIZZLE_32B, 8 x 16.
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t row_bytes = 128u) {
   uint64_t d = 0;
   d |= uint64_t((saddr & 0x3FFFFu) >> 4);
   d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;   // LBO: stride between MN chunks (one swizzle row each)
   d |= uint64_t((8u * row_bytes) >> 4) << 32;        // SBO: stride between 8-row K groups
   d |= uint64_t(1) << 46;
-  d |= uint64_t(row_bytes == 128u ? 2u : 4u) << 61;  // SWIZZLE_128B / SWIZZLE_64B
+  d |= uint64_t(row_bytes == 128u ? 2u : (row_bytes == 64u ? 4u : 6u)) << 61;  // SWIZZLE_128B / _64B / _32B
   return d;
 }
 
@@ -89,7 +89,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t a_row = uint32_t(p.UW) * 2u;                     // bytes per A row
   const int n_mtiles = (p.n_units + upt - 1) / upt;
   const int g_cta = min(p.G, n_mtiles - mt0);
-  const int nb_chunks = p.BN / 64;                                // 64-channel chunks of the N tile
+  const int nb_chunks = p.BN >= 64 ? p.BN / 64 : 1;               // 64-channel chunks of the N tile (or one narrow one)
+  const uint32_t b_row = p.BN >= 64 ? 128u : uint32_t(p.BN) * 2u;  // bytes per gys row of one chunk
   const int nb_boxes = nb_chunks * p.g_halves;                    // hi (and lo) boxes of gys
   const uint32_t a_bytes = uint32_t(p.n_a_boxes) * p.a_box_bytes;
   const uint32_t stage_bytes = a_bytes + uint32_t(nb_boxes) * p.b_box_bytes;
@@ -128,7 +129,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     uint8_t* base_generic = smem_raw + (tiles_base - smem_u32(smem_raw));
     const int a_w16 = int(a_row / 16u);                            // 16-byte words per A row
     const int a_tail = int(p.a_box_bytes / 16) - p.rows_a * a_w16;
-    const int b_tail = int(p.b_box_bytes / 16) - p.rows_b * 8;
+    const int b_w16 = int(b_row / 16u);
+    const int b_tail = int(p.b_box_bytes / 16) - p.rows_b * b_w16;
     const int per_stage = p.n_a_boxes * a_tail + nb_boxes * b_tail;
     const int total = p.stages * per_stage;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -143,7 +145,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         r -= p.n_a_boxes * a_tail;
         const int b = r / b_tail, w = r - b * b_tail;
         dst = base_generic + size_t(s) * stage_bytes + a_bytes + size_t(b) * p.b_box_bytes +
-              size_t(p.rows_b) * 128u + size_t(w) * 16u;
+              size_t(p.rows_b) * b_row + size_t(w) * 16u;
       }
       *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
@@ -163,7 +165,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (lane == 0) {
       const int n_a_loads = p.halo ? p.n_a_boxes : g_cta * upt;
       const uint32_t tx = uint32_t(n_a_loads) * uint32_t(p.rows_a) * a_row +
-                          uint32_t(nb_boxes) * uint32_t(p.rows_b) * 128u;
+                          uint32_t(nb_boxes) * uint32_t(p.rows_b) * b_row;
       int it = 0, tr_n = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
         const int stage = it % p.stages;
@@ -216,13 +218,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint32_t a_lo0 = uint32_t(ad0), a_hi = uint32_t(ad0 >> 32);
           const uint32_t acc = tmem_d + uint32_t(g * p.BN);
           for (int hf = 0; hf < p.g_halves; ++hf) {
-            const uint64_t bd0 = make_mnmajor_desc(b0 + hf * nb_chunks * p.b_box_bytes, p.b_box_bytes);
+            const uint64_t bd0 = make_mnmajor_desc(b0 + hf * nb_chunks * p.b_box_bytes, p.b_box_bytes, b_row);
+            const uint32_t b_kstep = b_row;                           // 16 K rows x b_row bytes, >> 4
             const uint32_t b_lo0 = uint32_t(bd0), b_hi = uint32_t(bd0 >> 32);
             // 16 pixel rows per K step: +2048 B (128-byte rows) = +128 in the low word's address field
             umma_bf16_split(acc, a_lo0, a_hi, b_lo0, b_hi, idesc, (it > 0 || hf > 0) ? 1u : 0u);
 #pragma unroll 4
             for (int k = 1; k < k_steps; ++k)
-              umma_bf16_split(acc, a_lo0 + uint32_t(k) * a_kstep, a_hi, b_lo0 + uint32_t(k) * 128u, b_hi, idesc, 1u);
+              umma_bf16_split(acc, a_lo0 + uint32_t(k) * a_kstep, a_hi, b_lo0 + uint32_t(k) * b_kstep, b_hi, idesc, 1u);
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));
@@ -306,10 +309,13 @@ struct WgradPlan {
   bool ok;
 };
 
+static WgradPlan plan_wgrad_small(const bdbnn_conv_shape* s, int halves);
+
 static WgradPlan plan_wgrad(const bdbnn_conv_shape* s, int halves) {
   WgradPlan pl;
   memset(&pl, 0, sizeof(pl));
   if (!s || (s->stride != 1 && s->stride != 2) || s->kh != s->kw || s->kh > 7 || s->pad > s->kh - 1) return pl;
+  if (s->Cin == 16 || s->Cin == 32 || s->Cout == 16 || s->Cout == 32) return plan_wgrad_small(s, halves);
   if (s->Cin % 64 != 0 || s->Cout % 64 != 0) return pl;
   if (s->Cout > 128 && s->Cout % 256 != 0) return pl;
   if (s->Wo > 128 || s->W > 128 * s->stride) return pl;
@@ -401,6 +407,69 @@ static WgradPlan plan_wgrad(const bdbnn_conv_shape* s, int halves) {
   const size_t stage_bytes = size_t(p.n_a_boxes) * p.a_box_bytes + size_t(p.BN / 64 * halves) * p.b_box_bytes;
   pl.smem = size_t(p.stages) * stage_bytes + 1024;
   pl.ok = pl.smem <= 227u * 1024u;
+  return pl;
+}
+
+// CIFAR-sized layers (ResNet-20: 16/32/64 channels): box mode with narrow units — A rows of Cin*2 bytes
+// (16 channels: SWIZZLE_32B, 32: SWIZZLE_64B, 64: SWIZZLE_128B), one gys box of Cout channels as the N
+// tile.  All M tiles of the layer live in one CTA when they fit (T*Cin/128 accumulators of Cout columns).
+static WgradPlan plan_wgrad_small(const bdbnn_conv_shape* s, int halves) {
+  WgradPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  auto ok_c = [](int c) { return c == 16 || c == 32 || c == 64; };
+  if (!ok_c(s->Cin) || !ok_c(s->Cout)) return pl;
+  if (s->Wo > 128 || s->W > 128 * s->stride) return pl;
+  TcWgradParams& p = pl.p;
+  const int T = s->kh * s->kw;
+  p.OW = s->Wo; p.OH = s->Ho; p.NIMG = s->N;
+  p.Cin = s->Cin; p.Cout = s->Cout; p.kh = s->kh; p.kw = s->kw; p.pad = s->pad; p.stride = s->stride;
+  p.g_halves = halves;
+  p.UW = s->Cin;
+  p.chunks_per_tap = 1;
+  p.n_units = T;
+  const int upt = kTileM / p.UW;
+  const int n_mtiles = (p.n_units + upt - 1) / upt;
+  p.BN = s->Cout;
+  p.G = kMaxUnits / upt;
+  if (p.G > n_mtiles) p.G = n_mtiles;
+  if (p.G * p.BN > 512) p.G = 512 / p.BN;
+  p.halo = 0;
+  p.BW = s->Wo;
+  const int a_row = p.UW * 2, b_row = p.BN >= 64 ? 128 : p.BN * 2;
+  // K stage: whole images when they are small, else rows of one image; <= 128 pixel rows
+  if (s->Ho * s->Wo <= kTileM) {
+    p.BH = s->Ho;
+    p.BNI = kTileM / (s->Ho * s->Wo);
+    if (p.BNI > s->N) p.BNI = s->N;
+  } else {
+    p.BH = kTileM / s->Wo;
+    p.BNI = 1;
+  }
+  p.rows_a = p.rows_b = p.BNI * p.BH * p.BW;
+  p.k_stage = (p.rows_a + 15) & ~15;
+  p.a_box_bytes = (uint32_t(p.k_stage) * uint32_t(a_row) + 1023u) & ~1023u;
+  p.b_box_bytes = (uint32_t(p.k_stage) * uint32_t(b_row) + 1023u) & ~1023u;
+  p.tiles_h = (s->Ho + p.BH - 1) / p.BH;
+  p.n_kboxes = p.tiles_h * ((s->N + p.BNI - 1) / p.BNI);
+  // fewer M tiles per CTA until a 2-stage ring fits in shared memory
+  size_t stage_bytes = 0;
+  for (;; --p.G) {
+    p.n_a_boxes = p.G * upt;
+    stage_bytes = size_t(p.n_a_boxes) * p.a_box_bytes + size_t(halves) * p.b_box_bytes;
+    p.stages = int((226u * 1024u) / stage_bytes);
+    if (p.stages >= 2 || p.G == 1) break;
+  }
+  if (p.stages > 4) p.stages = 4;
+  pl.mgroups = (n_mtiles + p.G - 1) / p.G;
+  pl.ntiles = 1;
+  int ks = num_sms() / pl.mgroups;
+  if (ks < 1) ks = 1;
+  pl.ks_cap = ks;
+  if (ks > p.n_kboxes) ks = p.n_kboxes;
+  p.kboxes_per_cta = (p.n_kboxes + ks - 1) / ks;
+  pl.ksplit = (p.n_kboxes + p.kboxes_per_cta - 1) / p.kboxes_per_cta;
+  pl.smem = size_t(p.stages) * stage_bytes + 1024;
+  pl.ok = p.stages >= 2 && pl.smem <= 227u * 1024u;
   return pl;
 }
 
@@ -522,9 +591,10 @@ extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_mod
   if (pl.p.halo)
     rc = make_act_map(&tmX, xb_bf16, s->N, s->H, s->W, s->Cin, 64, pl.p.PW, pl.p.PH, 1, 1);
   else
-    rc = make_act_map(&tmX, xb_bf16, s->N, s->H, s->W, s->Cin, 64, pl.p.BW, pl.p.BH, pl.p.BNI, s->stride);
+    rc = make_act_map(&tmX, xb_bf16, s->N, s->H, s->W, s->Cin, pl.p.UW, pl.p.BW, pl.p.BH, pl.p.BNI, s->stride);
   if (rc) return rc;
-  rc = make_act_map(&tmG, gys_bf16, s->N, s->Ho, s->Wo, s->Cout * grad_halves, 64, pl.p.BW, pl.p.BH, pl.p.BNI);
+  rc = make_act_map(&tmG, gys_bf16, s->N, s->Ho, s->Wo, s->Cout * grad_halves, pl.p.BN < 64 ? pl.p.BN : 64, pl.p.BW,
+                    pl.p.BH, pl.p.BNI);
   if (rc) return rc;
   BDBNN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
   dim3 grid(unsigned(pl.ksplit), unsigned(pl.mgroups), unsigned(pl.ntiles));

@@ -162,8 +162,13 @@ class BasicBlockCifar(nn.Module):
 
     def forward(self, x):
         residual = x if self.shortcut is None else self.shortcut(x)
-        out = self.bn1(self.conv1(x)) + residual
-        return self.bn2(self.conv2(out)) + out
+        out = _fused_unit(x, self.conv1, self.bn1, residual)
+        if out is None:
+            out = self.bn1(self.conv1(x)) + residual
+        out2 = _fused_unit(out, self.conv2, self.bn2, out)
+        if out2 is None:
+            out2 = self.bn2(self.conv2(out)) + out
+        return out2
 
 
 class ResNetCifar(nn.Module):
