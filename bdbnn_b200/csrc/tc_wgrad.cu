@@ -559,9 +559,11 @@ using namespace bdbnn;
 
 extern "C" size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s) {
   if (!s) return 0;
-  const WgradPlan pl = plan_wgrad(s, 2);
-  if (!pl.ok) return 0;
-  return size_t(pl.ks_cap) * s->kh * s->kw * s->Cin * s->Cout * sizeof(float);
+  // the split count may depend on the gradient mode (narrow-channel plan): size for the larger one
+  const WgradPlan p2 = plan_wgrad(s, 2), p1 = plan_wgrad(s, 1);
+  if (!p2.ok) return 0;
+  const int cap = p1.ok && p1.ks_cap > p2.ks_cap ? p1.ks_cap : p2.ks_cap;
+  return size_t(cap) * s->kh * s->kw * s->Cin * s->Cout * sizeof(float);
 }
 
 extern "C" int bdbnn_binconv_wgrad_tc(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
