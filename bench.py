@@ -62,7 +62,9 @@ TRAFFIC_KERNEL = {  # KernelTimer family -> kernel name in profiles/*_dram_traff
 def ncu_traffic(family):
     """dram__bytes_read+write per launch of the family's main kernel, from the newest committed ncu capture."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")))
+    import re
+    nat = lambda f: [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", os.path.basename(f))]
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")), key=nat)   # r1_step10 > r1_step9
     if not files or family not in TRAFFIC_KERNEL:
         return None, None
     with open(files[-1]) as fh:
