@@ -73,6 +73,17 @@ class _timed:
         return False
 
 
+def _dgrad_launches(sh):
+    """Kernels bdbnn_binconv_dgrad_tc launches: one per output-parity phase that has at least one tap."""
+    sd, n = sh.stride, 0
+    for a in range(sd):
+        for b in range(sd):
+            if any((a + sh.pad - r) % sd == 0 for r in range(sh.kh)) and \
+               any((b + sh.pad - q) % sd == 0 for q in range(sh.kw)):
+                n += 1
+    return n
+
+
 def _shape_key(sh):
     return f"N{sh.N}_{sh.H}x{sh.W}_c{sh.Cin}-{sh.Cout}_k{sh.kh}s{sh.stride}"
 
@@ -252,7 +263,7 @@ class _BinConv2d(torch.autograd.Function):
                 with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh)):
                     _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(mask_bits), _p(None), _p(gx),
                                                         ctypes.byref(sh), st), "binconv_dgrad_tc")
-                _lib.count(1)
+                _lib.count(_dgrad_launches(sh))
             if need_w and not (ctx.use & 4):
                 # wgrad on CUDA cores from the saved sign bits (tcgen05 wgrad not available for this shape)
                 gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
@@ -631,7 +642,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
                                       float(momentum), _p(running_mean), _p(running_var), _p(sums), _p(ymax),
                                       _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm), _p(zb), _p(zb8), fmt,
                                       1 if in_conv else 0, st), "bn_fwd")
-        _lib.count(3)
+        _lib.count(2 if in_conv else 3)
         ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
         ctx.shapes = (tuple(x.shape), tuple(weight.shape))
         ctx.has_res = residual is not None and sc_weight is None
@@ -681,7 +692,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
                 _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(xm),
                                                     _p(g) if ctx.res_is_x else _p(None), _p(gx),
                                                     ctypes.byref(sh), st), "binconv_dgrad_tc")
-            _lib.count(1)
+            _lib.count(_dgrad_launches(sh))
         if ctx.needs_input_grad[1]:
             gw = torch.empty(w_shape, dtype=torch.float32, device=dev)
             nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
@@ -789,7 +800,7 @@ def _shortcut_fwd_impl(x, weight, gamma, beta, running_mean, running_var, moment
                                   float(momentum), _p(running_mean), _p(running_var), _p(sums), _p(ymax),
                                   _p(mean), _p(invstd), _p(ab), _p(z), None, None, None, None, 0, 1, st),
                    "bn_fwd(shortcut)")
-    _lib.count(9)
+    _lib.count(7)       # x amax, x pack, W amax, W pack, conv, bn finalize, bn apply
     saved = (y, mean, invstd, gamma.detach(), ymax, xh, wt, gscale, inv_gscale)
     return z, saved, (sh1, shs, tuple(x.shape), tuple(weight.shape))
 
@@ -826,7 +837,7 @@ def _shortcut_bwd_impl(gz, saved, geom, need_x, need_w, acc=None):
         with _timed("shortcut_dgrad_tc", key, 2 * gys.numel() + (4 * gx.numel() if acc is None else 8 * n_pix * cin)):
             _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), 3, _p(amax), _p(wt), _p(ones), _p(acc), _p(gx),
                                                 ctypes.byref(shs), st), "binconv_dgrad_tc(shortcut)")
-        _lib.count(2)
+        _lib.count(_dgrad_launches(shs))
     if need_w:
         wones = torch.full(((cout * cin + 31) // 32,), -1, **i32)
         gw = torch.empty(w_shape, **f32)
@@ -895,7 +906,7 @@ def _bn_pool_fwd_impl(yc, gamma, beta, running_mean, running_var, momentum, eps,
                                        _p(sums), _p(ymax), _p(mean), _p(invstd), _p(ab), _p(z), _p(ysel), _p(idx),
                                        _p(zs), _p(zm), _p(zb), _p(zb8), fmt, 1 if stats is not None else 0,
                                        _stream()), "bn_pool_fwd")
-    _lib.count(3)
+    _lib.count(2 if stats is not None else 3)
     return (z, zs, zm, zb, zb8), (yc, ysel, idx, mean, invstd, gamma.detach(), ymax), (n, h, w, c, k, stride, pad, ho, wo)
 
 
@@ -999,7 +1010,7 @@ def _stem_conv_fwd_impl(x, weight, want_stats=False):
         _lib.check(L.bdbnn_stem_conv_fwd(_p(xw), _p(wf), _p(alpha), _p(y), n, h, w,
                                          _p(stats[0]) if stats else None, _p(stats[1]) if stats else None, st),
                    "stem_conv_fwd")
-    _lib.count(5)
+    _lib.count(4)       # x amax, x pack, W pack, conv
     if want_stats:
         return y, xw, x_amax, stats
     return y, xw, x_amax
