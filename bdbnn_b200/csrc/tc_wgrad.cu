@@ -557,6 +557,17 @@ int launch_stem_wgrad(const uint16_t* gys, const uint16_t* xw, float* ws, size_t
 
 using namespace bdbnn;
 
+// Host-only view of the wgrad tiling decision (no CUDA call): lets the CPU test-suite sweep shapes.
+extern "C" int bdbnn_debug_wgrad_plan(const bdbnn_conv_shape* s, int32_t grad_halves, int32_t* out, int32_t n_out) {
+  BDBNN_REQUIRE(s && out && n_out >= 12, "debug_wgrad_plan: need a shape and room for 12 ints");
+  BDBNN_REQUIRE(grad_halves == 1 || grad_halves == 2, "debug_wgrad_plan: grad_halves must be 1 or 2");
+  const WgradPlan pl = plan_wgrad(s, grad_halves);
+  const int32_t v[12] = {pl.ok ? 1 : 0, pl.ksplit, pl.ks_cap, pl.mgroups, pl.ntiles, int32_t(pl.smem), pl.p.G, pl.p.BN,
+                         pl.p.UW, pl.p.halo, pl.p.k_stage, pl.p.stages};
+  memcpy(out, v, sizeof(v));
+  return BDBNN_OK;
+}
+
 extern "C" size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s) {
   if (!s) return 0;
   // the split count may depend on the gradient mode (narrow-channel plan): size for the larger one

@@ -186,3 +186,40 @@ def test_make_optimizer_cpu_is_plain_torch_and_fused_rejects_cpu():
     p.grad = torch.ones(3)
     with pytest.raises(RuntimeError, match="CUDA"):
         FusedAdam([p]).step()
+
+
+def test_wgrad_tiling_plans_are_sane_for_every_network_layer():
+    """Host-only sweep of the wgrad planner (no GPU): every binary-conv geometry of the ResNet-18/34/20 shells,
+    both gradient operand widths — shared memory within the 227 KB CTA limit, one wave of CTAs, the
+    workspace large enough for the split the launch will use."""
+    import ctypes
+    from bdbnn_b200 import _lib
+    from bdbnn_b200.functional import conv_shape
+    L = _lib.lib()
+    shapes = []
+    for n in (1, 7, 256):
+        shapes += [((n, 64, 56, 56), (64, 64, 3, 3), 1), ((n, 64, 56, 56), (128, 64, 3, 3), 2),
+                   ((n, 128, 28, 28), (128, 128, 3, 3), 1), ((n, 128, 28, 28), (256, 128, 3, 3), 2),
+                   ((n, 256, 14, 14), (256, 256, 3, 3), 1), ((n, 256, 14, 14), (512, 256, 3, 3), 2),
+                   ((n, 512, 7, 7), (512, 512, 3, 3), 1),
+                   ((n, 64, 28, 28), (128, 64, 1, 1), 1), ((n, 256, 7, 7), (512, 256, 1, 1), 1),       # packed shortcuts
+                   ((n, 16, 32, 32), (16, 16, 3, 3), 1), ((n, 16, 32, 32), (32, 16, 3, 3), 2),
+                   ((n, 32, 16, 16), (32, 32, 3, 3), 1), ((n, 32, 16, 16), (64, 32, 3, 3), 2),
+                   ((n, 64, 8, 8), (64, 64, 3, 3), 1)]
+    for xs, ws, stride in shapes:
+        pad = 1 if ws[2] == 3 else 0
+        sh = conv_shape(xs, ws, stride, pad)
+        need = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
+        for halves in (1, 2):
+            out = (ctypes.c_int32 * 12)()
+            assert L.bdbnn_debug_wgrad_plan(ctypes.byref(sh), halves, out, 12) == 0
+            ok, ksplit, ks_cap, mgroups, ntiles, smem, G, BN, UW, halo, k_stage, stages = list(out)
+            assert ok == 1, (xs, ws, stride, halves)
+            assert smem <= 227 * 1024 and stages >= 2 and k_stage % 16 == 0 and k_stage > 0
+            assert 1 <= ksplit <= ks_cap and ksplit * mgroups * ntiles <= 148           # one wave on a B200
+            assert UW in (16, 32, 64) and G * BN <= 512                                 # TMEM columns
+            assert need >= ksplit * ws[0] * ws[1] * ws[2] * ws[3] * 4, (xs, ws, halves, need, ksplit)
+    # unsupported geometry is reported, not planned
+    out = (ctypes.c_int32 * 12)()
+    sh = conv_shape((1, 40, 8, 8), (64, 40, 3, 3), 1, 1)
+    assert L.bdbnn_debug_wgrad_plan(ctypes.byref(sh), 1, out, 12) == 0 and out[0] == 0
