@@ -368,6 +368,7 @@ int launch_stem_wgrad(const uint16_t* gys, const uint16_t* xw, float* ws, size_t
 // does not qualify (caller falls back to the one-tile-per-CTA kernel in tc_conv.cu).
 int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st);
 void set_tc_trace(long long* buf);
+void set_conv_plan_sink(int32_t* sink);   // host-only planning probe, see tc_conv2.cu
 long long* get_tc_trace();
 bool wgrad_tc_ok(const bdbnn_conv_shape* s);
 

@@ -365,6 +365,57 @@ extern "C" int bdbnn_debug_trace(long long* device_buf) {
   return BDBNN_OK;
 }
 
+// Host-only: the persistent kernel's tiling for the forward (mode 0: 16-bit operands, 2: fp8) or the first
+// dgrad phase (mode 1) of a shape.  out[12] = {planned, halo, TS, NB, BN, n_tiles, supers, stages, dynamic smem,
+// grid, stage bytes, patch bytes}; planned = 0 when the shape goes to the one-tile kernel.  No CUDA call.
+extern "C" int bdbnn_debug_conv_plan(const bdbnn_conv_shape* s, int32_t mode, int32_t grad_halves, int32_t* out,
+                                     int32_t n_out) {
+  int rc = validate_shape(s);
+  if (rc) return rc;
+  BDBNN_REQUIRE(out && n_out >= 12 && mode >= 0 && mode <= 2 && (grad_halves == 1 || grad_halves == 2),
+                "debug_conv_plan: bad arguments");
+  memset(out, 0, 12 * sizeof(int32_t));
+  if (!tc_shape_ok(s)) return BDBNN_OK;
+  TcConvLaunch L;
+  memset(&L, 0, sizeof(L));
+  const int T = s->kh * s->kw;
+  if (mode == 1) {
+    const int sd = s->stride;            // phase (0,0) of the stride decomposition
+    for (int r = 0; r < s->kh; ++r) {
+      if ((s->pad - r) % sd != 0) continue;
+      for (int q = 0; q < s->kw; ++q) {
+        if ((s->pad - q) % sd != 0) continue;
+        L.dh[L.n_taps] = int8_t((s->pad - r) / sd); L.dw[L.n_taps] = int8_t((s->pad - q) / sd);
+        L.tb[L.n_taps] = uint8_t(T - 1 - (r * s->kw + q));
+        ++L.n_taps;
+      }
+    }
+    L.OH = (s->H + sd - 1) / sd; L.OW = (s->W + sd - 1) / sd;
+    L.IH = s->Ho; L.IW = s->Wo; L.Kc = s->Cout; L.a_halves = grad_halves; L.in_step = 1;
+    L.b_taps = T; L.Nout = s->Cin; L.NIMG = s->N;
+    L.out_step = sd; L.OHf = s->H; L.OWf = s->W;
+    L.fmt = grad_halves == 1 ? BDBNN_FMT_FP16 : BDBNN_FMT_BF16;
+  } else {
+    L.IH = s->H; L.IW = s->W; L.Kc = s->Cin; L.a_halves = 1; L.in_step = s->stride;
+    L.b_taps = T; L.Nout = s->Cout; L.NIMG = s->N; L.OH = s->Ho; L.OW = s->Wo;
+    for (int r = 0; r < s->kh; ++r)
+      for (int q = 0; q < s->kw; ++q) {
+        const int t = r * s->kw + q;
+        L.dh[t] = int8_t(r - s->pad); L.dw[t] = int8_t(q - s->pad); L.tb[t] = uint8_t(t);
+      }
+    L.n_taps = T;
+    L.out_step = 1; L.OHf = s->Ho; L.OWf = s->Wo;
+    L.fmt = mode == 2 ? -1 : BDBNN_FMT_FP16;
+    if (mode == 2 && s->Cin % 128 != 0) return BDBNN_OK;
+  }
+  if (L.n_taps == 0) return BDBNN_OK;
+  set_conv_plan_sink(out);
+  rc = launch_tc_conv2(L, mode == 1 ? 1 : 0, nullptr);
+  set_conv_plan_sink(nullptr);
+  if (rc == BDBNN_ERR_UNSUPPORTED) { memset(out, 0, 12 * sizeof(int32_t)); return BDBNN_OK; }
+  return rc;
+}
+
 extern "C" int bdbnn_tc_supported(const bdbnn_conv_shape* s) {
   if (!tc_shape_ok(s)) return 0;
   // fp8 forward only with 128-byte K rows (Cin % 128 == 0): with 64-channel (64-byte, SWIZZLE_64B) rows

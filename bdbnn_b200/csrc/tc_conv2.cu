@@ -430,6 +430,11 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// Host-only planning probe (bdbnn_debug_conv_plan): when set, launch_tc_conv2 fills it with the tiling it
+// chose and returns before creating tensor maps or touching CUDA.
+thread_local int32_t* g_plan_sink = nullptr;
+void set_conv_plan_sink(int32_t* sink) { g_plan_sink = sink; }
+
 static long long* g_trace = nullptr;
 void set_tc_trace(long long* buf) { g_trace = buf; }
 long long* get_tc_trace() { return g_trace; }
@@ -513,7 +518,8 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
     p.patch_bytes = (rows * row_bytes + 1023u) & ~1023u;
     if (uint32_t(p.PW * p.PH * p.HBNI) * row_bytes > p.patch_bytes) return BDBNN_ERR_UNSUPPORTED;
     p.stage_bytes = (p.b_bytes + 1023u) & ~1023u;
-    rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, kb_elems, p.PW, p.PH, p.HBNI, 1, esize);
+    rc = g_plan_sink ? BDBNN_OK
+                     : make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, kb_elems, p.PW, p.PH, p.HBNI, 1, esize);
   } else {
     p.halo = 0;
     p.BW = L.OW;
@@ -531,14 +537,16 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
     p.n_mtiles = p.tiles_h * ((L.NIMG + p.BNI - 1) / p.BNI);
     p.n_supers = (p.n_mtiles + p.TS - 1) / p.TS;
     p.stage_bytes = (p.b_bytes + uint32_t(p.TS) * kTileM * row_bytes + 1023u) & ~1023u;
-    if (L.win)
+    if (g_plan_sink)
+      rc = BDBNN_OK;
+    else if (L.win)
       rc = make_window_map(&tmA, L.A, L.NIMG, L.IH, L.IW, kb_elems, L.win_stride, L.win_row_stride, L.win_img_stride,
                            p.BW, p.BH, p.BNI, L.in_step);
     else
       rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, kb_elems, p.BW, p.BH, p.BNI, L.in_step, esize);
   }
   if (rc) return rc;
-  rc = make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, kb_elems, p.BN, esize);
+  rc = g_plan_sink ? BDBNN_OK : make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, kb_elems, p.BN, esize);
   if (rc) return rc;
   const uint32_t kStaging = 4u * 4096u;   // epilogue transpose tiles
   const uint32_t fixed = (p.halo ? 2u * p.patch_bytes : 0u) + kStaging;
@@ -555,6 +563,12 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   const int n_work = p.n_supers * p.n_ntiles;
   int grid = num_sms();
   if (grid > n_work) grid = n_work;
+  if (g_plan_sink) {
+    const int32_t v[12] = {1, p.halo, p.TS, p.NB, p.BN, p.n_ntiles, p.n_supers, stages, int32_t(smem), grid,
+                           int32_t(p.stage_bytes), int32_t(p.halo ? p.patch_bytes : 0)};
+    memcpy(g_plan_sink, v, sizeof(v));
+    return BDBNN_OK;
+  }
   if (mode == 0) {
     BDBNN_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     tc_conv2_kernel<0><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);

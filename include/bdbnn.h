@@ -160,6 +160,12 @@ BDBNN_API int bdbnn_binconv_dgrad_tc(const uint16_t* gys, int32_t grad_mode, con
                            const uint16_t* wt, const uint32_t* mask_bits, const float* add, float* gx,
                            const bdbnn_conv_shape* s, void* stream);
 BDBNN_API size_t bdbnn_wgrad_tc_workspace_bytes(const bdbnn_conv_shape* s);
+/* Host-only: the persistent forward/dgrad kernel's tiling for a shape (mode 0 = forward, 1 = first dgrad
+ * phase, 2 = fp8 forward).  out[12] = {planned (0 = one-tile kernel), halo mode, M tiles per super tile,
+ * TMEM buffers, N tile, N tiles, super tiles, ring stages, dynamic smem bytes, grid, stage bytes, patch
+ * bytes}.  Makes no CUDA call. */
+BDBNN_API int bdbnn_debug_conv_plan(const bdbnn_conv_shape* s, int32_t mode, int32_t grad_halves, int32_t* out,
+                          int32_t n_out);
 /* Host-only: the tiling bdbnn_binconv_wgrad_tc would use, for tests.  out[12] = {supported, ksplit, ks_cap,
  * m_groups, n_tiles, dynamic smem bytes, M tiles per CTA, N tile, unit width, halo mode, K rows per stage,
  * ring stages}.  Makes no CUDA call. */

@@ -223,3 +223,36 @@ def test_wgrad_tiling_plans_are_sane_for_every_network_layer():
     out = (ctypes.c_int32 * 12)()
     sh = conv_shape((1, 40, 8, 8), (64, 40, 3, 3), 1, 1)
     assert L.bdbnn_debug_wgrad_plan(ctypes.byref(sh), 1, out, 12) == 0 and out[0] == 0
+
+
+def test_conv_tiling_plans_are_sane_for_every_network_layer():
+    """Host-only sweep of the persistent forward / dgrad kernel's planner (no GPU): TMEM columns, shared memory
+    (dynamic + the kernel's static 6.5 KB of BN-statistics scratch in the forward) and ring depth."""
+    import ctypes
+    from bdbnn_b200 import _lib
+    from bdbnn_b200.functional import conv_shape
+    L = _lib.lib()
+    layers = [((64, 56, 56), 64, 1), ((64, 56, 56), 128, 2), ((128, 28, 28), 128, 1), ((128, 28, 28), 256, 2),
+              ((256, 14, 14), 256, 1), ((256, 14, 14), 512, 2), ((512, 7, 7), 512, 1), ((64, 8, 8), 64, 1)]
+    planned = 0
+    for n in (2, 256, 512):
+        for (cin, h, w), cout, stride in layers:
+            sh = conv_shape((n, cin, h, w), (cout, cin, 3, 3), stride, 1)
+            for mode, halves in ((0, 1), (1, 1), (1, 2), (2, 1)):
+                out = (ctypes.c_int32 * 12)()
+                assert L.bdbnn_debug_conv_plan(ctypes.byref(sh), mode, halves, out, 12) == 0
+                ok, halo, TS, NB, BN, n_tiles, supers, stages, smem, grid, stage_bytes, patch = list(out)
+                if not ok:
+                    assert mode == 2 and cin % 128 != 0 or n == 2, (cin, cout, stride, mode)   # fp8 needs Cin % 128
+                    continue
+                planned += 1
+                assert TS * BN * NB <= 512 and BN in (64, 128, 256) and NB in (1, 2)
+                assert stages >= 2 and 1 <= grid <= 148 and supers >= 1
+                static = 7 * 1024 if mode != 1 else 1024
+                assert smem + static <= 227 * 1024, (cin, cout, stride, mode, smem)
+                assert BN * n_tiles == (cin if mode == 1 else cout)
+    assert planned > 60
+    # 16/32-channel layers are served by the one-tile kernel: the probe says "not planned"
+    out = (ctypes.c_int32 * 12)()
+    sh = conv_shape((4, 16, 32, 32), (16, 16, 3, 3), 1, 1)
+    assert L.bdbnn_debug_conv_plan(ctypes.byref(sh), 0, 1, out, 12) == 0 and out[0] == 0
