@@ -494,7 +494,13 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   const int super_rows = p.TS * kTileM;  // padded rows per super tile
   CUtensorMap tmA, tmB;
   int rc;
-  if (L.in_step == 1 && L.OH * L.OW > kTileM && PW <= 256 && PW * (1 + dh_span) <= super_rows) {
+  // BDBNN_TC_HALO_SMALL=1 (experimental, off): halo patches also for images of <= 128 pixels (several whole
+  // images per super tile).  The 7x7 layers then fetch one patch per K block instead of one box per tap
+  // (box mode: 2.3 MB of activation traffic per work item against 0.6 MB of weights), at 57 % instead of
+  // 77 % row utilisation; to be measured.
+  static const int halo_small = [] { const char* e = getenv("BDBNN_TC_HALO_SMALL"); return e ? atoi(e) : 0; }();
+  if (L.in_step == 1 && (L.OH * L.OW > kTileM || (halo_small && !L.win && L.OH * L.OW >= 16)) && PW <= 256 &&
+      PW * (1 + dh_span) <= super_rows) {
     p.halo = 1;
     p.PW = PW; p.dh_min = dh0; p.dw_min = dw0;
     const int img_block = (L.OH + dh_span) * PW;      // whole image incl. halo rows, padded raster
