@@ -26,8 +26,13 @@ __device__ __forceinline__ float blk_sum(float v, float* sh) {
   return warp_sum(t);
 }
 
-// One block per sample: row_loss = logsumexp(z) - z[target]; grad = (softmax(z) - onehot)/N;
+// One block per sample: row_loss = logsumexp(z) - z[target]; grad = (softmax(z) - onehot)/N_valid;
 // row_rank = number of classes that beat the target (ties: lower index wins, like a stable top-k).
+// nn.CrossEntropyLoss() edge cases (train.py:298 constructs it with the defaults): a target equal to
+// ignore_index (-100) contributes no loss and no gradient and is left out of the mean's divisor
+// (N_valid = number of non-ignored rows; all ignored -> NaN like torch); any other target outside
+// [0, C) is a caller bug — torch raises a device-side assert, this kernel traps (sticky launch failure).
+constexpr int64_t kIgnoreIndex = -100;
 __global__ void __launch_bounds__(128)
 ce_row_kernel(const float* __restrict__ z, const int64_t* __restrict__ target, int32_t N, int32_t C,
               float* __restrict__ row_loss, int32_t* __restrict__ row_rank, float* __restrict__ grad) {
@@ -36,7 +41,11 @@ ce_row_kernel(const float* __restrict__ z, const int64_t* __restrict__ target, i
   const float* zr = z + int64_t(n) * C;
   const int64_t t = target[n];
   const bool t_ok = t >= 0 && t < C;
+  if (!t_ok && t != kIgnoreIndex) __trap();
   const float zt = t_ok ? zr[t] : -INFINITY;
+  float valid = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) valid += target[i] != kIgnoreIndex ? 1.f : 0.f;
+  valid = blk_sum(valid, sh);
   float m = -INFINITY;
   for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, zr[c]);
   m = blk_max(m, sh);
@@ -50,7 +59,7 @@ ce_row_kernel(const float* __restrict__ z, const int64_t* __restrict__ target, i
   beat = blk_sum(beat, sh);
   const float lse = m + logf(e);
   if (grad != nullptr) {
-    const float inv_e = 1.0f / e, invN = 1.0f / float(N);
+    const float inv_e = 1.0f / e, invN = 1.0f / valid;
     for (int c = threadIdx.x; c < C; c += blockDim.x)
       grad[int64_t(n) * C + c] = t_ok ? (expf(zr[c] - m) * inv_e - (c == t ? 1.f : 0.f)) * invN : 0.f;
   }
@@ -63,24 +72,29 @@ ce_row_kernel(const float* __restrict__ z, const int64_t* __restrict__ target, i
 // loss = mean of the rows (fixed order), acc[k] = 100 * #(rank < topk[k]) / N; optional running meters
 // meters = {sum loss*N, sum acc1*N, sum acc5*N, samples} (AverageMeter.update(val, n), utils/utils.py).
 __global__ void __launch_bounds__(256)
-ce_finalize_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ row_rank, int32_t N, int32_t k1,
+ce_finalize_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ row_rank,
+                   const int64_t* __restrict__ target, int32_t N, int32_t k1,
                    int32_t k2, float* __restrict__ loss_out, float* __restrict__ acc_out,
                    double* __restrict__ meters) {
-  __shared__ double red[3][8];
-  double a = 0.0, c1 = 0.0, c2 = 0.0;
+  __shared__ double red[4][8];
+  double a = 0.0, c1 = 0.0, c2 = 0.0, nv = 0.0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     a += double(row_loss[i]);
     const int r = row_rank[i];
     c1 += r < k1 ? 1.0 : 0.0;
     c2 += r < k2 ? 1.0 : 0.0;
+    nv += target[i] != kIgnoreIndex ? 1.0 : 0.0;
   }
-  a = warp_sum(a); c1 = warp_sum(c1); c2 = warp_sum(c2);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = c1; red[2][threadIdx.x >> 5] = c2; }
+  a = warp_sum(a); c1 = warp_sum(c1); c2 = warp_sum(c2); nv = warp_sum(nv);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = c1; red[2][threadIdx.x >> 5] = c2;
+    red[3][threadIdx.x >> 5] = nv;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double ta = 0.0, t1 = 0.0, t2 = 0.0;
-    for (int i = 0; i < int(blockDim.x >> 5); ++i) { ta += red[0][i]; t1 += red[1][i]; t2 += red[2][i]; }
-    const float loss = float(ta / double(N));
+    double ta = 0.0, t1 = 0.0, t2 = 0.0, tv = 0.0;
+    for (int i = 0; i < int(blockDim.x >> 5); ++i) { ta += red[0][i]; t1 += red[1][i]; t2 += red[2][i]; tv += red[3][i]; }
+    const float loss = float(ta / tv);           // mean over the non-ignored rows (0/0 = NaN like torch)
     const float acc1 = float(t1 * 100.0 / double(N)), acc2 = float(t2 * 100.0 / double(N));
     loss_out[0] = loss;
     acc_out[0] = acc1;
@@ -172,7 +186,7 @@ extern "C" int bdbnn_ce_topk_fwd_bwd(const float* logits, const int64_t* target,
   ce_row_kernel<<<N, 128, 0, st>>>(logits, target, N, C, row_loss_ws, row_rank_ws, grad_logits);
   int rc = check_launch("ce_row_kernel");
   if (rc) return rc;
-  ce_finalize_kernel<<<1, 256, 0, st>>>(row_loss_ws, row_rank_ws, N, k1, k2, loss_out, acc_out, meters);
+  ce_finalize_kernel<<<1, 256, 0, st>>>(row_loss_ws, row_rank_ws, target, N, k1, k2, loss_out, acc_out, meters);
   return check_launch("ce_finalize_kernel");
 }
 

@@ -31,6 +31,7 @@ class GradAllReduce:
         self.overlap = bool(overlap) and self.world > 1
         self.scale = bool(scale)      # False: the optimizer applies 1/world (optim.FusedAdam/FusedSGD grad_scale)
         order = list(reversed(self.params))
+        self._view = {}                        # id(p) -> the parameter's view into the flat buffer
         target = max(1, (total + n_buckets - 1) // max(1, n_buckets))
         self.buckets = []                      # [start, end, n_params]
         self._bucket_of = {}
@@ -40,6 +41,7 @@ class GradAllReduce:
             # autograd accumulates in place into the view; keep the parameter's own strides
             # (channels_last conv weights) so fused optimizers see matching layouts
             p.grad = torch.as_strided(self.flat, p.size(), p.stride(), storage_offset=off)
+            self._view[id(p)] = p.grad
             self._bucket_of[id(p)] = len(self.buckets)
             off += n
             b_count += 1
@@ -62,7 +64,22 @@ class GradAllReduce:
         a, e, _ = self.buckets[b]
         self._works[b] = dist.all_reduce(self.flat[a:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
+    def _rebind(self, p):
+        """Fail-safe: `optimizer.zero_grad()` (torch's default set_to_none=True) or user code dropped /
+        replaced the .grad view, so autograd wrote this step's gradient into a fresh tensor.  Copy it into
+        the flat buffer and re-point .grad at the view — never all-reduce a stale buffer."""
+        v = self._view[id(p)]
+        g = p.grad
+        if g is None:
+            v.zero_()
+        elif g.data_ptr() != v.data_ptr() or g.stride() != v.stride():
+            v.copy_(g)
+        else:
+            return
+        p.grad = v
+
     def _hook(self, p):
+        self._rebind(p)
         b = self._bucket_of[id(p)]
         self._pending[b] -= 1
         if self._pending[b] == 0 and self._works[b] is None:
@@ -70,10 +87,17 @@ class GradAllReduce:
 
     def zero(self):
         self.flat.zero_()
+        for p in self.params:                  # re-point views a set_to_none zero_grad() dropped
+            v = self._view[id(p)]
+            if p.grad is not v:
+                p.grad = v
         self._pending = [b[2] for b in self.buckets]
         self._works = [None] * len(self.buckets)
 
     def __call__(self):
+        if not self.overlap:
+            for p in self.params:              # no hooks registered: verify the views here
+                self._rebind(p)
         if self.world > 1:
             for b in range(len(self.buckets)):
                 if self._works[b] is None:
@@ -87,7 +111,9 @@ class GradAllReduce:
 
 
 class FlatGradOptimizerShim:
-    """optimizer.zero_grad() replacement that keeps .grad views alive (zeroes the flat buffer)."""
+    """optimizer.zero_grad() replacement that keeps .grad views alive (zeroes the flat buffer) — the fast
+    path.  Without it GradAllReduce still gives correct results (see `_rebind`) at the cost of one copy
+    per parameter per step; TrainStep calls `grad_sync.zero()` itself when it is handed a GradAllReduce."""
 
     def __init__(self, optimizer, reducer: GradAllReduce):
         self.optimizer, self.reducer = optimizer, reducer

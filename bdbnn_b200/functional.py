@@ -3,6 +3,7 @@
 PyTorch supplies device memory, streams and autograd bookkeeping only; every arithmetic step of the
 hot path is a kernel in libbdbnn_b200.so.  CUDA tensors are mandatory: CPU tensors raise."""
 import ctypes
+import functools
 import os
 
 import torch
@@ -29,6 +30,28 @@ _VALID_IMPL = ("auto", "xnor", "tc")
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device(fn):
+    """Device guard for Function.forward / backward: the kernels are launched on the current stream of the
+    CURRENT device, so make the device of the first CUDA tensor argument current for the duration of the
+    call (a tensor on cuda:1 while cuda:0 is current would otherwise be launched on the wrong device)."""
+    @functools.wraps(fn)
+    def guarded(ctx, *args):
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(ctx, *args)
+                break
+        return fn(ctx, *args)
+    return guarded
+
+
+def _same_device(*tensors):
+    devs = {t.device for t in tensors if torch.is_tensor(t)}
+    if len(devs) > 1:
+        raise RuntimeError(f"bdbnn_b200: operands live on different devices: {sorted(map(str, devs))}")
 
 
 class KernelTimer:
@@ -156,9 +179,11 @@ class _BinConv2d(torch.autograd.Function):
     Saved for backward: bits only (plus the bf16 +-1 copy on the tensor-core path) — never fp32 x."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, weight, stride, padding, impl, ede_k=None, ede_t=None):
         _require_cuda(x, "binconv2d(x)")
         _require_cuda(weight, "binconv2d(weight)")
+        _same_device(x, weight, ede_k, ede_t)
         L = _lib.lib()
         sh = conv_shape(x.shape, weight.shape, stride, padding)
         use = resolve_impl(impl, sh)
@@ -225,15 +250,20 @@ class _BinConv2d(torch.autograd.Function):
             _require_cuda(ede_t, "binconv2d(t)")
             mask_bits = torch.full_like(mask_bits, -1)
             wmask = torch.full_like(wmask, -1)
-            ctx.ede_saved = (xc, w, ede_k.detach().reshape(-1)[:1].float().contiguous(),
-                             ede_t.detach().reshape(-1)[:1].float().contiguous())
-        if tc:
-            ctx.save_for_backward(sign_bits, mask_bits, wsign, wmask, alpha, xb, wt, gscale, inv_gscale)
+            # x and weight themselves go through save_for_backward, so an in-place update between forward
+            # and backward trips autograd's version check instead of giving silently wrong EDE factors
+            ede_saved = (x, weight, ede_k.detach().reshape(-1)[:1].float().contiguous(),
+                         ede_t.detach().reshape(-1)[:1].float().contiguous())
         else:
-            ctx.save_for_backward(sign_bits, mask_bits, wsign, wmask, alpha)
+            ede_saved = ()
+        if tc:
+            ctx.save_for_backward(sign_bits, mask_bits, wsign, wmask, alpha, xb, wt, gscale, inv_gscale, *ede_saved)
+        else:
+            ctx.save_for_backward(sign_bits, mask_bits, wsign, wmask, alpha, *ede_saved)
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, gy):
         L = _lib.lib()
         sh = ctx.sh
@@ -246,7 +276,7 @@ class _BinConv2d(torch.autograd.Function):
         sign_bits, mask_bits, wsign, wmask, alpha = saved[:5]
         key = _shape_key(sh)
         if ctx.use & 1:
-            xb, wt, gscale, inv_gscale = saved[5:]
+            xb, wt, gscale, inv_gscale = saved[5:9]
             n_pix_out = sh.N * sh.Ho * sh.Wo
             gname, gcode, gh = ctx.gmode          # the +-1 operands were packed in this mode's format
             gys = torch.empty((sh.N, sh.Ho, sh.Wo, gh * sh.Cout), dtype=torch.int16, device=dev)
@@ -295,7 +325,8 @@ class _BinConv2d(torch.autograd.Function):
                                                      ctypes.byref(sh), st), "binconv_wgrad")
                 _lib.count(1)
         if ctx.ede:
-            xv, wv, ek, et = ctx.ede_saved
+            xv, wv, ek, et = saved[-4:]
+            xv, wv = _nhwc(xv.detach()), wv.detach().contiguous()
             for gbuf, vbuf in ((gx, xv), (gw, wv)):
                 if gbuf is not None:
                     with _timed("ede_scale", key, 12 * gbuf.numel()):
@@ -324,6 +355,7 @@ class _KurtosisMulti(torch.autograd.Function):
     Replaces 19x KurtosisWeight.kurtosis_calc (kurtosis.py:23-39)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, targets, *weights):
         L = _lib.lib()
         n = len(weights)
@@ -339,8 +371,10 @@ class _KurtosisMulti(torch.autograd.Function):
         moments = torch.empty((n * 8,), dtype=torch.float64, device=dev)
         kurt = torch.empty((n,), dtype=torch.float32, device=dev)
         loss = torch.empty((n,), dtype=torch.float32, device=dev)
-        _lib.check(L.bdbnn_kurtosis_multi_fwd(_ptr_array(ws), numel, tg, n, _p(moments), _p(kurt),
-                                              _p(loss), _stream()), "kurtosis_multi_fwd")
+        tot = sum(w.numel() for w in ws)
+        with _timed("kurtosis_fwd", f"L{n}_n{tot}", 4 * tot):
+            _lib.check(L.bdbnn_kurtosis_multi_fwd(_ptr_array(ws), numel, tg, n, _p(moments), _p(kurt),
+                                                  _p(loss), _stream()), "kurtosis_multi_fwd")
         _lib.count(2)
         ctx.targets = tuple(float(t) for t in targets)
         ctx.save_for_backward(moments, *ws)
@@ -348,6 +382,7 @@ class _KurtosisMulti(torch.autograd.Function):
         return loss, kurt
 
     @staticmethod
+    @_on_device
     def backward(ctx, gloss, _gkurt):
         L = _lib.lib()
         moments, *ws = ctx.saved_tensors
@@ -356,8 +391,10 @@ class _KurtosisMulti(torch.autograd.Function):
         numel = (ctypes.c_int64 * n)(*[w.numel() for w in ws])
         tg = (ctypes.c_float * n)(*ctx.targets)
         gout = gloss.contiguous()
-        _lib.check(L.bdbnn_kurtosis_multi_bwd(_ptr_array(ws), numel, tg, n, _p(moments), _p(gout),
-                                              _ptr_array(grads), 0, _stream()), "kurtosis_multi_bwd")
+        tot = sum(w.numel() for w in ws)
+        with _timed("kurtosis_bwd", f"L{n}_n{tot}", 8 * tot):
+            _lib.check(L.bdbnn_kurtosis_multi_bwd(_ptr_array(ws), numel, tg, n, _p(moments), _p(gout),
+                                                  _ptr_array(grads), 0, _stream()), "kurtosis_multi_bwd")
         _lib.count(1)
         return (None, *grads)
 
@@ -371,6 +408,7 @@ class _KDLogits(torch.autograd.Function):
     """DistributionLoss.forward (utils/KD_loss.py:16-43): loss and d loss/d s in one pass."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, s, t):
         _require_cuda(s, "kd_logits(stud)")
         _require_cuda(t, "kd_logits(teacher)")
@@ -382,13 +420,15 @@ class _KDLogits(torch.autograd.Function):
         row = torch.empty((n,), dtype=torch.float32, device=s.device)
         loss = torch.empty((), dtype=torch.float32, device=s.device)
         grad = torch.empty_like(sc) if ctx.needs_input_grad[0] else None
-        _lib.check(L.bdbnn_kd_logits_fwd_bwd(_p(sc), _p(tc), n, c, _p(row), _p(loss), _p(grad), _stream()),
-                   "kd_logits_fwd_bwd")
+        with _timed("kd_logits", f"N{n}_C{c}", (8 + (4 if grad is not None else 0)) * n * c):
+            _lib.check(L.bdbnn_kd_logits_fwd_bwd(_p(sc), _p(tc), n, c, _p(row), _p(loss), _p(grad), _stream()),
+                       "kd_logits_fwd_bwd")
         _lib.count(2)
         ctx.save_for_backward(grad)
         return loss
 
     @staticmethod
+    @_on_device
     def backward(ctx, gout):
         (grad,) = ctx.saved_tensors
         return (grad * gout if grad is not None else None), None
@@ -403,6 +443,7 @@ class _CrossEntropyTopK(torch.autograd.Function):
     loss, its gradient and the two accuracies in two launches, nothing read back."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, logits, target, k1, k2, meters):
         _require_cuda(logits, "cross_entropy_topk(logits)")
         if not target.is_cuda:
@@ -430,6 +471,7 @@ class _CrossEntropyTopK(torch.autograd.Function):
         return loss, acc
 
     @staticmethod
+    @_on_device
     def backward(ctx, gout, _gacc):
         (grad,) = ctx.saved_tensors
         return (grad * gout if grad is not None else None), None, None, None, None
@@ -450,6 +492,7 @@ class _KDLayerMulti(torch.autograd.Function):
     """sum_l KLDivLoss(log_target=True)(Ws_l, Wt_l) (utils/KD_loss.py:52-67) in two launches."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, n_pairs, *tensors):
         L = _lib.lib()
         ws = [t.detach().contiguous() for t in tensors[:n_pairs]]
@@ -465,14 +508,17 @@ class _KDLayerMulti(torch.autograd.Function):
         numel = (ctypes.c_int64 * n_pairs)(*[w.numel() for w in ws])
         partial = torch.empty((n_pairs,), dtype=torch.float64, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        _lib.check(L.bdbnn_kd_layer_multi_fwd(_ptr_array(ws), _ptr_array(wt), numel, n_pairs, _p(partial),
-                                              _p(loss), _stream()), "kd_layer_multi_fwd")
+        tot = sum(w.numel() for w in ws)
+        with _timed("kd_layer_fwd", f"L{n_pairs}_n{tot}", 8 * tot):
+            _lib.check(L.bdbnn_kd_layer_multi_fwd(_ptr_array(ws), _ptr_array(wt), numel, n_pairs, _p(partial),
+                                                  _p(loss), _stream()), "kd_layer_multi_fwd")
         _lib.count(2)
         ctx.n_pairs = n_pairs
         ctx.save_for_backward(*wt)
         return loss
 
     @staticmethod
+    @_on_device
     def backward(ctx, gout):
         L = _lib.lib()
         wt = list(ctx.saved_tensors)
@@ -480,8 +526,10 @@ class _KDLayerMulti(torch.autograd.Function):
         grads = [torch.empty_like(w) for w in wt]
         numel = (ctypes.c_int64 * n)(*[w.numel() for w in wt])
         g = gout.contiguous().reshape(1)
-        _lib.check(L.bdbnn_kd_layer_multi_bwd(_ptr_array(wt), numel, n, _p(g), _ptr_array(grads), 0,
-                                              _stream()), "kd_layer_multi_bwd")
+        tot = sum(w.numel() for w in wt)
+        with _timed("kd_layer_bwd", f"L{n}_n{tot}", 8 * tot):
+            _lib.check(L.bdbnn_kd_layer_multi_bwd(_ptr_array(wt), numel, n, _p(g), _ptr_array(grads), 0,
+                                                  _stream()), "kd_layer_multi_bwd")
         _lib.count(1)
         return (None, *grads, *([None] * n))
 
@@ -495,6 +543,7 @@ class _MaxPoolNHWC(torch.autograd.Function):
     """torch.nn.MaxPool2d on NHWC fp32 with a one-byte winner index and a gather backward."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, k, stride, pad):
         _require_cuda(x, "max_pool2d_nhwc")
         n, c, h, w = x.shape
@@ -512,6 +561,7 @@ class _MaxPoolNHWC(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, gy):
         (idx,) = ctx.saved_tensors
         n, h, w, c, k, stride, pad, ho, wo = ctx.geom
@@ -557,10 +607,12 @@ class _ConvBNAddUnit(torch.autograd.Function):
     backward: bn_bwd_pack(gz, y) -> dgrad_tc, wgrad_tc ; residual grad = gz."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, stride,
                 padding, xs, xm, xb, xb8, res_is_x, sc_weight=None, sc_gamma=None, sc_beta=None, sc_rm=None,
                 sc_rv=None, sc_momentum=None, sc_eps=None, sc_stride=None):
         _require_cuda(x, "conv_bn_add(x)")
+        _same_device(x, weight, gamma, beta, residual, running_mean, running_var, sc_weight)
         # optional real-valued 1x1 shortcut branch evaluated inside this node: its output is the residual,
         # and its input gradient is added in place to this conv's (see backward)
         ctx.n_sc = 0
@@ -657,6 +709,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
         return z, None, None, None, None
 
     @staticmethod
+    @_on_device
     def backward(ctx, gz, _g1, _g2, _g3, _g4):
         if gz is None:
             return (None,) * 24
@@ -725,7 +778,8 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
     fmt = grad_mode()[3]
     pk = getattr(x, "_bdbnn_pack", None)
     xs = xm = xb = xb8 = None
-    if pk is not None and pk[3] == fmt:
+    # the packs describe x as it was when its producer wrote it: ignore them if x was modified in place since
+    if pk is not None and pk[3] == fmt and getattr(x, "_bdbnn_pack_version", None) == x._version:
         xs, xm, xb = pk[:3]
         xb8 = pk[4] if len(pk) > 4 else None
     res_is_x = residual is x and x.shape[1] == weight.shape[0] and int(stride) == 1
@@ -740,6 +794,7 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
                                                   int(padding), xs, xm, xb, xb8, res_is_x)
     if zs is not None:
         z._bdbnn_pack = (zs, zm, zb, fmt, zb8)
+        z._bdbnn_pack_version = z._version
     return z
 
 
@@ -854,6 +909,7 @@ class _RealConvBN(torch.autograd.Function):
     """z = BN_train(conv1x1_stride_s(x, W)) for the real-valued `downsample` branch (csrc/real_conv.cu)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, weight, gamma, beta, running_mean, running_var, momentum, eps, stride):
         _require_cuda(x, "shortcut_conv_bn(x)")
         z, saved, ctx.geom = _shortcut_fwd_impl(x, weight, gamma, beta, running_mean, running_var, momentum, eps, stride)
@@ -861,6 +917,7 @@ class _RealConvBN(torch.autograd.Function):
         return z
 
     @staticmethod
+    @_on_device
     def backward(ctx, gz):
         gx, gw, dgamma, dbeta = _shortcut_bwd_impl(gz, ctx.saved_tensors, ctx.geom, ctx.needs_input_grad[0],
                                                    ctx.needs_input_grad[1])
@@ -944,6 +1001,7 @@ class _StemBNPool(torch.autograd.Function):
     first binary conv's packs are emitted with z."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad):
         _require_cuda(y, "stem_bn_pool")
         ctx.set_materialize_grads(False)
@@ -956,6 +1014,7 @@ class _StemBNPool(torch.autograd.Function):
         return outs
 
     @staticmethod
+    @_on_device
     def backward(ctx, gz, *_unused):
         if gz is None:
             return (None,) * 10
@@ -1035,6 +1094,7 @@ class _StemConv(torch.autograd.Function):
     backward: grad_pack (fp16 x 2^e) -> stem_conv_wgrad (tcgen05, split-K) ; no input gradient."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, weight):
         y, xw, x_amax = _stem_conv_fwd_impl(x, weight)
         ctx.geom = (x.shape[0], x.shape[2], x.shape[3], y.shape[2], y.shape[3])
@@ -1042,6 +1102,7 @@ class _StemConv(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, gy):
         if not ctx.needs_input_grad[1]:
             return None, None
@@ -1065,6 +1126,7 @@ class _StemFused(torch.autograd.Function):
     bn_pool_bwd to stem_conv_wgrad as the fp16 operand only (no fp32 gradient of the 112x112x64 tensor)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, weight, gamma, beta, running_mean, running_var, momentum, eps, k, stride, pad):
         ctx.set_materialize_grads(False)
         y, xw, x_amax, stats = _stem_conv_fwd_impl(x, weight, want_stats=True)
@@ -1078,6 +1140,7 @@ class _StemFused(torch.autograd.Function):
         return outs
 
     @staticmethod
+    @_on_device
     def backward(ctx, gz, *_unused):
         if gz is None:
             return (None,) * 11
@@ -1094,6 +1157,7 @@ def stem_conv_bn_pool(x, weight, gamma, beta, running_mean, running_var, momentu
                                           int(kernel_size), int(stride), int(padding))
     if zs is not None:
         z._bdbnn_pack = (zs, zm, zb, grad_mode()[3], zb8)
+        z._bdbnn_pack_version = z._version
     return z
 
 
@@ -1110,4 +1174,5 @@ def stem_bn_pool(y, gamma, beta, running_mean, running_var, momentum, eps, kerne
                                            int(kernel_size), int(stride), int(padding))
     if zs is not None:
         z._bdbnn_pack = (zs, zm, zb, grad_mode()[3], zb8)
+        z._bdbnn_pack_version = z._version
     return z

@@ -41,6 +41,37 @@ class KurtosisWeight:
         self.kurtosis = kurt[0]
 
 
+class RidgeRegularization:
+    """kurtosis.py:42-53 (imported at train.py:29; only instantiated under `args.w_l2_reg`, which the
+    reference's parser never defines — dead upstream, kept so the import block of train.py resolves).
+    `l2_regularization()` returns None and leaves sum(W^2) on `.l2_loss`.  Plain torch ops: this object
+    is not on the hot path."""
+
+    def __init__(self, weight_tensor, name):
+        self.weight_tensor, self.name, self.l2_loss = weight_tensor, name, 0
+
+    def l2_calc(self):
+        self.l2_loss = self.weight_tensor.pow(2).sum()
+
+    def l2_regularization(self):
+        return self.l2_calc()
+
+
+class WeightRegularization:
+    """kurtosis.py:56-70 (same status as RidgeRegularization, flag `args.w_wr_reg`):
+    `.wr_loss` = || |W| - 1 ||_2 over the whole tensor; `.size` = element count."""
+
+    def __init__(self, weight_tensor, name):
+        self.weight_tensor, self.name, self.wr_loss = weight_tensor, name, 0
+        self.size = int(weight_tensor.numel())
+
+    def wr_calc(self):
+        self.wr_loss = torch.linalg.vector_norm(self.weight_tensor.abs() - 1, ord=2)
+
+    def w_regularization(self):
+        return self.wr_calc()
+
+
 def kurtosis_regularization(weights, targets, mode='avg', n_hooks=None, lam=1.0):
     """train.py:495-513 for all hooked layers at once. Returns (regulariser, per-layer losses, kurtosis).
     mode: 'sum' | 'avg' (sum / len(weight_to_hook)) | 'max'."""

@@ -31,6 +31,15 @@ def _dense_like(p, g):
     return g
 
 
+def _device_of(param_groups):
+    """Device of the first parameter that has a gradient (the launches go to ITS current stream)."""
+    for group in param_groups:
+        for p in group["params"]:
+            if p.grad is not None and p.is_cuda:
+                return p.device
+    return None
+
+
 def _check(p):
     if not p.is_cuda:
         raise RuntimeError("bdbnn_b200.optim: parameters must live on a CUDA device (no CPU path)")
@@ -49,6 +58,13 @@ class FusedAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        dev = _device_of(self.param_groups)
+        if dev is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):                 # device guard (parameters on a non-current device)
+                return self._step(closure)
+        return self._step(closure)
+
+    def _step(self, closure=None):
         loss = closure() if closure is not None else None
         for group in self.param_groups:
             for p in group["params"]:
@@ -97,6 +113,13 @@ class FusedSGD(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        dev = _device_of(self.param_groups)
+        if dev is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):                 # device guard (parameters on a non-current device)
+                return self._step(closure)
+        return self._step(closure)
+
+    def _step(self, closure=None):
         loss = closure() if closure is not None else None
         for group in self.param_groups:
             for p in group["params"]:

@@ -140,7 +140,8 @@ class TrainStep:
         # a caller-supplied criterion is honoured as is; otherwise the ops' fused CE+accuracy (if any)
         self._ce_acc = getattr(ops, "ce_acc", None) if criterion is None else None
         self.criterion = criterion or nn.CrossEntropyLoss()
-        self.meters = None          # device float64 {loss*N, acc1*N, acc5*N, N} (fused CE path)
+        self.meters = None          # device float64 {ce*N, acc1*N, acc5*N, N} (fused CE path)
+        self._loss_sum = None       # device float64 sum of total loss*N (train.py:519 / 638 `losses` meter)
         self.hooked = select_hooked_weights(model, self.cfg)
         if self.cfg.teacher_student and teacher is None:
             raise ValueError("teacher_student step needs a teacher model")
@@ -167,11 +168,16 @@ class TrainStep:
             return None
         m = self.meters.tolist()
         n = max(m[3], 1.0)
-        return {"loss": m[0] / n, "acc1": m[1] / n, "acc5": m[2] / n, "samples": int(m[3])}
+        # "loss" is the reference's `losses` meter = the TOTAL loss (CE + kurtosis + KD terms, train.py:519/638);
+        # "ce" its `losses_ce` meter (train.py:522/640).  They coincide for the plain CE step.
+        tot = float(self._loss_sum) if self._loss_sum is not None else m[0]
+        return {"loss": tot / n, "ce": m[0] / n, "acc1": m[1] / n, "acc5": m[2] / n, "samples": int(m[3])}
 
     def reset_meters(self):
         if self.meters is not None:
             self.meters.zero_()
+        if self._loss_sum is not None:
+            self._loss_sum.zero_()
 
     def __call__(self, images, target, epoch=0):
         cfg = self.cfg
@@ -179,7 +185,8 @@ class TrainStep:
         ce, acc1, acc5 = self._ce(output, target)                                 # train.py:493/614, :518
         loss_kl = loss_kl_c = 0
         if cfg.teacher_student:
-            with torch.no_grad():
+            from .functional import _timed
+            with torch.no_grad(), _timed("teacher_forward(cuDNN fp32)", "teacher", 0):
                 output_teacher = self.teacher(images)                             # train.py:603
             alpha, beta, lam_ce = cfg.alpha, cfg.beta, cfg.w_lambda_ce
             if cfg.react:                                                         # train.py:605-609
@@ -196,7 +203,17 @@ class TrainStep:
             kurt_reg = self.ops.kurtosis(list(self.hooked.values()), self.targets[:len(self.hooked)],
                                          cfg.kurtosis_mode, len(self.hooked), cfg.w_lambda_kurtosis)
         loss = loss_kl + loss_kl_c + orig_loss + kurt_reg                         # train.py:515 / 636
-        self.optimizer.zero_grad()                                                # train.py:527
+        extra_terms = cfg.teacher_student or torch.is_tensor(kurt_reg)
+        if self.meters is not None and (extra_terms or self._loss_sum is not None):
+            n_img = images.shape[0]
+            if self._loss_sum is None:       # steps so far were CE-only: their total equals the CE meter
+                self._loss_sum = self.meters[0:1].clone()
+                self._loss_sum.sub_(ce.detach(), alpha=n_img)       # this step's CE is already in meters[0]
+            self._loss_sum.add_(loss.detach(), alpha=n_img)                       # train.py:519 / 638, no .item()
+        if hasattr(self.grad_sync, "zero"):
+            self.grad_sync.zero()             # flat-buffer .grad views stay bound (GradAllReduce); train.py:527
+        else:
+            self.optimizer.zero_grad()                                            # train.py:527
         loss.backward()                                                           # train.py:528
         if self.grad_sync is not None:
             self.grad_sync()

@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"],
+                    help="b200 = this repo; reference = the reference's CPU path (oracle port) on the host cores; "
+                         "reference-gpu = the same pure-PyTorch oracle modules on cuda (stock eager cuDNN/ATen)")
     ap.add_argument("--model", default="resnet18", choices=["resnet18", "resnet34", "resnet20"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 256; 128 for resnet20)")
     ap.add_argument("--workload", default="ce", choices=["ce", "kurt_kd"],
@@ -44,7 +46,10 @@ def parse():
     ap.add_argument("--conv-impl", default=None, choices=[None, "auto", "xnor", "tc"])
     ap.add_argument("--ede", action="store_true",
                     help="EDE backward (train.py:409-415) at epoch 40/120; acts on HardBinaryConv_cifar (resnet20)")
-    ap.add_argument("--cpu-batch", type=int, default=32, help="bounded CPU sample: images per CPU step")
+    ap.add_argument("--cpu-batch", type=int, default=None,
+                    help="images per CPU step (default: the full per-GPU batch, cut only if the run would exceed ~4 min)")
+    ap.add_argument("--no-eager-gpu", action="store_true", help="skip the eager-cuDNN comparator line (N=1)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bf16x2 gradient-mode secondary value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
@@ -199,25 +204,34 @@ def host_threads():
     return n
 
 
-def cpu_reference_run(args, steps, warmup, batch):
+def cpu_reference_run(args, steps, warmup, batch, budget_s=240.0):
     """The reference arm / cpu_baseline: restated train.py step on the pure-PyTorch oracle modules.
     Thread count: the fastest of {16, 32, 64, all usable} on one probe step each (oversubscribing a
-    small batch across 128 SMT threads is far slower than 32), then `steps` timed steps at that count."""
-    from bdbnn_b200.step import TrainStep, make_optimizer
-    from oracle.models_ref import RefOps
+    small batch across 128 SMT threads is far slower than 32), then `steps` timed steps at that count.
+    Runs the FULL per-GPU batch; only if `steps` of them would not fit `budget_s` is the batch halved
+    (returned, so the caller can say what the sample was)."""
+    from oracle import step_ref as S
     n_all = host_threads()
     torch.set_num_threads(min(n_all, 16))
     torch.manual_seed(0)
     ishape, ncls, dataset = shapes(args.model, batch)
     model = build_model(args.model, ref=True)
     if getattr(args, "ede", False):
-        from bdbnn_b200.step import apply_ede
-        apply_ede(model, 40, 120, device="cpu")
+        from oracle.binconv_ref import cpt_tk
+        t, k = cpt_tk(40, 120)
+        for m in model.modules():                 # train.py:409-415
+            if isinstance(m, torch.nn.Conv2d):
+                m.k, m.t = k, t
     teacher = None
-    cfg = step_config(args.workload)
-    if cfg.teacher_student:
+    kd = args.workload == "kurt_kd"
+    if kd:
         teacher = build_teacher(args.model)
-    step = TrainStep(model, make_optimizer(model, dataset, fused=False), cfg, teacher=teacher, ops=RefOps)
+    hooked = S.ref_hooked_weights(model) if kd else {}
+    opt = S.ref_make_optimizer(model, dataset, 0.1 if dataset != "imagenet" else 1e-3)
+    # the oracle's restatement of the reference loop body (oracle/step_ref.py; pinned to the reference's own
+    # train() / train_teacher_student() by tests/test_ref_train.py)
+    step = lambda xs, ys: S.ref_train_step(model, opt, xs, ys, hooked=hooked, targets=[1.8] * len(hooked),
+                                           kurt_on=kd, teacher=teacher, alpha=0.9, beta=200.0)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(ishape, generator=g)
     y = torch.randint(0, ncls, (batch,), generator=g)
@@ -233,6 +247,12 @@ def cpu_reference_run(args, steps, warmup, batch):
         elif dt > 1.3 * best_t:
             break                                # past the scaling knee: stop probing
     torch.set_num_threads(best_n)
+    while best_t * (steps + max(0, warmup - 1)) > budget_s and batch > 8:
+        batch //= 2                              # bounded sample: a slice of the batch
+        x, y = x[:batch].contiguous(), y[:batch].contiguous()
+        t0 = time.perf_counter()
+        float(step(x, y)["loss"])
+        best_t = time.perf_counter() - t0
     for _ in range(max(0, warmup - 1)):
         step(x, y)
     t0 = time.perf_counter()
@@ -240,7 +260,41 @@ def cpu_reference_run(args, steps, warmup, batch):
         out = step(x, y)
         float(out["loss"])
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads(), batch
+
+
+def eager_gpu_run(args, steps, warmup, batch, dev):
+    """The same-box GPU comparator: the pure-PyTorch oracle modules and the oracle's restated
+    loop body on `dev` — stock eager PyTorch, cuDNN convolutions on +-1 fp32 tensors, ATen elementwise,
+    torch.optim, cudnn.benchmark=True as train.py:368.  None of this repo's kernels run on this path."""
+    from oracle import step_ref as S
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    ishape, ncls, dataset = shapes(args.model, batch)
+    model = build_model(args.model, ref=True).to(dev).to(memory_format=torch.channels_last)
+    kd = args.workload == "kurt_kd"
+    teacher = build_teacher(args.model).to(dev).to(memory_format=torch.channels_last) if kd else None
+    hooked = S.ref_hooked_weights(model) if kd else {}
+    opt = S.ref_make_optimizer(model, dataset, 0.1 if dataset != "imagenet" else 1e-3)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(ishape, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, ncls, (batch,), generator=g).to(dev)
+    step = lambda: S.ref_train_step(model, opt, x, y, hooked=hooked, targets=[1.8] * len(hooked), kurt_on=kd,
+                                    teacher=teacher, alpha=0.9, beta=200.0)
+    for _ in range(max(3, warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    float(out["loss"])
+    ms = e0.elapsed_time(e1) / steps
+    del model, opt, teacher
+    torch.cuda.empty_cache()
+    return batch / (ms / 1e3), ms
 
 
 def main():
@@ -256,16 +310,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = min(args.cpu_batch, batch)
-        v, ms, cores = cpu_reference_run(args, max(1, args.steps), max(0, args.warmup), cb)
+        cb = min(args.cpu_batch or batch, batch)
+        v, ms, cores, cb = cpu_reference_run(args, max(1, args.steps), max(0, args.warmup), cb)
         line = {"impl": "reference", "metric": "images/sec", "value": round(v, 3), "unit": "images/sec",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": workload, "parallelism": "cpu"},
+                "data": "synthetic", "config": {"workload": workload, "parallelism": "cpu",
+                                                "same_config": cb == batch, "cpu_batch": cb},
                 "cpu_baseline": {"value": round(v, 3), "unit": "images/sec", "cores": cores, "kind": "port",
-                                 "sample": f"{args.steps} steps of a {cb}-image slice of the {batch}-image batch "
-                                           "(pure-PyTorch oracle of the restated train.py step; the reference's "
-                                           "own train.py cannot run, SURVEY.md §0.3)"},
+                                 "sample": (f"{args.steps} steps of the full {batch}-image batch" if cb == batch else
+                                            f"{args.steps} steps of a {cb}-image slice of the {batch}-image batch") +
+                                           " (oracle/step_ref.py: the reference loop body restated on the pure-PyTorch "
+                                           "oracle modules, pinned to the reference's own train() by "
+                                           "tests/test_ref_train.py; train.py itself needs CUDA and the absent "
+                                           "models/ package, SURVEY.md §0.3)"},
                 "e2e": {"value": round(v, 3), "unit": "images/sec", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -275,6 +333,20 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
+    if args.impl == "reference-gpu":
+        if rank != 0:
+            return
+        dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(dev)
+        v, ms = eager_gpu_run(args, max(1, args.steps), max(3, args.warmup), batch, dev)
+        print(json.dumps({"impl": "reference-gpu", "metric": "images/sec", "value": round(v, 2), "unit": "images/sec",
+                          "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 3),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32 (cuDNN default: TF32 tensor-core convolutions allowed)", "data": "synthetic",
+                          "config": {"workload": workload, "parallelism": "dp1",
+                                     "path": "oracle modules on cuda: stock eager PyTorch (cuDNN + ATen + torch.optim)"},
+                          "gpu_launches": 0}))
+        return
     import torch.distributed as dist
     from bdbnn_b200 import _lib
     from bdbnn_b200.ddp import FlatGradOptimizerShim, GradAllReduce
@@ -407,10 +479,50 @@ def main():
                "d2h_bytes_per_step": 4,
                "note": "pinned fp32 batch, H2D double-buffered on a copy stream, loss read back every step"}
 
+    # ---- secondary value: the fp32-class gradient operand mode (bf16 hi+lo pair, two MMAs per K step) -------
+    from bdbnn_b200.functional import grad_mode
+    secondary = None
+    if not args.no_secondary and not args.profile_mode and grad_mode()[0] == "fp16s":
+        os.environ["BDBNN_GRAD_MODE"] = "bf16x2"
+        try:
+            for _ in range(3):
+                step(x_dev, y_dev)
+            barrier()
+            ns = max(3, min(10, args.steps))
+            gc.collect(); gc.disable()
+            e0.record()
+            for _ in range(ns):
+                step(x_dev, y_dev)
+            e1.record()
+            barrier()
+            gc.enable()
+            ms2 = max_over_ranks(e0.elapsed_time(e1)) / ns
+            secondary = {"grad_mode": "bf16x2", "value": round(batch * world / (ms2 / 1e3), 2), "unit": "images/sec",
+                         "ms_per_step": round(ms2, 3), "steps": ns,
+                         "note": "gradient operand = bf16 hi+lo pair (fp32-class, 5e-5 of max|grad| vs fp64; "
+                                 "tests/test_gpu_tc.py), everything else identical"}
+        finally:
+            os.environ["BDBNN_GRAD_MODE"] = "fp16s"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- same-box GPU comparator: stock eager PyTorch on the oracle modules (N=1 only) ----------------------
+    eager = None
+    if world == 1 and not args.no_eager_gpu and not args.profile_mode:
+        del step, model, opt
+        torch.cuda.empty_cache()
+        try:
+            ve, mse = eager_gpu_run(args, max(3, min(10, args.steps)), 3, batch, dev)
+            eager = {"value": round(ve, 2), "unit": "images/sec", "ms_per_step": round(mse, 3),
+                     "path": "pure-PyTorch oracle modules on cuda: eager cuDNN convs on +-1 fp32 tensors (TF32 allowed, "
+                             "cudnn.benchmark=True as train.py:368) + ATen elementwise + torch.optim; same batch, "
+                             "same loop body (oracle/step_ref.py)",
+                     "speedup_value_over_eager": round(value / ve, 3)}
+        except Exception as exc:                      # the comparator must never take the bench line down
+            eager = {"error": repr(exc)[:300]}
 
     # ---- roofline of the dominant kernel family ---------------------------------------------------
     peak, peak_src = peaks()
@@ -437,13 +549,13 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cb = min(args.cpu_batch, batch)
-        v, ms, cores = cpu_reference_run(args, 2, 1, cb)
+        cb = min(args.cpu_batch or batch, batch)
+        v, ms, cores, cb = cpu_reference_run(args, 2, 1, cb, budget_s=60.0)
         cpu = {"value": round(v, 3), "unit": "images/sec", "cores": cores, "kind": "port",
-               "sample": f"2 timed steps (1 warm-up) of a {cb}-image slice of the {batch}-image batch, "
-                         f"{ms:.0f} ms/step, oracle CPU step"}
+               "sample": f"2 timed steps (1 warm-up) of " +
+                         (f"the full {batch}-image batch" if cb == batch else f"a {cb}-image slice of the {batch}-image batch") +
+                         f", {ms:.0f} ms/step, oracle CPU step (oracle/step_ref.py)"}
 
-    from bdbnn_b200.functional import grad_mode
     gname = grad_mode()[0]
     dtype_str = {"fp16s": "f16 (+-1 operands exact; gradient = fp16 x per-call 2^e scale), f32 accumulate",
                  "bf16x2": "bf16 (+-1 operands exact; gradient = bf16 hi+lo pair), f32 accumulate",
@@ -458,7 +570,7 @@ def main():
                        else "SGD (train.py:319-321)", "conv_impl": args.conv_impl or "auto", "grad_mode": gname,
                        "l2_policy": "per-step working set (>3 GB of activations) exceeds the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "kernels": kernels, "cpu_baseline": cpu}
+            "kernels": kernels, "cpu_baseline": cpu, "eager_gpu": eager, "secondary": secondary}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

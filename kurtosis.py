@@ -1,2 +1,3 @@
-"""Drop-in for the reference's kurtosis.py (imported at train.py:29): same class name, fused kernel."""
-from bdbnn_b200.losses import KurtosisWeight  # noqa: F401
+"""Drop-in for the reference's kurtosis.py — `from kurtosis import KurtosisWeight, RidgeRegularization,
+WeightRegularization` (train.py:29): same three class names; KurtosisWeight runs on the fused kernel."""
+from bdbnn_b200.losses import KurtosisWeight, RidgeRegularization, WeightRegularization  # noqa: F401

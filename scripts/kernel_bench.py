@@ -34,6 +34,68 @@ def timeit(fn, flush, iters=5):
     return ts[len(ts) // 2]
 
 
+def loss_kernels(a, flush, peak):
+    """kurtosis (19 hooked ResNet-18 weights, kurtosis.py:23-39), KD logits ([256,1000], KD_loss.py:16-43) and
+    KD layer (16 weight pairs, KD_loss.py:52-67) kernels: fwd and bwd launches timed separately."""
+    if a.layers and "losses" not in a.layers.split(","):
+        return []
+    import ctypes as C
+    L = _lib.lib()
+    ck = _lib.check
+    st = _stream()
+    from bdbnn_b200.functional import _ptr_array
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = []
+    for cin, cout, n3, ds in ((64, 64, 4, False), (64, 128, 1, True), (128, 128, 3, False), (128, 256, 1, True),
+                              (256, 256, 3, False), (256, 512, 1, True), (512, 512, 3, False)):
+        shapes += [(cout, cin, 3, 3)] * n3
+        if ds:
+            shapes.append((cout, cin, 1, 1))
+    ws = [torch.randn(sh, device="cuda", generator=g) * 0.05 for sh in shapes]
+    n = len(ws)
+    tot = sum(w.numel() for w in ws)
+    numel = (C.c_int64 * n)(*[w.numel() for w in ws])
+    tg = (C.c_float * n)(*([1.8] * n))
+    moments = torch.empty(n * 8, dtype=torch.float64, device="cuda")
+    kurt, loss = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    gout = torch.ones(n, device="cuda")
+    grads = [torch.empty_like(w) for w in ws]
+    wp, gp = _ptr_array(ws), _ptr_array(grads)
+    rows = []
+
+    def add(name, fn, nbytes, note):
+        fn(); torch.cuda.synchronize()
+        ms = timeit(fn, flush, iters=9)
+        gbs = nbytes / 1e9 / (ms / 1e3)
+        rows.append({"layer": "losses", "kernel": name, "ms": round(ms, 4), "alg_MB": round(nbytes / 1e6, 2),
+                     "GBs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4), "TFLOPs": None, "note": note})
+        print(rows[-1], flush=True)
+
+    add("kurtosis_multi_fwd", lambda: ck(L.bdbnn_kurtosis_multi_fwd(wp, numel, tg, n, _p(moments), _p(kurt), _p(loss), st), "k"),
+        4 * tot, f"{n} tensors, {tot} weights: moments + finalize (2 launches)")
+    add("kurtosis_multi_bwd", lambda: ck(L.bdbnn_kurtosis_multi_bwd(wp, numel, tg, n, _p(moments), _p(gout), gp, 0, st), "k"),
+        8 * tot, "closed-form gradient, read W + write grad")
+    N, Cc = a.batch, 1000
+    s_, t_ = torch.randn(N, Cc, device="cuda", generator=g), torch.randn(N, Cc, device="cuda", generator=g)
+    row, l0, gr = torch.empty(N, device="cuda"), torch.empty((), device="cuda"), torch.empty(N, Cc, device="cuda")
+    add("kd_logits_fwd_bwd", lambda: ck(L.bdbnn_kd_logits_fwd_bwd(_p(s_), _p(t_), N, Cc, _p(row), _p(l0), _p(gr), st), "kd"),
+        12 * N * Cc, f"[{N},{Cc}] student/teacher logits: loss + gradient (2 launches); latency-bound")
+    w3 = [w for w in ws if w.shape[-1] == 3]
+    wt3 = [torch.randn_like(w) * 0.05 for w in w3]
+    n3 = len(w3)
+    tot3 = sum(w.numel() for w in w3)
+    numel3 = (C.c_int64 * n3)(*[w.numel() for w in w3])
+    partial = torch.empty(n3, dtype=torch.float64, device="cuda")
+    g3 = [torch.empty_like(w) for w in w3]
+    one = torch.ones(1, device="cuda")
+    sp, tp, g3p = _ptr_array(w3), _ptr_array(wt3), _ptr_array(g3)
+    add("kd_layer_multi_fwd", lambda: ck(L.bdbnn_kd_layer_multi_fwd(sp, tp, numel3, n3, _p(partial), _p(l0), st), "kl"),
+        8 * tot3, f"{n3} weight pairs, {tot3} weights")
+    add("kd_layer_multi_bwd", lambda: ck(L.bdbnn_kd_layer_multi_bwd(tp, numel3, n3, _p(one), g3p, 0, st), "kl"),
+        8 * tot3, "read Wt, write grad")
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
@@ -88,11 +150,12 @@ def main():
             nb = int(L.bdbnn_wgrad_tc_workspace_bytes(shp))
             wsb = torch.empty(max(nb, 4) // 4, device="cuda")
             kernels.update({
-                "fwd_tc8": lambda: (ck(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), shp, None, None, st), "f8") if caps & 8 else None),
                 "fwd_tc": lambda: ck(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), FMT, _p(alpha), _p(y), shp, None, None, st), "f"),
                 "grad_pack": lambda: ck(L.bdbnn_grad_pack(_p(gy), _p(gs), n * sh.Ho * sh.Wo, cout, GC, _p(amax), _p(gys), st), "g"),
                 "dgrad_tc": lambda: ck(L.bdbnn_binconv_dgrad_tc(_p(gys), GC, _p(amax), _p(wt), _p(mb), _p(None), _p(gx), shp, st), "d"),
             })
+            if caps & 8:         # fp8 forward only where the kernel takes the shape (never time a no-op)
+                kernels["fwd_tc8"] = lambda: ck(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), shp, None, None, st), "f8")
             if caps & 4:
                 kernels["wgrad_tc"] = lambda: ck(L.bdbnn_binconv_wgrad_tc(_p(gys), GC, _p(amax), _p(xb), _p(wm), _p(igs), _p(gw), shp, _p(wsb), nb, st), "w")
             else:
@@ -121,6 +184,7 @@ def main():
             print(rows[-1], flush=True)
         del x, y, gy, gx, xb, gys
         torch.cuda.empty_cache()
+    rows += loss_kernels(a, flush, peak)
     if a.out:
         json.dump(rows, open(a.out, "w"), indent=1)
 

@@ -18,7 +18,8 @@ def test_resnet20_step_matches_cpu_oracle(ts, ede):
     from bdbnn_b200 import _lib
     from bdbnn_b200.resnet import resnet20
     from bdbnn_b200.step import StepConfig, TrainStep, make_optimizer
-    from oracle.models_ref import RefOps, resnet20_ref
+    from oracle.models_ref import resnet20_fp32, resnet20_ref
+    from oracle import step_ref as S
     torch.manual_seed(0)
     ref = resnet20_ref()
     gpu = resnet20()
@@ -30,7 +31,7 @@ def test_resnet20_step_matches_cpu_oracle(ts, ede):
         from bdbnn_b200.resnet import ResNetCifar
         fp32_conv = lambda i, o, k, s, p: nn.Conv2d(i, o, k, s, p, bias=False)   # fp32 teacher (train.py:250-277)
         torch.manual_seed(1)
-        teacher_ref = ResNetCifar(3, conv_cls=fp32_conv).eval()   # same names/shapes as the student (KD_loss.py:63)
+        teacher_ref = resnet20_fp32().eval()          # same names/shapes as the student (KD_loss.py:63)
         for p in teacher_ref.parameters():
             p.requires_grad = False                   # train.py:275-276
         teacher_gpu = ResNetCifar(3, conv_cls=fp32_conv)
@@ -41,11 +42,18 @@ def test_resnet20_step_matches_cpu_oracle(ts, ede):
     if ede:                                           # train.py:409-415 at epoch 40 of 120
         from bdbnn_b200.step import apply_ede
         t, k = apply_ede(gpu, 40, 120)
-        apply_ede(ref, 40, 120, device="cpu")
+        for m in ref.modules():                       # the oracle's own restatement of train.py:409-415
+            if isinstance(m, torch.nn.Conv2d):
+                m.k, m.t = k.cpu(), t.cpu()
         assert all(m.ede_active for m in gpu.modules() if hasattr(m, "ede_active"))
     cfg = StepConfig(w_kurtosis=True, teacher_student=ts, beta=200.0, alpha=0.9)
-    # lr=0: compare gradients of one step without the update moving the weights
-    s_ref = TrainStep(ref, make_optimizer(ref, "cifar10", lr=0.0), cfg, teacher=teacher_ref, ops=RefOps)
+    # lr=0: compare gradients of one step without the update moving the weights.  The CPU side is the
+    # oracle's independent restatement of the loop body (oracle/step_ref.py, pinned to the reference's own
+    # train() by tests/test_ref_train.py) — not the product's step driver.
+    hooked = S.ref_hooked_weights(ref)
+    s_ref = lambda xs, ys: S.ref_train_step(ref, S.ref_make_optimizer(ref, "cifar10", 0.0), xs, ys, hooked=hooked,
+                                            targets=[1.8] * len(hooked), kurt_on=True, teacher=teacher_ref,
+                                            alpha=0.9, beta=200.0)
     s_gpu = TrainStep(gpu, make_optimizer(gpu, "cifar10", lr=0.0), cfg, teacher=teacher_gpu)
     g = torch.Generator().manual_seed(3)
     x = torch.randn(16, 3, 32, 32, generator=g)

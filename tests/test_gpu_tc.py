@@ -441,3 +441,48 @@ def test_unit_with_in_node_shortcut_equals_two_nodes(geom):
     torch.testing.assert_close(rm1, rm2, rtol=1e-5, atol=1e-6)
     for a, b in zip(g1, g2):
         assert (a - b).abs().max().item() <= 2e-4 * b.abs().max().item() + 1e-7
+
+
+FULL_SIZE = [  # BASELINE.json config-2 layer geometries at N=256 (cin, hw, cout, stride)
+    (64, 56, 64, 1),      # layer1: M = 802 816 accumulations per weight-gradient element
+    (64, 56, 128, 2),     # layer2.0.conv1 (stride 2)
+    (256, 14, 256, 1),    # layer3
+    (512, 7, 512, 1),     # layer4: K = 4608
+]
+
+
+@pytest.mark.parametrize("mode", ["fp16s", "bf16x2"])
+@pytest.mark.parametrize("geom", FULL_SIZE)
+def test_backward_tc_full_size_vs_fp64_conv_on_gpu(geom, mode, monkeypatch):
+    """dgrad / wgrad at the sizes the headline times (N=256) against a float64 reference computed on the GPU
+    with torch.nn.grad.conv2d_input / conv2d_weight of the spec's +-1 / alpha operands.
+    Two error measures per gradient: max error relative to max|ref| (tolerance of the mode, as in the small
+    tests) and — because a max-normalised bound says nothing about small elements — the relative L2 error
+    over ALL elements, which bounds the average damage of fp16s flushing values far below the per-call max."""
+    from bdbnn_b200.functional import binconv2d
+    monkeypatch.setenv("BDBNN_GRAD_MODE", mode)
+    cin, hw, cout, stride = geom
+    g = torch.Generator(device="cuda").manual_seed(5 + cin + cout)
+    x = (torch.randn(256, cin, hw, hw, device="cuda", generator=g) * 1.2).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.6
+    xd, wd = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    y = binconv2d(xd, wd, stride, 1, "tc")
+    # heavy-tailed upstream gradient (a few large entries, many tiny ones) like a real backward signal
+    gy = torch.randn(y.shape, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    gy = gy * torch.exp(2.0 * torch.randn(y.shape[0], 1, 1, 1, device="cuda", generator=g)) * 1e-3
+    y.backward(gy)
+    alpha = w.double().abs().mean(dim=(1, 2, 3))
+    xb = torch.where(x >= 0, 1.0, -1.0).double()
+    wb = torch.where(w >= 0, 1.0, -1.0).double() * alpha.view(-1, 1, 1, 1)
+    gy64 = gy.double()
+    gx_ref = torch.nn.grad.conv2d_input(x.shape, wb, gy64, stride=stride, padding=1) * (x.abs() <= 1)
+    gw_ref = torch.nn.grad.conv2d_weight(xb, w.shape, gy64, stride=stride, padding=1) * (w.abs() <= 1)
+    tol_max = GRAD_TOL[mode]
+    tol_l2 = {"fp16s": 1e-3, "bf16x2": 2e-5}[mode]
+    for name, got, ref in (("gx", xd.grad, gx_ref), ("gw", wd.grad, gw_ref)):
+        err = (got.double() - ref)
+        e_max = err.abs().max().item() / (ref.abs().max().item() + 1e-300)
+        e_l2 = err.norm().item() / (ref.norm().item() + 1e-300)
+        assert e_max <= tol_max, (name, "max", e_max)
+        assert e_l2 <= tol_l2, (name, "l2", e_l2)
+    assert (xd.grad[x.abs() > 1] == 0).all() and (wd.grad[w.abs() > 1] == 0).all()
