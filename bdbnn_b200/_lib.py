@@ -37,6 +37,10 @@ SIGNATURES = {
     "bdbnn_optim_adam_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_float, c_int64, ctypes.c_float, _P]),
     "bdbnn_optim_sgd_multi": (c_int, [_P, _P, _P, _P, _P, _P, c_int, ctypes.c_float, c_int, ctypes.c_float, _P]),
+    "bdbnn_optim_step_inc": (c_int, [_P, _P]),
+    "bdbnn_optim_adam_multi_graph": (c_int, [_P, _P, _P, _P, _P, _P, c_int, ctypes.c_float, ctypes.c_float,
+                                             ctypes.c_float, _P, _P, ctypes.c_float, _P]),
+    "bdbnn_optim_sgd_multi_graph": (c_int, [_P, _P, _P, _P, _P, c_int, ctypes.c_float, _P, ctypes.c_float, _P]),
     "bdbnn_real_conv_pack": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int] + [_P] * 8),
     "bdbnn_stem_supported": (c_int, [c_int, c_int, c_int]),
     "bdbnn_stem_xw_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -62,6 +66,9 @@ SIGNATURES = {
     "bdbnn_kd_layer_multi_bwd": (c_int, [_P, _P, c_int, _P, _P, c_int, _P]),
     "bdbnn_bn_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, ctypes.c_float, ctypes.c_float] + [_P] * 12 + [c_int, c_int, _P]),
     "bdbnn_bn_bwd_pack": (c_int, [_P] * 7 + [c_int64, c_int, c_int] + [_P] * 8),
+    "bdbnn_bn_fwd_i16": (c_int, [_P] * 5 + [c_int64, c_int, ctypes.c_float, ctypes.c_float] + [_P] * 12 + [c_int, _P]),
+    "bdbnn_bn_bwd_pack_i16": (c_int, [_P] * 8 + [c_int64, c_int, c_int] + [_P] * 8),
+    "bdbnn_binconv_fwd_tc_i16": (c_int, [_P, _P, c_int, _P, _P, _SH, _P, _P, _P]),
     "bdbnn_bn_pool_fwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [ctypes.c_float, ctypes.c_float] + [_P] * 14 + [c_int, c_int, _P]),
     "bdbnn_bn_pool_bwd": (c_int, [_P] * 9 + [c_int] * 9 + [_P] * 9),
     "bdbnn_maxpool_fwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [_P]),

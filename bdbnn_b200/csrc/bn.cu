@@ -34,13 +34,26 @@ __device__ __forceinline__ float bn_bf16_round(float v) {
   return __uint_as_float(bn_pack_bf16x2(0.f, v) & 0xffff0000u);
 }
 
+// y operand of the fused units: fp32 (y itself) or the exact int16 accumulator y_int with y = alpha[c]*y_int
+// (bdbnn_binconv_fwd_tc_i16).  The loaders return y_int as floats for I16 — callers fold alpha into their
+// per-channel constants, which is exact in the same sense (one fp32 multiply either way).
+template <bool I16>
+__device__ __forceinline__ float4 load_y4(const void* __restrict__ y, int64_t i) {
+  if (I16) {
+    const uint2 r = __ldcs(reinterpret_cast<const uint2*>(y) + i);
+    return make_float4(float(int16_t(r.x & 0xffffu)), float(int16_t(r.x >> 16)), float(int16_t(r.y & 0xffffu)),
+                       float(int16_t(r.y >> 16)));
+  }
+  return __ldcs(reinterpret_cast<const float4*>(y) + i);
+}
+
 // Per-channel (sum a, sum b, max c) over pixels; thread = one float4 channel group, strided over pixels.
 // Block partials go through shared-memory atomics, then one double atomicAdd per channel per block.
-template <bool BWD>
+template <bool BWD, bool I16 = false>
 __global__ void __launch_bounds__(kBnThreads)
-bn_reduce_kernel(const float4* __restrict__ p0, const float4* __restrict__ p1, const float* __restrict__ mean,
+bn_reduce_kernel(const float4* __restrict__ p0, const void* __restrict__ p1, const float* __restrict__ mean,
                  const float* __restrict__ invstd, int64_t n_pix, int C4, double* __restrict__ sums,
-                 uint32_t* __restrict__ maxbits) {
+                 uint32_t* __restrict__ maxbits, const float* __restrict__ alpha = nullptr) {
   extern __shared__ float sh[];               // [3][C]
   const int C = C4 * 4;
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sh[i] = 0.f;
@@ -53,16 +66,27 @@ bn_reduce_kernel(const float4* __restrict__ p0, const float4* __restrict__ p1, c
   if (BWD) {
     mu = *reinterpret_cast<const float4*>(mean + c4 * 4);
     is = *reinterpret_cast<const float4*>(invstd + c4 * 4);
+    if (I16) {     // yhat = (alpha*yi - mean)*invstd = (yi - mean/alpha) * (alpha*invstd); alpha == 0 -> yhat = -mean*invstd
+      const float4 al = *reinterpret_cast<const float4*>(alpha + c4 * 4);
+      // keep the exact form: yhat = yi*(alpha*is) - mean*is, expressed through (v - mu')*is' with v = yi
+      mu = make_float4(mu.x * is.x, mu.y * is.y, mu.z * is.z, mu.w * is.w);           // mean*invstd
+      is = make_float4(al.x * is.x, al.y * is.y, al.z * is.z, al.w * is.w);           // alpha*invstd
+    }
   }
   float4 sa = make_float4(0, 0, 0, 0), sb = sa, mx = sa;
 #pragma unroll 8
   for (int64_t p = gtid / C4; p < n_pix; p += p_step) {
     const float4 u = __ldcs(p0 + p * C4 + c4);
     if (BWD) {   // u = gz, v = y:  a = gz, b = gz * yhat, c = |gz|
-      const float4 v = __ldg(p1 + p * C4 + c4);
+      const float4 v = load_y4<I16>(p1, p * C4 + c4);
       sa.x += u.x; sa.y += u.y; sa.z += u.z; sa.w += u.w;
-      sb.x += u.x * ((v.x - mu.x) * is.x); sb.y += u.y * ((v.y - mu.y) * is.y);
-      sb.z += u.z * ((v.z - mu.z) * is.z); sb.w += u.w * ((v.w - mu.w) * is.w);
+      if (I16) {
+        sb.x += u.x * fmaf(v.x, is.x, -mu.x); sb.y += u.y * fmaf(v.y, is.y, -mu.y);
+        sb.z += u.z * fmaf(v.z, is.z, -mu.z); sb.w += u.w * fmaf(v.w, is.w, -mu.w);
+      } else {
+        sb.x += u.x * ((v.x - mu.x) * is.x); sb.y += u.y * ((v.y - mu.y) * is.y);
+        sb.z += u.z * ((v.z - mu.z) * is.z); sb.w += u.w * ((v.w - mu.w) * is.w);
+      }
     } else {     // u = y:  a = y, b = y*y, c = |y|
       sa.x += u.x; sa.y += u.y; sa.z += u.z; sa.w += u.w;
       sb.x += u.x * u.x; sb.y += u.y * u.y; sb.z += u.z * u.z; sb.w += u.w * u.w;
@@ -91,7 +115,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n_pi
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ a,
                                    float* __restrict__ b, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float momentum) {
+                                   float* __restrict__ running_var, float momentum,
+                                   const float* __restrict__ alpha_i16 = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double n = double(n_pix);
@@ -103,7 +128,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n_pi
   mean[c] = mf;
   invstd[c] = is;
   const float av = gamma[c] * is;
-  a[c] = av;
+  a[c] = alpha_i16 != nullptr ? av * alpha_i16[c] : av;     // int16 operand: z = y_int * (a*alpha) + b
   b[c] = beta[c] - mf * av;
   if (running_mean != nullptr) {
     const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
@@ -113,9 +138,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n_pi
 }
 
 // z = y*a + b (+ residual); optionally the sign / STE-mask bits and the +-1 16-bit copy of z.
-template <bool PACK>
+template <bool PACK, bool I16 = false>
 __global__ void __launch_bounds__(kBnThreads)
-bn_apply_add_pack_kernel(const float4* __restrict__ y, const float4* __restrict__ res,
+bn_apply_add_pack_kernel(const void* __restrict__ y, const float4* __restrict__ res,
                          const float* __restrict__ a, const float* __restrict__ b, int64_t n4, int C4,
                          float4* __restrict__ z, uint32_t* __restrict__ sign_bits,
                          uint32_t* __restrict__ mask_bits, uint2* __restrict__ xb4, uint32_t* __restrict__ xb8,
@@ -130,7 +155,7 @@ bn_apply_add_pack_kernel(const float4* __restrict__ y, const float4* __restrict_
   const float4 av = *reinterpret_cast<const float4*>(a + c4 * 4);
   const float4 bv = *reinterpret_cast<const float4*>(b + c4 * 4);
   for (; i < n4; i += nthreads) {
-    const float4 v = __ldcs(y + i);
+    const float4 v = load_y4<I16>(y, i);         // I16: `a` already carries alpha (a = gamma*invstd*alpha)
     float4 o = make_float4(fmaf(v.x, av.x, bv.x), fmaf(v.y, av.y, bv.y), fmaf(v.z, av.z, bv.z),
                            fmaf(v.w, av.w, bv.w));
     if (res != nullptr) {
@@ -167,7 +192,7 @@ __global__ void bn_bwd_bound_kernel(const double* __restrict__ sums, const uint3
                                     const float* __restrict__ gamma, const float* __restrict__ gscale,
                                     float4* __restrict__ consts, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, uint32_t* __restrict__ amax_bits,
-                                    float gz_mult = 1.0f) {
+                                    float gz_mult = 1.0f, const float* __restrict__ alpha_i16 = nullptr) {
   __shared__ float red[32];
   float bound = 0.f;
   const double n = double(n_pix);
@@ -178,7 +203,15 @@ __global__ void bn_bwd_bound_kernel(const double* __restrict__ sums, const uint3
     const float m1 = float(sums[c] / n), m2 = float(sums[C + c] / n);
     const float is = invstd[c], mu = mean[c];
     const float A = gamma[c] * is * gscale[c];
-    consts[c] = make_float4(m1, m2 * is, mu, A);
+    // pack kernel: (gz - k.x - (v - k.z)*k.y) * k.w with v = y; for the int16 operand v = y_int, so
+    // (y - mu)*m2*is = (y_int - mu/alpha) * (alpha*m2*is)   (alpha == 0: y == 0 everywhere, term = -mu*m2*is)
+    if (alpha_i16 != nullptr) {
+      const float al = alpha_i16[c];
+      if (al != 0.f) consts[c] = make_float4(m1, al * m2 * is, mu / al, A);
+      else           consts[c] = make_float4(m1 - mu * m2 * is, 0.f, 0.f, A);
+    } else {
+      consts[c] = make_float4(m1, m2 * is, mu, A);
+    }
     const float ymax = __uint_as_float(ymax_bits[c]), gmax = __uint_as_float(gmax_bits[c]);
     // gz_mult: how many gradient values can land on one position (pooled stem: windows per pixel)
     bound = fmaxf(bound, fabsf(A) * (gz_mult * gmax + fabsf(m1) + (ymax + fabsf(mu)) * is * fabsf(m2)));
@@ -194,9 +227,9 @@ __global__ void bn_bwd_bound_kernel(const double* __restrict__ sums, const uint3
 }
 
 // gys = 16-bit operand of the conv backward, straight from gz and y.
-template <int MODE>
+template <int MODE, bool I16 = false>
 __global__ void __launch_bounds__(kBnThreads)
-bn_bwd_pack_kernel(const float4* __restrict__ gz, const float4* __restrict__ y, const float4* __restrict__ consts,
+bn_bwd_pack_kernel(const float4* __restrict__ gz, const void* __restrict__ y, const float4* __restrict__ consts,
                    const uint32_t* __restrict__ amax_bits, int64_t n4, int C4, uint16_t* __restrict__ out) {
   constexpr int HALVES = MODE == 2 ? 2 : 1;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;       // multiple of C4
@@ -209,7 +242,7 @@ bn_bwd_pack_kernel(const float4* __restrict__ gz, const float4* __restrict__ y, 
   const int64_t pix_step = nthreads / C4;
   for (; i < n4; i += nthreads, pix += pix_step) {
     const float4 g = __ldcs(gz + i);
-    const float4 v = __ldcs(y + i);
+    const float4 v = load_y4<I16>(y, i);
     const float a0 = (g.x - k0.x - (v.x - k0.z) * k0.y) * k0.w * up;
     const float a1 = (g.y - k1.x - (v.y - k1.z) * k1.y) * k1.w * up;
     const float a2 = (g.z - k2.x - (v.z - k2.z) * k2.y) * k2.w * up;
@@ -264,12 +297,14 @@ static int bn_dims_ok(int64_t n_pix, int32_t C, bool pack) {
   return BDBNN_OK;
 }
 
-extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* gamma, const float* beta,
-                            int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
-                            float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean,
-                            float* invstd, float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits,
-                            uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, int32_t stats_ready, void* stream) {
+static int bn_fwd_impl(const void* y, const float* alpha_i16, const float* residual, const float* gamma,
+                       const float* beta, int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
+                       float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean, float* invstd,
+                       float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits, uint16_t* xb,
+                       uint8_t* xb_fp8, int32_t fmt, int32_t stats_ready, void* stream) {
   const bool pack = sign_bits != nullptr;
+  const bool i16 = alpha_i16 != nullptr;
+  BDBNN_REQUIRE(!i16 || stats_ready, "bn_fwd_i16: the statistics must come from the conv epilogue (stats_ready = 1)");
   int rc = bn_dims_ok(n_pix, C, pack);
   if (rc) return rc;
   BDBNN_REQUIRE(y && gamma && beta && sums_ws && ymax_bits && mean && invstd && ab_ws && z, "bn_fwd: NULL pointer");
@@ -280,36 +315,65 @@ extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* 
   if (!stats_ready) {          // else: sums_ws / ymax_bits were filled by the conv's epilogue
     BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
     BDBNN_CUDA(cudaMemsetAsync(ymax_bits, 0, size_t(C) * sizeof(uint32_t), st));
-    rc = bn_stats_launch(y, n_pix, C, sums_ws, ymax_bits, st);
+    rc = bn_stats_launch(static_cast<const float*>(y), n_pix, C, sums_ws, ymax_bits, st);
     if (rc) return rc;
   }
   float* a = ab_ws;
   float* b = ab_ws + C;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_ws, n_pix, C, eps, gamma, beta, mean, invstd, a, b,
-                                                       running_mean, running_var, momentum);
+                                                       running_mean, running_var, momentum, alpha_i16);
   rc = check_launch("bn_finalize_kernel");
   if (rc) return rc;
   const int64_t n4 = n_pix * C4;
   const int grid = bn_grid(n4, C4);
+  const float4* r4 = reinterpret_cast<const float4*>(residual);
+  float4* z4 = reinterpret_cast<float4*>(z);
   if (pack) {
     const uint32_t one16 = fmt == BDBNN_FMT_FP16 ? 0x3C00u : 0x3F80u;
-    bn_apply_add_pack_kernel<true><<<grid, kBnThreads, 0, st>>>(
-        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(residual), a, b, n4, C4,
-        reinterpret_cast<float4*>(z), sign_bits, mask_bits, reinterpret_cast<uint2*>(xb),
-        reinterpret_cast<uint32_t*>(xb_fp8), one16);
+    uint2* xb2 = reinterpret_cast<uint2*>(xb);
+    uint32_t* xb8 = reinterpret_cast<uint32_t*>(xb_fp8);
+    if (i16)
+      bn_apply_add_pack_kernel<true, true><<<grid, kBnThreads, 0, st>>>(y, r4, a, b, n4, C4, z4, sign_bits, mask_bits,
+                                                                         xb2, xb8, one16);
+    else
+      bn_apply_add_pack_kernel<true, false><<<grid, kBnThreads, 0, st>>>(y, r4, a, b, n4, C4, z4, sign_bits, mask_bits,
+                                                                          xb2, xb8, one16);
   } else {
-    bn_apply_add_pack_kernel<false><<<grid, kBnThreads, 0, st>>>(
-        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(residual), a, b, n4, C4,
-        reinterpret_cast<float4*>(z), nullptr, nullptr, nullptr, nullptr, 0u);
+    if (i16)
+      bn_apply_add_pack_kernel<false, true><<<grid, kBnThreads, 0, st>>>(y, r4, a, b, n4, C4, z4, nullptr, nullptr,
+                                                                          nullptr, nullptr, 0u);
+    else
+      bn_apply_add_pack_kernel<false, false><<<grid, kBnThreads, 0, st>>>(y, r4, a, b, n4, C4, z4, nullptr, nullptr,
+                                                                           nullptr, nullptr, 0u);
   }
   return check_launch("bn_apply_add_pack_kernel");
 }
 
-extern "C" int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* mean, const float* invstd,
-                                 const float* gamma, const float* gscale, const uint32_t* ymax_bits,
-                                 int64_t n_pix, int32_t C, int32_t grad_mode, double* sums_ws,
-                                 uint32_t* gmax_bits, float* consts_ws, float* dgamma, float* dbeta,
-                                 uint32_t* amax_bits, uint16_t* gys, void* stream) {
+extern "C" int bdbnn_bn_fwd(const float* y, const float* residual, const float* gamma, const float* beta,
+                            int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
+                            float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean,
+                            float* invstd, float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits,
+                            uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, int32_t stats_ready, void* stream) {
+  return bn_fwd_impl(y, nullptr, residual, gamma, beta, n_pix, C, eps, momentum, running_mean, running_var, sums_ws,
+                     ymax_bits, mean, invstd, ab_ws, z, sign_bits, mask_bits, xb, xb_fp8, fmt, stats_ready, stream);
+}
+
+extern "C" int bdbnn_bn_fwd_i16(const int16_t* y_int, const float* alpha, const float* residual, const float* gamma,
+                                const float* beta, int64_t n_pix, int32_t C, float eps, float momentum,
+                                float* running_mean, float* running_var, double* sums_ws, uint32_t* ymax_bits,
+                                float* mean, float* invstd, float* ab_ws, float* z, uint32_t* sign_bits,
+                                uint32_t* mask_bits, uint16_t* xb, uint8_t* xb_fp8, int32_t fmt, void* stream) {
+  BDBNN_REQUIRE(alpha != nullptr, "bn_fwd_i16: NULL alpha");
+  return bn_fwd_impl(y_int, alpha, residual, gamma, beta, n_pix, C, eps, momentum, running_mean, running_var, sums_ws,
+                     ymax_bits, mean, invstd, ab_ws, z, sign_bits, mask_bits, xb, xb_fp8, fmt, 1, stream);
+}
+
+static int bn_bwd_pack_impl(const float* gz, const void* y, const float* alpha_i16, const float* mean,
+                            const float* invstd, const float* gamma, const float* gscale, const uint32_t* ymax_bits,
+                            int64_t n_pix, int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits,
+                            float* consts_ws, float* dgamma, float* dbeta, uint32_t* amax_bits, uint16_t* gys,
+                            void* stream) {
+  const bool i16 = alpha_i16 != nullptr;
   int rc = bn_dims_ok(n_pix, C, false);
   if (rc) return rc;
   BDBNN_REQUIRE(gz && y && mean && invstd && gamma && gscale && ymax_bits && sums_ws && gmax_bits && consts_ws &&
@@ -320,27 +384,59 @@ extern "C" int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* m
   const int C4 = C / 4;
   BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
   BDBNN_CUDA(cudaMemsetAsync(gmax_bits, 0, size_t(C) * sizeof(uint32_t), st));
-  bn_reduce_kernel<true><<<bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3), kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
-      reinterpret_cast<const float4*>(gz), reinterpret_cast<const float4*>(y), mean, invstd, n_pix, C4, sums_ws,
-      gmax_bits);
+  const int rgrid = bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3);
+  if (i16)
+    bn_reduce_kernel<true, true><<<rgrid, kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+        reinterpret_cast<const float4*>(gz), y, mean, invstd, n_pix, C4, sums_ws, gmax_bits, alpha_i16);
+  else
+    bn_reduce_kernel<true, false><<<rgrid, kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+        reinterpret_cast<const float4*>(gz), y, mean, invstd, n_pix, C4, sums_ws, gmax_bits, nullptr);
   rc = check_launch("bn_reduce_kernel<bwd>");
   if (rc) return rc;
   bn_bwd_bound_kernel<<<1, 256, 0, st>>>(sums_ws, gmax_bits, ymax_bits, n_pix, C, mean, invstd, gamma, gscale,
-                                         reinterpret_cast<float4*>(consts_ws), dgamma, dbeta, amax_bits);
+                                         reinterpret_cast<float4*>(consts_ws), dgamma, dbeta, amax_bits, 1.0f,
+                                         alpha_i16);
   rc = check_launch("bn_bwd_bound_kernel");
   if (rc) return rc;
   const int64_t n4 = n_pix * C4;
   const int grid = bn_grid(n4, C4);
   const float4* g4 = reinterpret_cast<const float4*>(gz);
-  const float4* y4 = reinterpret_cast<const float4*>(y);
   const float4* k4 = reinterpret_cast<const float4*>(consts_ws);
-  if (grad_mode == BDBNN_GRAD_FP16S)
-    bn_bwd_pack_kernel<3><<<grid, kBnThreads, 0, st>>>(g4, y4, k4, amax_bits, n4, C4, gys);
-  else if (grad_mode == BDBNN_GRAD_BF16X2)
-    bn_bwd_pack_kernel<2><<<grid, kBnThreads, 0, st>>>(g4, y4, k4, amax_bits, n4, C4, gys);
-  else
-    bn_bwd_pack_kernel<1><<<grid, kBnThreads, 0, st>>>(g4, y4, k4, amax_bits, n4, C4, gys);
+  if (i16) {
+    if (grad_mode == BDBNN_GRAD_FP16S)
+      bn_bwd_pack_kernel<3, true><<<grid, kBnThreads, 0, st>>>(g4, y, k4, amax_bits, n4, C4, gys);
+    else if (grad_mode == BDBNN_GRAD_BF16X2)
+      bn_bwd_pack_kernel<2, true><<<grid, kBnThreads, 0, st>>>(g4, y, k4, amax_bits, n4, C4, gys);
+    else
+      bn_bwd_pack_kernel<1, true><<<grid, kBnThreads, 0, st>>>(g4, y, k4, amax_bits, n4, C4, gys);
+  } else {
+    if (grad_mode == BDBNN_GRAD_FP16S)
+      bn_bwd_pack_kernel<3, false><<<grid, kBnThreads, 0, st>>>(g4, y, k4, amax_bits, n4, C4, gys);
+    else if (grad_mode == BDBNN_GRAD_BF16X2)
+      bn_bwd_pack_kernel<2, false><<<grid, kBnThreads, 0, st>>>(g4, y, k4, amax_bits, n4, C4, gys);
+    else
+      bn_bwd_pack_kernel<1, false><<<grid, kBnThreads, 0, st>>>(g4, y, k4, amax_bits, n4, C4, gys);
+  }
   return check_launch("bn_bwd_pack_kernel");
+}
+
+extern "C" int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* mean, const float* invstd,
+                                 const float* gamma, const float* gscale, const uint32_t* ymax_bits,
+                                 int64_t n_pix, int32_t C, int32_t grad_mode, double* sums_ws,
+                                 uint32_t* gmax_bits, float* consts_ws, float* dgamma, float* dbeta,
+                                 uint32_t* amax_bits, uint16_t* gys, void* stream) {
+  return bn_bwd_pack_impl(gz, y, nullptr, mean, invstd, gamma, gscale, ymax_bits, n_pix, C, grad_mode, sums_ws,
+                          gmax_bits, consts_ws, dgamma, dbeta, amax_bits, gys, stream);
+}
+
+extern "C" int bdbnn_bn_bwd_pack_i16(const float* gz, const int16_t* y_int, const float* alpha, const float* mean,
+                                     const float* invstd, const float* gamma, const float* gscale,
+                                     const uint32_t* ymax_bits, int64_t n_pix, int32_t C, int32_t grad_mode,
+                                     double* sums_ws, uint32_t* gmax_bits, float* consts_ws, float* dgamma,
+                                     float* dbeta, uint32_t* amax_bits, uint16_t* gys, void* stream) {
+  BDBNN_REQUIRE(alpha != nullptr, "bn_bwd_pack_i16: NULL alpha");
+  return bn_bwd_pack_impl(gz, y_int, alpha, mean, invstd, gamma, gscale, ymax_bits, n_pix, C, grad_mode, sums_ws,
+                          gmax_bits, consts_ws, dgamma, dbeta, amax_bits, gys, stream);
 }
 
 // ===================================================================================================

@@ -121,16 +121,25 @@ struct OptTable {
 };
 
 // torch.optim.Adam (L2 weight decay added to the gradient, no amsgrad), blockIdx.y = tensor.
+// step_dev != NULL (CUDA-graph mode): the 1-based step count and the learning rates are read from device memory
+// (step_dev[0]; lr_dev[lr_off + t]), so a captured launch stays valid while both advance between replays.
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const OptTable tab, float beta1, float beta2, float eps, float bc1, float rsqrt_bc2,
-                  float grad_scale) {
+                  float grad_scale, const float* __restrict__ step_dev, const float* __restrict__ lr_dev, int lr_off) {
   const int t = blockIdx.y;
   float* __restrict__ p = tab.p[t];
   const float* __restrict__ g = tab.g[t];
   float* __restrict__ m = tab.m[t];
   float* __restrict__ v = tab.v[t];
   const int64_t n = tab.n[t];
-  const float wd = tab.wd[t], step_size = tab.lr[t] / bc1;
+  float lr = tab.lr[t];
+  if (step_dev != nullptr) {
+    const float step = __ldg(step_dev);
+    bc1 = 1.0f - powf(beta1, step);
+    rsqrt_bc2 = rsqrtf(1.0f - powf(beta2, step));
+    if (lr_dev != nullptr) lr = __ldg(lr_dev + lr_off + t);
+  }
+  const float wd = tab.wd[t], step_size = lr / bc1;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const float pv = p[i];
     const float gv = fmaf(wd, pv, g[i] * grad_scale);
@@ -145,13 +154,14 @@ adam_multi_kernel(const OptTable tab, float beta1, float beta2, float eps, float
 
 // torch.optim.SGD with momentum (dampening 0, no nesterov): buf = g' on the first step, else mu*buf + g'.
 __global__ void __launch_bounds__(256)
-sgd_multi_kernel(const OptTable tab, float momentum, int first_step, float grad_scale) {
+sgd_multi_kernel(const OptTable tab, float momentum, int first_step, float grad_scale,
+                 const float* __restrict__ lr_dev, int lr_off) {
   const int t = blockIdx.y;
   float* __restrict__ p = tab.p[t];
   const float* __restrict__ g = tab.g[t];
   float* __restrict__ m = tab.m[t];
   const int64_t n = tab.n[t];
-  const float wd = tab.wd[t], lr = tab.lr[t];
+  const float wd = tab.wd[t], lr = lr_dev != nullptr ? __ldg(lr_dev + lr_off + t) : tab.lr[t];
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const float pv = p[i];
     const float gv = fmaf(wd, pv, g[i] * grad_scale);
@@ -163,6 +173,8 @@ sgd_multi_kernel(const OptTable tab, float momentum, int first_step, float grad_
     p[i] = pv - lr * d;
   }
 }
+
+__global__ void step_inc_kernel(float* step) { step[0] += 1.0f; }
 
 static unsigned opt_blocks(const int64_t* n, int count) {
   int64_t mx = 1;
@@ -205,16 +217,14 @@ static int fill_table(OptTable& tab, float* const* p, const float* const* g, flo
   return BDBNN_OK;
 }
 
-extern "C" int bdbnn_optim_adam_multi(float* const* params_host, const float* const* grads_host,
-                                      float* const* exp_avg_host, float* const* exp_avg_sq_host,
-                                      const int64_t* numel_host, const float* weight_decay_host,
-                                      const float* lr_host, int32_t count, float beta1, float beta2, float eps,
-                                      int64_t step, float grad_scale, void* stream) {
-  BDBNN_REQUIRE(count >= 0 && step >= 1, "optim_adam: bad count/step");
+static int adam_launch(float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                       float* const* exp_avg_sq_host, const int64_t* numel_host, const float* weight_decay_host,
+                       const float* lr_host, int32_t count, float beta1, float beta2, float eps, int64_t step,
+                       const float* step_dev, const float* lr_dev, float grad_scale, void* stream) {
   BDBNN_REQUIRE(count == 0 || (params_host && grads_host && exp_avg_host && exp_avg_sq_host && numel_host &&
                                weight_decay_host && lr_host), "optim_adam: NULL table");
-  const float bc1 = float(1.0 - pow(double(beta1), double(step)));
-  const float rsqrt_bc2 = float(1.0 / sqrt(1.0 - pow(double(beta2), double(step))));
+  const float bc1 = step_dev ? 1.0f : float(1.0 - pow(double(beta1), double(step)));
+  const float rsqrt_bc2 = step_dev ? 1.0f : float(1.0 / sqrt(1.0 - pow(double(beta2), double(step))));
   for (int off = 0; off < count; off += kOptMaxTensors) {
     const int cnt = count - off < kOptMaxTensors ? count - off : kOptMaxTensors;
     OptTable tab;
@@ -223,17 +233,57 @@ extern "C" int bdbnn_optim_adam_multi(float* const* params_host, const float* co
                         lr_host, off, cnt, true, true);
     if (rc) return rc;
     dim3 grid(opt_blocks(numel_host + off, cnt), unsigned(cnt));
-    adam_multi_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(tab, beta1, beta2, eps, bc1, rsqrt_bc2, grad_scale);
+    adam_multi_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(tab, beta1, beta2, eps, bc1, rsqrt_bc2, grad_scale,
+                                                              step_dev, lr_dev, off);
     rc = check_launch("adam_multi_kernel");
     if (rc) return rc;
   }
   return BDBNN_OK;
 }
 
-extern "C" int bdbnn_optim_sgd_multi(float* const* params_host, const float* const* grads_host,
-                                     float* const* momentum_buf_host, const int64_t* numel_host,
-                                     const float* weight_decay_host, const float* lr_host, int32_t count,
-                                     float momentum, int32_t first_step, float grad_scale, void* stream) {
+extern "C" int bdbnn_optim_adam_multi(float* const* params_host, const float* const* grads_host,
+                                      float* const* exp_avg_host, float* const* exp_avg_sq_host,
+                                      const int64_t* numel_host, const float* weight_decay_host,
+                                      const float* lr_host, int32_t count, float beta1, float beta2, float eps,
+                                      int64_t step, float grad_scale, void* stream) {
+  BDBNN_REQUIRE(count >= 0 && step >= 1, "optim_adam: bad count/step");
+  return adam_launch(params_host, grads_host, exp_avg_host, exp_avg_sq_host, numel_host, weight_decay_host, lr_host,
+                     count, beta1, beta2, eps, step, nullptr, nullptr, grad_scale, stream);
+}
+
+extern "C" int bdbnn_optim_step_inc(float* step_dev, void* stream) {
+  BDBNN_REQUIRE(step_dev != nullptr, "optim_step_inc: NULL step");
+  step_inc_kernel<<<1, 1, 0, cudaStream_t(stream)>>>(step_dev);
+  return check_launch("step_inc_kernel");
+}
+
+extern "C" int bdbnn_optim_adam_multi_graph(float* const* params_host, const float* const* grads_host,
+                                            float* const* exp_avg_host, float* const* exp_avg_sq_host,
+                                            const int64_t* numel_host, const float* weight_decay_host,
+                                            int32_t count, float beta1, float beta2, float eps,
+                                            const float* step_dev, const float* lr_dev, float grad_scale,
+                                            void* stream) {
+  BDBNN_REQUIRE(count >= 0 && step_dev && lr_dev, "optim_adam_graph: bad count / NULL device step or lr");
+  float lr0[kOptMaxTensors] = {0};
+  // learning rates come from lr_dev; the host table is only a placeholder of the right length
+  const float* lr_host = nullptr;
+  float* lr_tmp = nullptr;
+  if (count > kOptMaxTensors) {
+    lr_tmp = static_cast<float*>(calloc(size_t(count), sizeof(float)));
+    BDBNN_REQUIRE(lr_tmp != nullptr, "optim_adam_graph: out of host memory");
+    lr_host = lr_tmp;
+  } else {
+    lr_host = lr0;
+  }
+  const int rc = adam_launch(params_host, grads_host, exp_avg_host, exp_avg_sq_host, numel_host, weight_decay_host,
+                             lr_host, count, beta1, beta2, eps, 1, step_dev, lr_dev, grad_scale, stream);
+  free(lr_tmp);
+  return rc;
+}
+
+static int sgd_launch(float* const* params_host, const float* const* grads_host, float* const* momentum_buf_host,
+                      const int64_t* numel_host, const float* weight_decay_host, const float* lr_host, int32_t count,
+                      float momentum, int32_t first_step, float grad_scale, const float* lr_dev, void* stream) {
   BDBNN_REQUIRE(count >= 0, "optim_sgd: bad count");
   BDBNN_REQUIRE(count == 0 || (params_host && grads_host && numel_host && weight_decay_host && lr_host),
                 "optim_sgd: NULL table");
@@ -246,9 +296,31 @@ extern "C" int bdbnn_optim_sgd_multi(float* const* params_host, const float* con
                         numel_host, weight_decay_host, lr_host, off, cnt, false, momentum != 0.0f);
     if (rc) return rc;
     dim3 grid(opt_blocks(numel_host + off, cnt), unsigned(cnt));
-    sgd_multi_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(tab, momentum, first_step, grad_scale);
+    sgd_multi_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(tab, momentum, first_step, grad_scale, lr_dev, off);
     rc = check_launch("sgd_multi_kernel");
     if (rc) return rc;
   }
   return BDBNN_OK;
+}
+
+extern "C" int bdbnn_optim_sgd_multi(float* const* params_host, const float* const* grads_host,
+                                     float* const* momentum_buf_host, const int64_t* numel_host,
+                                     const float* weight_decay_host, const float* lr_host, int32_t count,
+                                     float momentum, int32_t first_step, float grad_scale, void* stream) {
+  return sgd_launch(params_host, grads_host, momentum_buf_host, numel_host, weight_decay_host, lr_host, count,
+                    momentum, first_step, grad_scale, nullptr, stream);
+}
+
+extern "C" int bdbnn_optim_sgd_multi_graph(float* const* params_host, const float* const* grads_host,
+                                           float* const* momentum_buf_host, const int64_t* numel_host,
+                                           const float* weight_decay_host, int32_t count, float momentum,
+                                           const float* lr_dev, float grad_scale, void* stream) {
+  BDBNN_REQUIRE(count >= 0 && lr_dev, "optim_sgd_graph: bad count / NULL device lr");
+  float* lr_tmp = static_cast<float*>(calloc(size_t(count > 0 ? count : 1), sizeof(float)));
+  BDBNN_REQUIRE(lr_tmp != nullptr, "optim_sgd_graph: out of host memory");
+  // zero-initialised momentum buffers make the first step identical to torch's (buf = mu*0 + g)
+  const int rc = sgd_launch(params_host, grads_host, momentum_buf_host, numel_host, weight_decay_host, lr_tmp, count,
+                            momentum, 0, grad_scale, lr_dev, stream);
+  free(lr_tmp);
+  return rc;
 }

@@ -250,6 +250,7 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
     const int rc2 = launch_tc_conv2(L, MODE, st);
     if (rc2 != BDBNN_ERR_UNSUPPORTED) return rc2;
   }
+  if (L.out_i16) return BDBNN_ERR_UNSUPPORTED;      // int16 output exists in the persistent kernel only
   TcConvParams p;
   memset(&p, 0, sizeof(p));
   p.OW = L.OW; p.OH = L.OH; p.NIMG = L.NIMG;
@@ -421,7 +422,51 @@ extern "C" int bdbnn_tc_supported(const bdbnn_conv_shape* s) {
   // fp8 forward only with 128-byte K rows (Cin % 128 == 0): with 64-channel (64-byte, SWIZZLE_64B) rows
   // each K=32 MMA took ~240 clk on B200 (vs ~105 clk for the 16-bit K=16 MMA), i.e. no gain for layer1
   const bool v2 = s->Cin % 128 == 0 && (s->Cout == 64 || s->Cout % 128 == 0);
-  return BDBNN_TC_FWD | BDBNN_TC_DGRAD | (wgrad_tc_ok(s) ? BDBNN_TC_WGRAD : 0) | (v2 ? BDBNN_TC_FWD8 : 0);
+  // int16 forward output: the persistent kernel must take the 16-bit-operand forward of this shape, and the
+  // integer result must fit (|y_int| <= kh*kw*Cin)
+  bool i16 = s->kh * s->kw * s->Cin <= 32767 && s->Cout <= 512;
+  if (i16) {
+    int32_t plan[12] = {0};
+    i16 = bdbnn_debug_conv_plan(s, 0, 1, plan, 12) == BDBNN_OK && plan[0] == 1;
+    if (i16 && v2) i16 = bdbnn_debug_conv_plan(s, 2, 1, plan, 12) == BDBNN_OK && plan[0] == 1;   // fp8 forward
+  }
+  return BDBNN_TC_FWD | BDBNN_TC_DGRAD | (wgrad_tc_ok(s) ? BDBNN_TC_WGRAD : 0) | (v2 ? BDBNN_TC_FWD8 : 0) |
+         (i16 ? BDBNN_TC_FWD_I16 : 0);
+}
+
+// Forward with the result stored as the exact integer accumulator (int16) — see include/bdbnn.h.
+extern "C" int bdbnn_binconv_fwd_tc_i16(const void* xb, const void* wf, int32_t fmt, const float* alpha,
+                                        int16_t* y_int, const bdbnn_conv_shape* s, double* bn_sums,
+                                        uint32_t* bn_ymax, void* stream) {
+  BDBNN_REQUIRE(fmt == BDBNN_FMT_FP16 || fmt == BDBNN_FMT_BF16 || fmt == -1, "binconv_fwd_tc_i16: bad operand format");
+  int rc = validate_shape(s);
+  if (rc) return rc;
+  BDBNN_REQUIRE(xb && wf && alpha && y_int, "binconv_fwd_tc_i16: NULL pointer");
+  if (!tc_shape_ok(s) || (fmt == -1 && s->Cin % 128 != 0) || s->kh * s->kw * s->Cin > 32767) {
+    set_error("binconv_fwd_tc_i16: shape not supported");
+    return BDBNN_ERR_UNSUPPORTED;
+  }
+  TcConvLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.A = static_cast<const uint16_t*>(xb); L.IH = s->H; L.IW = s->W; L.Kc = s->Cin; L.a_halves = 1; L.in_step = s->stride;
+  L.B = static_cast<const uint16_t*>(wf); L.b_taps = s->kh * s->kw; L.Nout = s->Cout;
+  L.NIMG = s->N; L.OH = s->Ho; L.OW = s->Wo;
+  for (int r = 0; r < s->kh; ++r)
+    for (int q = 0; q < s->kw; ++q) {
+      const int t = r * s->kw + q;
+      L.dh[t] = int8_t(r - s->pad); L.dw[t] = int8_t(q - s->pad); L.tb[t] = uint8_t(t);
+    }
+  L.n_taps = s->kh * s->kw;
+  L.out_step = 1; L.OHf = s->Ho; L.OWf = s->Wo;
+  L.alpha = alpha; L.out = nullptr; L.out_i16 = y_int; L.fmt = fmt;
+  BDBNN_REQUIRE((bn_sums == nullptr) == (bn_ymax == nullptr), "binconv_fwd_tc_i16: bn_sums and bn_ymax go together");
+  BDBNN_REQUIRE(bn_sums == nullptr || s->Cout <= 512, "binconv_fwd_tc_i16: statistics need Cout <= 512");
+  L.bn_sums = bn_sums; L.bn_ymax = bn_ymax;
+  rc = bn_stats_zero(bn_sums, bn_ymax, s->Cout, cudaStream_t(stream));
+  if (rc) return rc;
+  rc = launch_tc_conv2(L, 0, cudaStream_t(stream));
+  if (rc == BDBNN_ERR_UNSUPPORTED) set_error("binconv_fwd_tc_i16: geometry not supported by the persistent kernel");
+  return rc;
 }
 
 extern "C" int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_bf16, int32_t fmt,

@@ -19,7 +19,13 @@
 
 namespace bdbnn {
 
-constexpr int kMaxTS = 4;  // max M tiles (accumulators) per super tile; p.TS is the per-launch value
+// Warp roles: warps 0..7 = epilogue (two groups of four; group g = warp / 4 handles the 32-column blocks cb with
+// (cb & 1) == g, both groups read every TMEM lane quadrant warp % 4), warp 8 = TMA producer, warp 9 = MMA issuer.
+// Two epilogue groups double the loads / stores in flight per SM: with four warps the dgrad epilogue of the
+// 56x56 layers (reads the STE mask and the shortcut gradient, writes gx: 0.5 GB per launch) was latency-bound
+// at ~16 KB in flight per SM and left the MMA pipe idle more than half of the kernel (ncu: tensor pipe 17 %).
+constexpr int kTc2Threads = 320;
+constexpr int kEpiWarps = 8;
 
 struct TcConv2Params {
   int32_t OW, OH, NIMG;
@@ -38,6 +44,7 @@ struct TcConv2Params {
   int32_t out_step, out_off_h, out_off_w, OHf, OWf;
   int32_t Nout, BN, NB, TS;
   int32_t stages;
+  int32_t cg;                // CTAs per MMA: 1, or 2 (CTA pair, M = 256 cta_group::2 MMAs; b_bytes = half the N tile)
   int32_t dbg;               // BDBNN_TC_DBG experiment bits: 1 = no global stores, 2 = no TMEM loads, 4 = no MMAs
   uint32_t stage_bytes, b_bytes;
   int32_t fmt;               // BDBNN_FMT_* or -1 (fp8)
@@ -48,6 +55,7 @@ struct TcConv2Params {
   const float* alpha;
   const uint32_t* mask;
   float* out;
+  int16_t* out_i16;          // MODE 0: write the exact integer accumulator as int16 (y = alpha * int, |int| <= taps*Kc)
   double* bn_sums;           // MODE 0: per-channel sum / sum of squares of the result [2*Nout] (or NULL)
   uint32_t* bn_ymax;         // MODE 0: per-channel max|result| bits [Nout]
   long long* trace;          // optional clock64 trace of CTA 0 (bdbnn_debug_trace), else NULL
@@ -92,8 +100,14 @@ __device__ __forceinline__ SuperGeom super_geom(const TcConv2Params& p, int sup)
   return g;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// CG = 1: one CTA per work item (super tile x N tile).  CG = 2: a CTA PAIR (2-CTA cluster) per TWO adjacent super
+// tiles of the same N tile, executed as M = 256 tcgen05.mma.cta_group::2 instructions issued by the leader CTA:
+// each CTA stages its own activation patch / boxes (A) and HALF of the weight tile (B rows rank*BN/2 ...), so
+// per unit of work every SM fetches half the B bytes from shared memory — the measured limiter of the SS-mode
+// MMAs (DESIGN.md §5 finding 3).  Barriers the MMA thread waits on live in the leader; the peer's TMA loads
+// complete_tx on them (cta_group::2 TMA form) and its epilogue warps arrive on them through shared::cluster.
+template <int MODE, int CG>
+__global__ void __launch_bounds__(kTc2Threads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const TcConv2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -116,7 +130,13 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ring_base = smem_base + (p.halo ? 2u * p.patch_bytes : 0u);
   const int kb_total = p.n_kb * p.a_halves;
-  const int n_work = p.n_supers * p.n_ntiles;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;        // 0 = leader of the pair
+  const int cta_w = int(blockIdx.x) / CG, n_ctas_w = int(gridDim.x) / CG;   // work-item walkers (CTAs or pairs)
+  const int n_sup_w = (p.n_supers + CG - 1) / CG;                // super tiles (CG=2: pairs of them) to walk
+  const int n_work = n_sup_w * p.n_ntiles;
+  // super tile this CTA (r = rank) or its peer handles in work item w; a missing odd super is a clamped duplicate
+  auto sup_of = [&](int w, uint32_t r) { const int sp = w / p.n_ntiles; return min(sp * CG + int(r), p.n_supers - 1); };
+  auto is_dup = [&](int w, uint32_t r) { const int sp = w / p.n_ntiles; return sp * CG + int(r) >= p.n_supers; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -127,29 +147,36 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(smem_u32(&pfull_bar[s]), 1);
       mbar_init(smem_u32(&pempty_bar[s]), 1);
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);   // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps * CG);   // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kEpiWarps && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
-  if (warp == 5) tmem_alloc(smem_u32(&tmem_slot), 512);
+  if (warp == kEpiWarps + 1) {
+    if (CG == 2) tmem_alloc_cg2(smem_u32(&tmem_slot), 512);
+    else tmem_alloc(smem_u32(&tmem_slot), 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t it = 0, pcount = 0;
       int tr_n = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int sup = w / p.n_ntiles, nt = w - sup * p.n_ntiles;
+      const uint32_t patch_tx = uint32_t(p.PW * p.PH * p.HBNI) * uint32_t(p.row_bytes);
+      for (int w = cta_w; w < n_work; w += n_ctas_w) {
+        const int nt = w % p.n_ntiles;
+        const int sup = sup_of(w, rank);
         const SuperGeom g = super_geom(p, sup);
-        const int nn0 = nt * p.BN;
+        const int ntl_peer = CG == 2 ? super_geom(p, sup_of(w, rank ^ 1u)).ntl : 0;
+        const int nn0 = nt * p.BN + int(rank) * (p.BN / CG);        // this CTA's rows of the weight tile
         for (int kb = 0; kb < kb_total; ++kb) {
           const int kbb = kb >= p.n_kb ? kb - p.n_kb : kb;
           if (p.halo) {
@@ -158,47 +185,64 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(smem_u32(&pempty_bar[pa]), ((pcount >> 1) & 1u) ^ 1u);
             BDBNN_TR(0, 1);
             const uint32_t pb = smem_u32(&pfull_bar[pa]);
-            mbar_expect_tx(pb, uint32_t(p.PW * p.PH * p.HBNI) * uint32_t(p.row_bytes));
-            tma_load_4d(smem_base + pa * p.patch_bytes, &tmA, pb, kb * p.kb_elems, p.dw_min, g.h0 + p.dh_min, g.n0);
+            if (CG == 2) {
+              if (rank == 0) mbar_expect_tx(pb, 2u * patch_tx);          // both CTAs' patches land on the leader's barrier
+              tma_load_4d_cg2(smem_base + pa * p.patch_bytes, &tmA, mapa_shared(pb, 0), kb * p.kb_elems, p.dw_min,
+                              g.h0 + p.dh_min, g.n0);
+            } else {
+              mbar_expect_tx(pb, patch_tx);
+              tma_load_4d(smem_base + pa * p.patch_bytes, &tmA, pb, kb * p.kb_elems, p.dw_min, g.h0 + p.dh_min, g.n0);
+            }
             ++pcount;
           }
           for (int ti = 0; ti < p.n_taps; ++ti, ++it) {
             const uint32_t stage = it % uint32_t(p.stages);
             const uint32_t phase = (it / uint32_t(p.stages)) & 1u;
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
+            const uint32_t fb_local = smem_u32(&full_bar[stage]);
+            const uint32_t fb = CG == 2 ? mapa_shared(fb_local, 0) : fb_local;
             const uint32_t dst = ring_base + stage * p.stage_bytes;
-            if (p.halo) {
-              mbar_expect_tx(fb, p.b_bytes);
-            } else {
-              mbar_expect_tx(fb, p.b_bytes + uint32_t(g.ntl * p.BNI * p.BH * p.BW) * uint32_t(p.row_bytes));
+            const uint32_t box_tx = uint32_t(p.BNI * p.BH * p.BW) * uint32_t(p.row_bytes);
+            if (rank == 0) {
+              uint32_t tx = p.b_bytes * uint32_t(CG);
+              if (!p.halo) tx += uint32_t(g.ntl + ntl_peer) * box_tx;
+              mbar_expect_tx(fb_local, tx);
+            }
+            if (!p.halo) {
               for (int j = 0; j < g.ntl; ++j) {
                 const int t = sup * p.TS + j;
                 const int tile_n = t / p.tiles_h, tile_h = t - tile_n * p.tiles_h;
-                tma_load_4d(dst + p.b_bytes + uint32_t(j) * (kTileM * uint32_t(p.row_bytes)), &tmA, fb, kb * p.kb_elems, p.tap_dw[ti],
-                            tile_h * p.BH * p.in_step + p.tap_dh[ti], tile_n * p.BNI);
+                const uint32_t d = dst + p.b_bytes + uint32_t(j) * (kTileM * uint32_t(p.row_bytes));
+                if (CG == 2)
+                  tma_load_4d_cg2(d, &tmA, fb, kb * p.kb_elems, p.tap_dw[ti], tile_h * p.BH * p.in_step + p.tap_dh[ti],
+                                  tile_n * p.BNI);
+                else
+                  tma_load_4d(d, &tmA, fb, kb * p.kb_elems, p.tap_dw[ti], tile_h * p.BH * p.in_step + p.tap_dh[ti],
+                              tile_n * p.BNI);
               }
             }
-            tma_load_2d(dst, &tmB, fb, p.tap_b[ti] * p.Kc + kbb * p.kb_elems, nn0);
+            if (CG == 2) tma_load_2d_cg2(dst, &tmB, fb, p.tap_b[ti] * p.Kc + kbb * p.kb_elems, nn0);
+            else tma_load_2d(dst, &tmB, fb, p.tap_b[ti] * p.Kc + kbb * p.kb_elems, nn0);
           }
           BDBNN_TR(0, 2);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       const bool f8 = p.fmt < 0;
-      const uint32_t idesc = f8 ? make_idesc_f8(kTileM, uint32_t(p.BN))
-                                : make_idesc_bf16(kTileM, uint32_t(p.BN), uint32_t(p.fmt));
+      const uint32_t idesc = f8 ? make_idesc_f8(kTileM * CG, uint32_t(p.BN))
+                                : make_idesc_bf16(kTileM * CG, uint32_t(p.BN), uint32_t(p.fmt));
       const uint32_t desc_hi = kmajor_hi(uint32_t(p.row_bytes));
       const uint32_t row16 = uint32_t(p.row_bytes) >> 4;          // descriptor-address units per pixel row
       const int k_steps = p.row_bytes / 32;
       uint32_t it = 0, pcount = 0, wcount = 0;
       int tr_n = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wcount) {
-        const int sup = w / p.n_ntiles;
-        const SuperGeom g = super_geom(p, sup);
+      auto commit = [&](uint32_t bar) { if (CG == 2) umma_commit_cg2(bar); else umma_commit(bar); };
+      for (int w = cta_w; w < n_work; w += n_ctas_w, ++wcount) {
+        int ntl = super_geom(p, sup_of(w, 0)).ntl;
+        if (CG == 2) ntl = max(ntl, super_geom(p, sup_of(w, 1)).ntl);   // the peer's extra tiles cost this CTA garbage MMAs
         const uint32_t buf = wcount % uint32_t(p.NB);
         BDBNN_TR(1, 0);
         mbar_wait(smem_u32(&tempty_bar[buf]), ((wcount / uint32_t(p.NB)) & 1u) ^ 1u);
@@ -228,8 +272,13 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t a_lo = p.halo ? kmajor_lo(patch) + tap_shift_rows[ti] * row16 : kmajor_lo(b_src + p.b_bytes);
             uint32_t acc = acc0;
             if (!(p.dbg & 4)) {
-              for (int j = 0; j < g.ntl; ++j, a_lo += kTileM * row16, acc += uint32_t(p.BN)) {
-                if (f8) {
+              for (int j = 0; j < ntl; ++j, a_lo += kTileM * row16, acc += uint32_t(p.BN)) {
+                if (CG == 2) {
+                  for (int k = 0; k < k_steps; ++k) {
+                    if (f8) umma_split_cg2<1>(acc, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc, (!first || k > 0) ? 1u : 0u);
+                    else    umma_split_cg2<0>(acc, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc, (!first || k > 0) ? 1u : 0u);
+                  }
+                } else if (f8) {
                   for (int k = 0; k < k_steps; ++k)
                     umma_f8_split(acc, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc, (!first || k > 0) ? 1u : 0u);
                 } else if (p.row_bytes == 128) {
@@ -241,16 +290,18 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
             first = false;
-            umma_commit(smem_u32(&empty_bar[stage]));
+            commit(smem_u32(&empty_bar[stage]));
           }
-          if (p.halo) umma_commit(smem_u32(&pempty_bar[pa]));
+          if (p.halo) commit(smem_u32(&pempty_bar[pa]));
         }
-        umma_commit(smem_u32(&tfull_bar[buf]));
+        commit(smem_u32(&tfull_bar[buf]));
         BDBNN_TR(1, 4);
       }
     }
   } else {
-    // ================================ epilogue (warps 0..3) ================================
+    // ================================ epilogue (warps 0..7) ================================
+    const int quad = warp & 3;        // TMEM lane quadrant = rows quad*32 .. quad*32+31 of every M tile
+    const int grp = warp >> 2;        // column-block parity this warp handles
     const int mask_words = (p.Nout + 31) >> 5;
     const float post = p.amax_bits ? amax_pow2_scale(__ldg(p.amax_bits), true) : 1.0f;
     uint32_t wcount = 0;
@@ -262,7 +313,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // every 32-column block of the N tile, across tiles and work items, and flushes them to shared memory
     // only when the N tile changes or the CTA is done (per-block shuffles + atomics cost 25-35 % of the
     // forward kernels when done per 32x32 block).
-    constexpr int kAcc = MODE == 0 ? 8 : 1;          // 32-column blocks of the widest N tile (256)
+    constexpr int kAcc = MODE == 0 ? 4 : 1;          // this group's 32-column blocks of the widest N tile (256)
     float4 acc_s[kAcc], acc_q[kAcc], acc_m[kAcc];
 #pragma unroll
     for (int cb = 0; cb < kAcc; ++cb) acc_s[cb] = acc_q[cb] = acc_m[cb] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -270,9 +321,10 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     auto flush_stats = [&]() {
       if (!do_stats || acc_nn0 < 0) return;
 #pragma unroll
-      for (int cb = 0; cb < kAcc; ++cb) {
+      for (int ca = 0; ca < kAcc; ++ca) {
+        const int cb = 2 * ca + grp;                   // the column block accumulator `ca` belongs to
         if (cb * 32 >= p.BN) break;
-        float4 ss = acc_s[cb], sq = acc_q[cb], mx = acc_m[cb];
+        float4 ss = acc_s[ca], sq = acc_q[ca], mx = acc_m[ca];
         // lanes cq, cq+8, cq+16, cq+24 hold the same 4 channels for different rows
 #pragma unroll
         for (int d = 8; d <= 16; d <<= 1) {
@@ -292,11 +344,13 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           atomicMax(&stat_max[ch], __float_as_uint(mx.x)); atomicMax(&stat_max[ch + 1], __float_as_uint(mx.y));
           atomicMax(&stat_max[ch + 2], __float_as_uint(mx.z)); atomicMax(&stat_max[ch + 3], __float_as_uint(mx.w));
         }
-        acc_s[cb] = acc_q[cb] = acc_m[cb] = make_float4(0.f, 0.f, 0.f, 0.f);
+        acc_s[ca] = acc_q[ca] = acc_m[ca] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wcount) {
-      const int sup = w / p.n_ntiles, nt = w - sup * p.n_ntiles;
+    for (int w = cta_w; w < n_work; w += n_ctas_w, ++wcount) {
+      const int nt = w % p.n_ntiles;
+      const int sup = sup_of(w, rank);
+      const bool dup = is_dup(w, rank);          // odd super-tile count: this CTA only shadows the leader's last item
       const SuperGeom g = super_geom(p, sup);
       const int nn0 = nt * p.BN;
       if (do_stats && nn0 != acc_nn0) {
@@ -309,7 +363,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       BDBNN_TR(2, 1);
       for (int j = 0; j < g.ntl; ++j) {
-        const int m = j * kTileM + warp * 32 + lane;
+        const int m = j * kTileM + quad * 32 + lane;
         int ni, hi, wi;
         bool valid;
         if (p.halo) {
@@ -324,7 +378,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else {
           const int t = sup * p.TS + j;
           const int tile_n = t / p.tiles_h, tile_h = t - tile_n * p.tiles_h;
-          const int r = warp * 32 + lane;
+          const int r = quad * 32 + lane;
           wi = r % p.BW;
           const int q = r / p.BW;
           hi = tile_h * p.BH + q % p.BH;
@@ -335,13 +389,14 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int oh = hi * p.out_step + p.out_off_h, ow = wi * p.out_step + p.out_off_w;
         valid = valid && oh < p.OHf && ow < p.OWf;
         const int64_t pix = (int64_t(ni) * p.OHf + oh) * p.OWf + ow;
-        const uint32_t tbase = tmem_d + (uint32_t(warp * 32) << 16) + buf * uint32_t(p.TS * p.BN) + uint32_t(j * p.BN);
-        if (p.dbg & 1) valid = false;
+        const uint32_t tbase = tmem_d + (uint32_t(quad * 32) << 16) + buf * uint32_t(p.TS * p.BN) + uint32_t(j * p.BN);
+        if ((p.dbg & 1) || dup) valid = false;
         if (p.dbg & 2) continue;
         // Row offsets/validity of this warp's 32 rows are exchanged by shuffle in the store phase.
         const int64_t row_off = valid ? pix * p.Nout + nn0 : int64_t(-1);
 #pragma unroll
-        for (int cb = 0; cb < 8; ++cb) {
+        for (int ca = 0; ca < 4; ++ca) {
+          const int cb = 2 * ca + grp;
           const int c0 = cb * 32;
           if (c0 >= p.BN) break;
           uint32_t v[32];
@@ -357,9 +412,14 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int q = c * 4;
             float4 o;
             if (MODE == 0) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(p.alpha + nn0 + c0 + q));
-              o = make_float4(__uint_as_float(v[q]) * a.x, __uint_as_float(v[q + 1]) * a.y,
-                              __uint_as_float(v[q + 2]) * a.z, __uint_as_float(v[q + 3]) * a.w);
+              if (p.out_i16 != nullptr) {      // raw integers; alpha is applied to the statistics only (below)
+                o = make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
+                                __uint_as_float(v[q + 3]));
+              } else {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.alpha + nn0 + c0 + q));
+                o = make_float4(__uint_as_float(v[q]) * a.x, __uint_as_float(v[q + 1]) * a.y,
+                                __uint_as_float(v[q + 2]) * a.z, __uint_as_float(v[q + 3]) * a.w);
+              }
             } else {
               o = make_float4(((word >> q) & 1u) ? __uint_as_float(v[q]) * post : 0.0f,
                               ((word >> (q + 1)) & 1u) ? __uint_as_float(v[q + 1]) * post : 0.0f,
@@ -376,6 +436,9 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 8; ++i) offs[i] = __shfl_sync(0xffffffffu, row_off, 4 * i + (lane >> 3));
           const int cq = lane & 7;
+          float4 a16 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (MODE == 0 && p.out_i16 != nullptr)
+            a16 = __ldg(reinterpret_cast<const float4*>(p.alpha + nn0 + c0 + cq * 4));
           float4 addv[8];
           if (MODE == 1 && p.add != nullptr) {
 #pragma unroll
@@ -391,10 +454,19 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               o.x += addv[i].x; o.y += addv[i].y; o.z += addv[i].z; o.w += addv[i].w;
             }
             if (offs[i] >= 0) {
-              *reinterpret_cast<float4*>(p.out + offs[i] + c0 + cq * 4) = o;
+              if (MODE == 0 && p.out_i16 != nullptr) {
+                // exact: |o| <= 9 * 512 fits int16; 8 lanes write one 64-byte row segment
+                uint2 pk;
+                pk.x = (uint32_t(int(o.x)) & 0xffffu) | (uint32_t(int(o.y)) << 16);
+                pk.y = (uint32_t(int(o.z)) & 0xffffu) | (uint32_t(int(o.w)) << 16);
+                *reinterpret_cast<uint2*>(p.out_i16 + offs[i] + c0 + cq * 4) = pk;
+                o.x *= a16.x; o.y *= a16.y; o.z *= a16.z; o.w *= a16.w;      // y = alpha * int for the statistics
+              } else {
+                *reinterpret_cast<float4*>(p.out + offs[i] + c0 + cq * 4) = o;
+              }
               if (do_stats) {
-                float4& ss = acc_s[MODE == 0 ? cb : 0]; float4& sq = acc_q[MODE == 0 ? cb : 0];
-                float4& mx = acc_m[MODE == 0 ? cb : 0];
+                float4& ss = acc_s[MODE == 0 ? ca : 0]; float4& sq = acc_q[MODE == 0 ? ca : 0];
+                float4& mx = acc_m[MODE == 0 ? ca : 0];
                 ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
                 sq.x += o.x * o.x; sq.y += o.y * o.y; sq.z += o.z * o.z; sq.w += o.w * o.w;
                 mx.x = fmaxf(mx.x, fabsf(o.x)); mx.y = fmaxf(mx.y, fabsf(o.y));
@@ -407,12 +479,16 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       BDBNN_TR(2, 2);
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[buf]), 0));   // the leader's MMA thread waits
+        else mbar_arrive(smem_u32(&tempty_bar[buf]));
+      }
     }
     flush_stats();
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // nobody leaves (or frees TMEM) while the pair's MMAs / commits may be in flight
   if (do_stats) {
     // one fp64 atomic per channel per CTA; channels this CTA never touched hold zeros
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) {
@@ -423,10 +499,11 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   }
-  if (warp == 5) {
+  if (warp == kEpiWarps + 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_d, 512);
+    if (CG == 2) tmem_dealloc_cg2(tmem_d, 512);
+    else tmem_dealloc(tmem_d, 512);
   }
 }
 
@@ -465,7 +542,11 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   // bound by that fetch, DESIGN.md section 5 finding 3).  BDBNN_TC_BN256=0 restores 128.
   static const int bn256 = [] { const char* e = getenv("BDBNN_TC_BN256"); return e ? atoi(e) : 3; }();   // 1 dgrad, 2 fwd8, 3 both (default)
   // forward: the fp8 layers with Cout >= 256 (bit 1 of the knob)
-  const bool wide = L.Nout % 256 == 0 && ((mode == 1 && !f8 && (bn256 & 1)) || (mode == 0 && f8 && (bn256 & 2)));
+  // CTA pairs (cta_group::2): each CTA stages half of the N tile, so the widest tile (256) costs a CTA what a
+  // 128-wide one costs alone — use it whenever the channel count allows.  BDBNN_TC_CG2=0: single-CTA MMAs.
+  static const int cg2_env = [] { const char* e = getenv("BDBNN_TC_CG2"); return e ? atoi(e) : 1; }();
+  p.cg = cg2_env ? 2 : 1;
+  const bool wide = L.Nout % 256 == 0 && (p.cg == 2 || (mode == 1 && !f8 && (bn256 & 1)) || (mode == 0 && f8 && (bn256 & 2)));
   p.BN = wide ? 256 : (L.Nout >= 128 ? 128 : 64);
   p.n_ntiles = L.Nout / p.BN;
   // 512 TMEM columns = NB buffers x TS accumulators x BN columns.  BDBNN_TC_TS128 picks the BN=128 split:
@@ -478,11 +559,13 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   p.TS = p.BN == 256 ? 2 : (p.BN == 64 ? 4 : (ts128 == 4 ? 4 : (ts128 == 2 ? 2 : ts_auto)));
   p.NB = 512 / (p.TS * p.BN);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
+  p.out_i16 = mode == 0 ? L.out_i16 : nullptr;
+  if (L.out_i16 && (mode != 0 || L.n_taps * L.Kc * L.a_halves > 32767)) return BDBNN_ERR_UNSUPPORTED;
   p.fmt = L.fmt; p.amax_bits = L.amax_bits; p.add = L.add;
   p.bn_sums = (mode == 0 && L.Nout <= kMaxStatCh) ? L.bn_sums : nullptr;
   p.bn_ymax = L.bn_ymax;
   if (L.bn_sums && !p.bn_sums) return BDBNN_ERR_UNSUPPORTED;
-  p.b_bytes = uint32_t(p.BN) * row_bytes;
+  p.b_bytes = uint32_t(p.BN / p.cg) * row_bytes;       // rows of the weight tile THIS CTA stages
 
   int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
   for (int i = 0; i < p.n_taps; ++i) {
@@ -552,9 +635,9 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
       rc = make_act_map(&tmA, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, kb_elems, p.BW, p.BH, p.BNI, L.in_step, esize);
   }
   if (rc) return rc;
-  rc = g_plan_sink ? BDBNN_OK : make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, kb_elems, p.BN, esize);
+  rc = g_plan_sink ? BDBNN_OK : make_weight_map(&tmB, L.B, L.Nout, L.b_taps * L.Kc, kb_elems, p.BN / p.cg, esize);
   if (rc) return rc;
-  const uint32_t kStaging = 4u * 4096u;   // epilogue transpose tiles
+  const uint32_t kStaging = uint32_t(kEpiWarps) * 4096u;   // epilogue transpose tiles
   const uint32_t fixed = (p.halo ? 2u * p.patch_bytes : 0u) + kStaging;
   // 227 KB per CTA minus static shared memory (barriers; MODE 0 also holds 6 KB of BN statistics)
   const uint32_t budget = 224u * 1024u - 1024u - (mode == 0 ? 3u * kMaxStatCh * 4u : 0u);
@@ -566,22 +649,31 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   static const int dbg_env = [] { const char* e = getenv("BDBNN_TC_DBG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg_env;
   p.trace = g_trace;
-  const int n_work = p.n_supers * p.n_ntiles;
-  int grid = num_sms();
+  const int n_work = ((p.n_supers + p.cg - 1) / p.cg) * p.n_ntiles;      // work items of a CTA (pair)
+  int grid = num_sms() / p.cg;
   if (grid > n_work) grid = n_work;
+  grid *= p.cg;
   if (g_plan_sink) {
     const int32_t v[12] = {1, p.halo, p.TS, p.NB, p.BN, p.n_ntiles, p.n_supers, stages, int32_t(smem), grid,
                            int32_t(p.stage_bytes), int32_t(p.halo ? p.patch_bytes : 0)};
     memcpy(g_plan_sink, v, sizeof(v));
     return BDBNN_OK;
   }
-  if (mode == 0) {
-    BDBNN_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    tc_conv2_kernel<0><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
-  } else {
-    BDBNN_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    tc_conv2_kernel<1><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
-  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kTc2Threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(p.cg); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  auto launch = [&](auto kern) -> int {
+    BDBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    BDBNN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    return BDBNN_OK;
+  };
+  if (mode == 0) rc = p.cg == 2 ? launch(tc_conv2_kernel<0, 2>) : launch(tc_conv2_kernel<0, 1>);
+  else           rc = p.cg == 2 ? launch(tc_conv2_kernel<1, 2>) : launch(tc_conv2_kernel<1, 1>);
+  if (rc) return rc;
   return check_launch("tc_conv2_kernel");
 }
 

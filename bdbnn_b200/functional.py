@@ -592,6 +592,12 @@ def conv_stats_enabled():
     return os.environ.get("BDBNN_CONV_STATS", "1") != "0"
 
 
+def y_i16_enabled():
+    """BDBNN_Y_I16 (default 1): inside the fused units the conv result is kept as the exact int16 accumulator
+    (y = alpha*int) instead of fp32 — half the bytes for BatchNorm's one forward and two backward reads."""
+    return os.environ.get("BDBNN_Y_I16", "1") != "0"
+
+
 def fuse_enabled():
     return os.environ.get(_FUSE_ENV, "1") != "0"
 
@@ -658,28 +664,37 @@ class _ConvBNAddUnit(torch.autograd.Function):
         inv_gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
         _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask), _p(wf), _p(wt),
                                        _p(wf8), _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
-        y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
-                        memory_format=torch.channels_last)
         # BN batch statistics of y are accumulated by the conv kernel's epilogue (BDBNN_CONV_STATS=0: separate pass)
         sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
         ymax = torch.empty((cout,), **i32)
         in_conv = conv_stats_enabled() and cout <= 512
         s_ptr, m_ptr = (_p(sums), _p(ymax)) if in_conv else (None, None)
-        if use8:
-            with _timed("binconv_fwd_tc8", key, algorithmic_bytes("fwd_tc8", sh)):
-                _lib.check(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), ctypes.byref(sh), s_ptr, m_ptr,
-                                                   st), "binconv_fwd_tc8")
+        i16 = bool(caps & 16) and in_conv and y_i16_enabled()
+        if i16:     # y kept as the exact integer accumulator, int16 NHWC (y = alpha * y_int)
+            y = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.int16, device=dev)
+            with _timed("binconv_fwd_tc8" if use8 else "binconv_fwd_tc", key,
+                        algorithmic_bytes("fwd_tc8" if use8 else "fwd_tc", sh) - 2 * y.numel()):
+                _lib.check(L.bdbnn_binconv_fwd_tc_i16(_p(xb8) if use8 else _p(xb), _p(wf8) if use8 else _p(wf),
+                                                      -1 if use8 else fmt, _p(alpha), _p(y), ctypes.byref(sh), s_ptr,
+                                                      m_ptr, st), "binconv_fwd_tc_i16")
         else:
-            with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
-                _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), s_ptr, m_ptr,
-                                                  st), "binconv_fwd_tc")
+            y = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev,
+                            memory_format=torch.channels_last)
+            if use8:
+                with _timed("binconv_fwd_tc8", key, algorithmic_bytes("fwd_tc8", sh)):
+                    _lib.check(L.bdbnn_binconv_fwd_tc8(_p(xb8), _p(wf8), _p(alpha), _p(y), ctypes.byref(sh), s_ptr,
+                                                       m_ptr, st), "binconv_fwd_tc8")
+            else:
+                with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
+                    _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), s_ptr,
+                                                      m_ptr, st), "binconv_fwd_tc")
         _lib.count(3)
         n_pix = n * sh.Ho * sh.Wo
         if res_is_x:            # identity shortcut: the residual IS the conv input (one autograd edge)
             rc = _nhwc(x.detach())
         else:
             rc = _nhwc(residual.detach()) if residual is not None else None
-        z = torch.empty_like(y)
+        z = torch.empty((n, cout, sh.Ho, sh.Wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
         mean = torch.empty((cout,), dtype=torch.float32, device=dev)
         invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
         ab = torch.empty((2 * cout,), dtype=torch.float32, device=dev)
@@ -688,18 +703,27 @@ class _ConvBNAddUnit(torch.autograd.Function):
         zm = torch.empty((n, sh.Ho, sh.Wo, cout // 32), **i32) if pack else None
         zb = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.int16, device=dev) if pack else None
         zb8 = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.uint8, device=dev) if (pack and fwd8_enabled()) else None
-        with _timed("bn_fwd", key, ((0 if in_conv else 4) + 12 + (2.25 if pack else 0) +
+        ybytes = 2 if i16 else 4
+        with _timed("bn_fwd", key, ((0 if in_conv else 4) + ybytes + 8 + (2.25 if pack else 0) +
                                     (1 if zb8 is not None else 0)) * n_pix * cout):
-            _lib.check(L.bdbnn_bn_fwd(_p(y), _p(rc), _p(gamma.detach()), _p(beta.detach()), n_pix, cout, float(eps),
-                                      float(momentum), _p(running_mean), _p(running_var), _p(sums), _p(ymax),
-                                      _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm), _p(zb), _p(zb8), fmt,
-                                      1 if in_conv else 0, st), "bn_fwd")
+            if i16:
+                _lib.check(L.bdbnn_bn_fwd_i16(_p(y), _p(alpha), _p(rc), _p(gamma.detach()), _p(beta.detach()), n_pix,
+                                              cout, float(eps), float(momentum), _p(running_mean), _p(running_var),
+                                              _p(sums), _p(ymax), _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm),
+                                              _p(zb), _p(zb8), fmt, st), "bn_fwd_i16")
+            else:
+                _lib.check(L.bdbnn_bn_fwd(_p(y), _p(rc), _p(gamma.detach()), _p(beta.detach()), n_pix, cout, float(eps),
+                                          float(momentum), _p(running_mean), _p(running_var), _p(sums), _p(ymax),
+                                          _p(mean), _p(invstd), _p(ab), _p(z), _p(zs), _p(zm), _p(zb), _p(zb8), fmt,
+                                          1 if in_conv else 0, st), "bn_fwd")
         _lib.count(2 if in_conv else 3)
+        ctx.y_i16 = i16
         ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
         ctx.shapes = (tuple(x.shape), tuple(weight.shape))
         ctx.has_res = residual is not None and sc_weight is None
         ctx.res_is_x = bool(res_is_x)
-        ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale, *sc_saved)
+        ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale, alpha,
+                              *sc_saved)
         if pack:
             if zb8 is not None:
                 ctx.mark_non_differentiable(zs, zm, zb, zb8)
@@ -717,7 +741,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
         sh = ctx.sh
         st = _stream()
         dev = gz.device
-        y, mean, invstd, gamma, ymax, xm, xb, wt, wmask, gscale, inv_gscale = ctx.saved_tensors[:11]
+        y, mean, invstd, gamma, ymax, xm, xb, wt, wmask, gscale, inv_gscale, alpha = ctx.saved_tensors[:12]
         gname, gcode, gh = ctx.gmode
         key = _shape_key(sh)
         g = _nhwc(gz)
@@ -731,10 +755,16 @@ class _ConvBNAddUnit(torch.autograd.Function):
         dbeta = torch.empty((cout,), dtype=torch.float32, device=dev)
         amax = torch.empty((1,), **i32)
         gys = torch.empty((sh.N, sh.Ho, sh.Wo, gh * cout), dtype=torch.int16, device=dev)
-        with _timed("bn_bwd_pack", key, (8 + 8 + 2 * gh) * n_pix * cout):
-            _lib.check(L.bdbnn_bn_bwd_pack(_p(g), _p(y), _p(mean), _p(invstd), _p(gamma), _p(gscale), _p(ymax), n_pix,
-                                           cout, gcode, _p(sums), _p(gmax), _p(consts), _p(dgamma), _p(dbeta),
-                                           _p(amax), _p(gys), st), "bn_bwd_pack")
+        ybytes = 2 if ctx.y_i16 else 4
+        with _timed("bn_bwd_pack", key, (8 + 2 * ybytes + 2 * gh) * n_pix * cout):
+            if ctx.y_i16:
+                _lib.check(L.bdbnn_bn_bwd_pack_i16(_p(g), _p(y), _p(alpha), _p(mean), _p(invstd), _p(gamma), _p(gscale),
+                                                   _p(ymax), n_pix, cout, gcode, _p(sums), _p(gmax), _p(consts),
+                                                   _p(dgamma), _p(dbeta), _p(amax), _p(gys), st), "bn_bwd_pack_i16")
+            else:
+                _lib.check(L.bdbnn_bn_bwd_pack(_p(g), _p(y), _p(mean), _p(invstd), _p(gamma), _p(gscale), _p(ymax),
+                                               n_pix, cout, gcode, _p(sums), _p(gmax), _p(consts), _p(dgamma),
+                                               _p(dbeta), _p(amax), _p(gys), st), "bn_bwd_pack")
         _lib.count(3)
         x_shape, w_shape = ctx.shapes
         gx = gw = None
@@ -758,7 +788,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
         sc_gw = sc_dg = sc_db = None
         if ctx.n_sc:
             # shortcut branch: residual gradient = gz; its dgrad accumulates into gx in place
-            sgx, sc_gw, sc_dg, sc_db = _shortcut_bwd_impl(gz, ctx.saved_tensors[11:], ctx.sc_geom,
+            sgx, sc_gw, sc_dg, sc_db = _shortcut_bwd_impl(gz, ctx.saved_tensors[12:], ctx.sc_geom,
                                                           ctx.needs_input_grad[0], ctx.needs_input_grad[16], acc=gx)
             gx = sgx if sgx is not None else gx
             sc_dg = sc_dg if ctx.needs_input_grad[17] else None

@@ -223,6 +223,93 @@ class TrainStep:
                 "kl_c": det(loss_kl_c), "acc1": acc1, "acc5": acc5, "output": output.detach()}
 
 
+class GraphedTrainStep:
+    """The whole optimisation step (forward, losses, backward, gradient all-reduce, optimizer) captured ONCE as
+    a CUDA graph and replayed: ~350 launches per ResNet-18 step leave the Python / ctypes / autograd path, so the
+    step time is the GPU's, not the host's (the C ABI neither allocates nor synchronises,
+    which is what makes it capturable).
+
+        step = GraphedTrainStep(TrainStep(model, make_optimizer(model), cfg, ...))
+        out = step(images, target)        # first call: `warmup` eager steps + capture; later calls: replay
+
+    * inputs are copied into static device buffers (skipped when the caller passes those very buffers:
+      `step.static_images`, `step.static_target` — e.g. as the destination of its H2D copies);
+    * the returned dict holds STATIC tensors that the next call overwrites (read or clone what you keep);
+    * everything that changes between steps lives in device memory: Adam's step count, the learning rates
+      (`optimizer.sync_lr()` before every replay picks up LR-scheduler changes), BatchNorm buffers, meters;
+    * shapes, the loss configuration and `epoch >= kurtepoch` are frozen at capture — a change of batch shape or
+      of the kurtosis gate re-captures.
+    Requires the fused optimizers (their graph mode) and CUDA tensors."""
+
+    def __init__(self, step: "TrainStep", warmup: int = 3):
+        self.step, self.warmup = step, max(1, int(warmup))
+        self.graph = None
+        self._key = None
+        self.static_images = self.static_target = None
+        self.launches_per_replay = 0
+        self.out = None
+
+    @property
+    def meters(self):
+        return self.step.meters
+
+    def averages(self):
+        return self.step.averages()
+
+    def reset_meters(self):
+        self.step.reset_meters()
+
+    def _optimizer(self):
+        opt = self.step.optimizer
+        return getattr(opt, "optimizer", opt)            # FlatGradOptimizerShim wraps the real one
+
+    def _capture(self, images, target, epoch):
+        from . import _lib
+        from .functional import KernelTimer
+        if KernelTimer.enabled:
+            raise RuntimeError("GraphedTrainStep: per-kernel CUDA-event timing cannot run inside a capture")
+        opt = self._optimizer()
+        if not hasattr(opt, "enable_graph_mode"):
+            raise RuntimeError("GraphedTrainStep needs bdbnn_b200.optim.FusedAdam / FusedSGD (graph mode)")
+        self.static_images = images.clone(memory_format=torch.preserve_format)
+        self.static_target = target.clone()
+        opt.enable_graph_mode()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            # eager warm-up on the capture side stream: lazy initialisation (kernel attributes, tensor-map
+            # encoder, cuDNN algorithm choice for an fp32 teacher), optimizer / meter state, allocator pools
+            for _ in range(self.warmup):
+                self.step(self.static_images, self.static_target, epoch)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+            self.out = self.step(self.static_images, self.static_target, epoch)
+        self.launches_per_replay = _lib.launch_count() - n0
+        self._key = (tuple(images.shape), tuple(target.shape),
+                     bool(self.step.cfg.w_kurtosis and self.step.cfg.kurtepoch <= epoch))
+
+    def __call__(self, images, target, epoch=0):
+        key = (tuple(images.shape), tuple(target.shape),
+               bool(self.step.cfg.w_kurtosis and self.step.cfg.kurtepoch <= epoch))
+        if self.graph is None or key != self._key:
+            self.graph = None
+            self._capture(images, target, epoch)        # the warm-up steps are real optimisation steps;
+            # the capture pass itself only records — replay it once so that this call, too, performs a step
+        from . import _lib
+        if images.data_ptr() != self.static_images.data_ptr():
+            self.static_images.copy_(images, non_blocking=True)
+        if target.data_ptr() != self.static_target.data_ptr():
+            self.static_target.copy_(target, non_blocking=True)
+        self._optimizer().sync_lr()
+        self.graph.replay()
+        _lib.count(self.launches_per_replay)
+        return self.out
+
+
 def make_optimizer(model, dataset='imagenet', lr=None, momentum=0.9, weight_decay=None, fused=None):
     """train.py:319-336. CIFAR: SGD(lr .1, m .9, wd 1e-4). ImageNet: Adam, weight decay only on
     4-D / 'conv' parameters (train.py:323-330)."""

@@ -68,6 +68,7 @@ BDBNN_API int bdbnn_debug_trace(long long* device_buf);
 #define BDBNN_TC_DGRAD 2
 #define BDBNN_TC_WGRAD 4
 #define BDBNN_TC_FWD8 8   /* fp8 (e4m3 +-1) forward: bdbnn_binconv_fwd_tc8 */
+#define BDBNN_TC_FWD_I16 16 /* forward can store the integer accumulator as int16: bdbnn_binconv_fwd_tc_i16 */
 BDBNN_API int bdbnn_tc_supported(const bdbnn_conv_shape* s);
 
 /* ---- activation sign/pack ---------------------------------------------------------------------
@@ -123,6 +124,16 @@ BDBNN_API int bdbnn_binconv_fwd_tc(const uint16_t* xb_bf16, const uint16_t* wf_b
  * 16-bit kernel; still exact.  Requires bdbnn_tc_supported(s) & BDBNN_TC_FWD8. */
 BDBNN_API int bdbnn_binconv_fwd_tc8(const uint8_t* xb_fp8, const uint8_t* wf_fp8, const float* alpha, float* y,
                           const bdbnn_conv_shape* s, double* bn_sums, uint32_t* bn_ymax, void* stream);
+
+/* Forward with the result stored as the EXACT INTEGER accumulator, int16 NHWC [N,Ho,Wo,Cout]:
+ * y = alpha[o] * y_int[o], |y_int| <= kh*kw*Cin <= 32767 — lossless, half the bytes of the fp32 y that the
+ * fused BatchNorm units (bdbnn_bn_fwd_i16 / bdbnn_bn_bwd_pack_i16) read once in the forward and twice in the
+ * backward.  fmt = BDBNN_FMT_FP16 / BDBNN_FMT_BF16 (16-bit +-1 operands) or -1 (fp8 e4m3 operands, needs
+ * BDBNN_TC_FWD8).  The statistics (bn_sums / bn_ymax) are those of y = alpha * y_int, as in fwd_tc.
+ * Requires bdbnn_tc_supported(s) & BDBNN_TC_FWD_I16 (persistent kernel only). */
+BDBNN_API int bdbnn_binconv_fwd_tc_i16(const void* xb, const void* wf, int32_t fmt, const float* alpha,
+                             int16_t* y_int, const bdbnn_conv_shape* s, double* bn_sums, uint32_t* bn_ymax,
+                             void* stream);
 
 /* ---- backward: data gradient -------------------------------------------------------------------
  * gx[n,h,w,c] = mask(n,h,w,c) * sum_{t,o} gy[n,ho,wo,o] * alpha[o] * sign(W[o,c,t])
@@ -237,6 +248,20 @@ BDBNN_API int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* me
                       int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits, float* consts_ws,
                       float* dgamma, float* dbeta, uint32_t* amax_bits, uint16_t* gys, void* stream);
 
+/* The same two passes on the int16 conv result of bdbnn_binconv_fwd_tc_i16 (y = alpha[c] * y_int): 2 instead of
+ * 4 bytes per element for the one forward and the two backward reads of y.  The statistics always come from the
+ * conv epilogue (stats_ready is implied). */
+BDBNN_API int bdbnn_bn_fwd_i16(const int16_t* y_int, const float* alpha, const float* residual, const float* gamma,
+                     const float* beta, int64_t n_pix, int32_t C, float eps, float momentum, float* running_mean,
+                     float* running_var, double* sums_ws, uint32_t* ymax_bits, float* mean, float* invstd,
+                     float* ab_ws, float* z, uint32_t* sign_bits, uint32_t* mask_bits, uint16_t* xb,
+                     uint8_t* xb_fp8, int32_t fmt, void* stream);
+BDBNN_API int bdbnn_bn_bwd_pack_i16(const float* gz, const int16_t* y_int, const float* alpha, const float* mean,
+                          const float* invstd, const float* gamma, const float* gscale, const uint32_t* ymax_bits,
+                          int64_t n_pix, int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits,
+                          float* consts_ws, float* dgamma, float* dbeta, uint32_t* amax_bits, uint16_t* gys,
+                          void* stream);
+
 /* ---- stem: BatchNorm(train) + MaxPool fused (the BN output is never written) -----------------------
  * bn_pool_fwd: y fp32 NHWC [N,H,W,C] (stem conv output) -> z = maxpool_k,s,p(gamma*(y-mean)*invstd+beta)
  *              [N,Ho,Wo,C], idx = winning tap per output element (1 byte), y_sel = y at the winner;
@@ -321,6 +346,22 @@ BDBNN_API int bdbnn_optim_sgd_multi(float* const* params_host, const float* cons
                           float* const* momentum_buf_host, const int64_t* numel_host,
                           const float* weight_decay_host, const float* lr_host, int32_t count, float momentum,
                           int32_t first_step, float grad_scale, void* stream);
+/* CUDA-graph variants (the whole step of train.py:492-529 captured once and replayed): everything that changes
+ * from step to step is read from DEVICE memory so a captured launch stays valid —
+ * step_dev  float[1], the 1-based Adam step count (bdbnn_optim_step_inc adds 1; launch it before the update);
+ * lr_dev    float[count], one learning rate per tensor in table order (the LR scheduler of train.py:336 / 322
+ *           rewrites it between replays).  SGD: momentum buffers must exist and start at zero (first step then
+ *           equals torch's buf = g). */
+BDBNN_API int bdbnn_optim_step_inc(float* step_dev, void* stream);
+BDBNN_API int bdbnn_optim_adam_multi_graph(float* const* params_host, const float* const* grads_host,
+                                 float* const* exp_avg_host, float* const* exp_avg_sq_host,
+                                 const int64_t* numel_host, const float* weight_decay_host, int32_t count,
+                                 float beta1, float beta2, float eps, const float* step_dev, const float* lr_dev,
+                                 float grad_scale, void* stream);
+BDBNN_API int bdbnn_optim_sgd_multi_graph(float* const* params_host, const float* const* grads_host,
+                                float* const* momentum_buf_host, const int64_t* numel_host,
+                                const float* weight_decay_host, int32_t count, float momentum,
+                                const float* lr_dev, float grad_scale, void* stream);
 
 /* ---- fp32 1x1 shortcut convolution (`downsample` of the ResNet shells) on the tcgen05 kernels -----------
  * Packing only (bdbnn_b200/csrc/real_conv.cu): xh = fp16(x[:, ::stride, ::stride, :] * 2^ex) dense NHWC

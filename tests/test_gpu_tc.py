@@ -125,15 +125,17 @@ def test_fwd_tc_full_size_layers_equal_xnor():
 UNIT_SHAPES = [(2, 64, 16, 16, 64, 1), (2, 64, 20, 20, 128, 2), (3, 128, 14, 14, 128, 1), (4, 256, 7, 7, 256, 1)]
 
 
+@pytest.mark.parametrize("y_i16", ["1", "0"])
 @pytest.mark.parametrize("mode", ["fp16s", "bf16x2"])
 @pytest.mark.parametrize("with_res", [True, False])
 @pytest.mark.parametrize("shape", UNIT_SHAPES)
-def test_fused_conv_bn_add_unit_vs_oracle(shape, with_res, mode, monkeypatch):
+def test_fused_conv_bn_add_unit_vs_oracle(shape, with_res, mode, y_i16, monkeypatch):
     """z = BN_train(binconv(x)) + residual: fused kernels vs RefBinarizeConv2d + nn.BatchNorm2d + add on CPU
     (values, running statistics, and the gradients of x, W, gamma, beta, residual)."""
     import torch.nn as nn
     from bdbnn_b200.functional import conv_bn_add, unit_supported
     monkeypatch.setenv("BDBNN_GRAD_MODE", mode)
+    monkeypatch.setenv("BDBNN_Y_I16", y_i16)      # conv result kept as int16 accumulator (default) or fp32
     n, cin, h, w, cout, stride = shape
     assert unit_supported((n, cin, h, w), (cout, cin, 3, 3), stride, 1)
     g = torch.Generator().manual_seed(31 + sum(shape))
