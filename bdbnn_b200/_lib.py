@@ -31,6 +31,7 @@ SIGNATURES = {
     "bdbnn_debug_trace": (c_int, [_P]),
     "bdbnn_act_pack": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P]),
     "bdbnn_weight_pack": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "bdbnn_weight_pack_multi": (c_int, [c_int] + [_P] * 12 + [c_int, _P]),
     "bdbnn_bits_to_fp8": (c_int, [_P, c_int64, c_int, _P, _P]),
     "bdbnn_ede_scale": (c_int, [_P, _P, _P, _P, c_int64, _P]),
     "bdbnn_ce_topk_fwd_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
@@ -67,7 +68,8 @@ SIGNATURES = {
     "bdbnn_bn_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, ctypes.c_float, ctypes.c_float] + [_P] * 12 + [c_int, c_int, _P]),
     "bdbnn_bn_bwd_pack": (c_int, [_P] * 7 + [c_int64, c_int, c_int] + [_P] * 8),
     "bdbnn_bn_fwd_i16": (c_int, [_P] * 5 + [c_int64, c_int, ctypes.c_float, ctypes.c_float] + [_P] * 12 + [c_int, _P]),
-    "bdbnn_bn_bwd_pack_i16": (c_int, [_P] * 8 + [c_int64, c_int, c_int] + [_P] * 8),
+    "bdbnn_bn_bwd_pack_i16": (c_int, [_P] * 8 + [c_int64, c_int, c_int] + [_P] * 7 + [c_int, _P]),
+    "bdbnn_binconv_dgrad_tc_stats": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _SH] + [_P] * 7),
     "bdbnn_binconv_fwd_tc_i16": (c_int, [_P, _P, c_int, _P, _P, _SH, _P, _P, _P]),
     "bdbnn_bn_pool_fwd": (c_int, [_P, _P, _P] + [c_int] * 9 + [ctypes.c_float, ctypes.c_float] + [_P] * 14 + [c_int, c_int, _P]),
     "bdbnn_bn_pool_bwd": (c_int, [_P] * 9 + [c_int] * 9 + [_P] * 9),

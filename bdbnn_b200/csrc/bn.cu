@@ -372,7 +372,7 @@ static int bn_bwd_pack_impl(const float* gz, const void* y, const float* alpha_i
                             const float* invstd, const float* gamma, const float* gscale, const uint32_t* ymax_bits,
                             int64_t n_pix, int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits,
                             float* consts_ws, float* dgamma, float* dbeta, uint32_t* amax_bits, uint16_t* gys,
-                            void* stream) {
+                            int stats_ready, void* stream) {
   const bool i16 = alpha_i16 != nullptr;
   int rc = bn_dims_ok(n_pix, C, false);
   if (rc) return rc;
@@ -382,17 +382,19 @@ static int bn_bwd_pack_impl(const float* gz, const void* y, const float* alpha_i
   BDBNN_REQUIRE(grad_mode >= BDBNN_GRAD_BF16 && grad_mode <= BDBNN_GRAD_FP16S, "bn_bwd_pack: bad grad_mode");
   cudaStream_t st = cudaStream_t(stream);
   const int C4 = C / 4;
-  BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
-  BDBNN_CUDA(cudaMemsetAsync(gmax_bits, 0, size_t(C) * sizeof(uint32_t), st));
-  const int rgrid = bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3);
-  if (i16)
-    bn_reduce_kernel<true, true><<<rgrid, kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
-        reinterpret_cast<const float4*>(gz), y, mean, invstd, n_pix, C4, sums_ws, gmax_bits, alpha_i16);
-  else
-    bn_reduce_kernel<true, false><<<rgrid, kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
-        reinterpret_cast<const float4*>(gz), y, mean, invstd, n_pix, C4, sums_ws, gmax_bits, nullptr);
-  rc = check_launch("bn_reduce_kernel<bwd>");
-  if (rc) return rc;
+  if (!stats_ready) {       // else: sums_ws / gmax_bits were filled by the dgrad epilogue that produced gz
+    BDBNN_CUDA(cudaMemsetAsync(sums_ws, 0, size_t(2 * C) * sizeof(double), st));
+    BDBNN_CUDA(cudaMemsetAsync(gmax_bits, 0, size_t(C) * sizeof(uint32_t), st));
+    const int rgrid = bn_grid(n_pix * C4 / 8, C4, n_pix * C4 > (int64_t(16) << 20) ? 8 : 3);
+    if (i16)
+      bn_reduce_kernel<true, true><<<rgrid, kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+          reinterpret_cast<const float4*>(gz), y, mean, invstd, n_pix, C4, sums_ws, gmax_bits, alpha_i16);
+    else
+      bn_reduce_kernel<true, false><<<rgrid, kBnThreads, size_t(3 * C) * sizeof(float), st>>>(
+          reinterpret_cast<const float4*>(gz), y, mean, invstd, n_pix, C4, sums_ws, gmax_bits, nullptr);
+    rc = check_launch("bn_reduce_kernel<bwd>");
+    if (rc) return rc;
+  }
   bn_bwd_bound_kernel<<<1, 256, 0, st>>>(sums_ws, gmax_bits, ymax_bits, n_pix, C, mean, invstd, gamma, gscale,
                                          reinterpret_cast<float4*>(consts_ws), dgamma, dbeta, amax_bits, 1.0f,
                                          alpha_i16);
@@ -426,17 +428,18 @@ extern "C" int bdbnn_bn_bwd_pack(const float* gz, const float* y, const float* m
                                  uint32_t* gmax_bits, float* consts_ws, float* dgamma, float* dbeta,
                                  uint32_t* amax_bits, uint16_t* gys, void* stream) {
   return bn_bwd_pack_impl(gz, y, nullptr, mean, invstd, gamma, gscale, ymax_bits, n_pix, C, grad_mode, sums_ws,
-                          gmax_bits, consts_ws, dgamma, dbeta, amax_bits, gys, stream);
+                          gmax_bits, consts_ws, dgamma, dbeta, amax_bits, gys, 0, stream);
 }
 
 extern "C" int bdbnn_bn_bwd_pack_i16(const float* gz, const int16_t* y_int, const float* alpha, const float* mean,
                                      const float* invstd, const float* gamma, const float* gscale,
                                      const uint32_t* ymax_bits, int64_t n_pix, int32_t C, int32_t grad_mode,
                                      double* sums_ws, uint32_t* gmax_bits, float* consts_ws, float* dgamma,
-                                     float* dbeta, uint32_t* amax_bits, uint16_t* gys, void* stream) {
+                                     float* dbeta, uint32_t* amax_bits, uint16_t* gys, int32_t stats_ready,
+                                     void* stream) {
   BDBNN_REQUIRE(alpha != nullptr, "bn_bwd_pack_i16: NULL alpha");
   return bn_bwd_pack_impl(gz, y_int, alpha, mean, invstd, gamma, gscale, ymax_bits, n_pix, C, grad_mode, sums_ws,
-                          gmax_bits, consts_ws, dgamma, dbeta, amax_bits, gys, stream);
+                          gmax_bits, consts_ws, dgamma, dbeta, amax_bits, gys, stats_ready, stream);
 }
 
 // ===================================================================================================

@@ -58,14 +58,13 @@ act_pack_kernel(const float* __restrict__ x, int64_t n_words, int32_t C, int32_t
   }
 }
 
-// One block per output channel.
-__global__ void __launch_bounds__(256)
-weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32_t T, int32_t Cw,
-                   float* __restrict__ alpha, uint32_t* __restrict__ wsign,
-                   uint16_t* __restrict__ wf, uint16_t* __restrict__ wt, uint8_t* __restrict__ wf8,
-                   float* __restrict__ gscale, float* __restrict__ inv_gscale, uint16_t one16,
-                   uint32_t* __restrict__ wmask_inline, int wt_inline) {
-  const int o = blockIdx.x;
+// One block per output channel (o).
+__device__ __forceinline__ void
+weight_pack_body(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32_t T, int32_t Cw,
+                 float* __restrict__ alpha, uint32_t* __restrict__ wsign,
+                 uint16_t* __restrict__ wf, uint16_t* __restrict__ wt, uint8_t* __restrict__ wf8,
+                 float* __restrict__ gscale, float* __restrict__ inv_gscale, uint16_t one16,
+                 uint32_t* __restrict__ wmask_inline, int wt_inline, const int o) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int per = Cin * T;
   const float* Wo = W + int64_t(o) * per;
@@ -122,15 +121,25 @@ weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32
   }
 }
 
+__global__ void __launch_bounds__(256)
+weight_pack_kernel(const float* __restrict__ W, int32_t Cout, int32_t Cin, int32_t T, int32_t Cw,
+                   float* __restrict__ alpha, uint32_t* __restrict__ wsign,
+                   uint16_t* __restrict__ wf, uint16_t* __restrict__ wt, uint8_t* __restrict__ wf8,
+                   float* __restrict__ gscale, float* __restrict__ inv_gscale, uint16_t one16,
+                   uint32_t* __restrict__ wmask_inline, int wt_inline) {
+  weight_pack_body(W, Cout, Cin, T, Cw, alpha, wsign, wf, wt, wf8, gscale, inv_gscale, one16, wmask_inline, wt_inline,
+                   int(blockIdx.x));
+}
+
 // dgrad operand wt[c][T-1-t][o] = alpha[o] > 0 ? sign(W[o][c][t]) : 0 as a 32x32 tile transpose: reads run along
 // (c,t) for one filter, writes run along o (the per-filter kernel's scattered 2-byte stores cost 50 us at
 // 512x512x9).  grid = (ceil(per/32), ceil(Cout/32)), block = (32, 8).
-__global__ void __launch_bounds__(256)
-weight_wt_kernel(const float* __restrict__ W, const float* __restrict__ alpha, int32_t Cout, int32_t Cin, int32_t T,
-                 uint16_t* __restrict__ wt, uint16_t one16) {
+__device__ __forceinline__ void
+weight_wt_body(const float* __restrict__ W, const float* __restrict__ alpha, int32_t Cout, int32_t Cin, int32_t T,
+               uint16_t* __restrict__ wt, uint16_t one16, const int bx, const int by) {
   __shared__ uint16_t tile[32][33];
   const int per = Cin * T;
-  const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  const int i0 = bx * 32, o0 = by * 32;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int o = o0 + r, i = i0 + threadIdx.x;
     uint16_t sg = 0;
@@ -148,6 +157,55 @@ weight_wt_kernel(const float* __restrict__ W, const float* __restrict__ alpha, i
       wt[(int64_t(c) * T + (T - 1 - t)) * Cout + o] = tile[threadIdx.x][r];
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+weight_wt_kernel(const float* __restrict__ W, const float* __restrict__ alpha, int32_t Cout, int32_t Cin, int32_t T,
+                 uint16_t* __restrict__ wt, uint16_t one16) {
+  weight_wt_body(W, alpha, Cout, Cin, T, wt, one16, int(blockIdx.x), int(blockIdx.y));
+}
+
+// ---- all binary convs of a network in two launches (one multi-tensor pass over the weights) ----
+// 16 + 16 per-layer launches of a ResNet-18 step each fill a fraction of the GPU (64..512 blocks of a few KB);
+// batched, the same work is one grid of sum(Cout) filter blocks plus one grid of transpose tiles.
+constexpr int kPackMaxLayers = 32;
+struct WPackTable {
+  const float* W[kPackMaxLayers];
+  float* alpha[kPackMaxLayers];
+  uint32_t* wsign[kPackMaxLayers];
+  uint32_t* wmask[kPackMaxLayers];
+  uint16_t* wf[kPackMaxLayers];
+  uint16_t* wt[kPackMaxLayers];
+  uint8_t* wf8[kPackMaxLayers];
+  float* gscale[kPackMaxLayers];
+  float* inv_gscale[kPackMaxLayers];
+  int32_t Cout[kPackMaxLayers], Cin[kPackMaxLayers], T[kPackMaxLayers];
+  int32_t blk0[kPackMaxLayers + 1];    // first filter block of layer l (prefix sums of Cout)
+  int32_t tile0[kPackMaxLayers + 1];   // first transpose tile of layer l
+  int32_t n;
+};
+
+__device__ __forceinline__ int wpack_find(const int32_t* start, int n, int b) {
+  int l = 0;
+  while (l + 1 < n && b >= start[l + 1]) ++l;
+  return l;
+}
+
+__global__ void __launch_bounds__(256)
+weight_pack_multi_kernel(const __grid_constant__ WPackTable tab, uint16_t one16) {
+  const int l = wpack_find(tab.blk0, tab.n, int(blockIdx.x));
+  const int Cin = tab.Cin[l];
+  weight_pack_body(tab.W[l], tab.Cout[l], Cin, tab.T[l], (Cin + 31) / 32, tab.alpha[l], tab.wsign[l], tab.wf[l],
+                   nullptr, tab.wf8[l], tab.gscale[l], tab.inv_gscale[l], one16, tab.wmask[l], 0,
+                   int(blockIdx.x) - tab.blk0[l]);
+}
+
+__global__ void __launch_bounds__(256)
+weight_wt_multi_kernel(const __grid_constant__ WPackTable tab, uint16_t one16) {
+  const int l = wpack_find(tab.tile0, tab.n, int(blockIdx.x));
+  const int t = int(blockIdx.x) - tab.tile0[l];
+  const int tiles_x = (tab.Cin[l] * tab.T[l] + 31) / 32;
+  weight_wt_body(tab.W[l], tab.alpha[l], tab.Cout[l], tab.Cin[l], tab.T[l], tab.wt[l], one16, t % tiles_x, t / tiles_x);
 }
 
 // sign bits -> fp8 e4m3 +-1 bytes (0x38 / 0xB8), C % 32 == 0: word w expands to 32 consecutive bytes.
@@ -334,6 +392,50 @@ extern "C" int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int3
   if (blocks > 1024) blocks = 1024;
   flat_mask_kernel<<<unsigned(blocks), 256, 0, cudaStream_t(stream)>>>(W, n, wmask_bits);
   return check_launch("flat_mask_kernel");
+}
+
+extern "C" int bdbnn_weight_pack_multi(int32_t count, const float* const* W_host, const int32_t* Cout_host,
+                                       const int32_t* Cin_host, const int32_t* taps_host, float* const* alpha_host,
+                                       uint32_t* const* wsign_host, uint32_t* const* wmask_host,
+                                       uint16_t* const* wf_host, uint16_t* const* wt_host, uint8_t* const* wf8_host,
+                                       float* const* gscale_host, float* const* inv_gscale_host, int32_t fmt,
+                                       void* stream) {
+  BDBNN_REQUIRE(fmt == BDBNN_FMT_FP16 || fmt == BDBNN_FMT_BF16, "weight_pack_multi: bad operand format");
+  BDBNN_REQUIRE(count >= 0, "weight_pack_multi: bad count");
+  BDBNN_REQUIRE(count == 0 || (W_host && Cout_host && Cin_host && taps_host && alpha_host && wsign_host && wmask_host &&
+                               wf_host && wt_host && wf8_host && gscale_host && inv_gscale_host),
+                "weight_pack_multi: NULL table");
+  cudaStream_t st = cudaStream_t(stream);
+  for (int off = 0; off < count; off += kPackMaxLayers) {
+    const int cnt = count - off < kPackMaxLayers ? count - off : kPackMaxLayers;
+    WPackTable tab;
+    memset(&tab, 0, sizeof(tab));
+    tab.n = cnt;
+    int blocks = 0, tiles = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const int l = off + i;
+      const int per = Cin_host[l] * taps_host[l];
+      BDBNN_REQUIRE(W_host[l] && alpha_host[l] && wsign_host[l] && wmask_host[l] && wt_host[l] && gscale_host[l] &&
+                        inv_gscale_host[l], "weight_pack_multi: NULL pointer in layer %d", l);
+      BDBNN_REQUIRE(Cout_host[l] > 0 && per > 0 && (per & 31) == 0,
+                    "weight_pack_multi: layer %d needs Cin*taps %% 32 == 0 (use bdbnn_weight_pack)", l);
+      tab.W[i] = W_host[l]; tab.alpha[i] = alpha_host[l]; tab.wsign[i] = wsign_host[l]; tab.wmask[i] = wmask_host[l];
+      tab.wf[i] = wf_host[l]; tab.wt[i] = wt_host[l]; tab.wf8[i] = wf8_host[l];
+      tab.gscale[i] = gscale_host[l]; tab.inv_gscale[i] = inv_gscale_host[l];
+      tab.Cout[i] = Cout_host[l]; tab.Cin[i] = Cin_host[l]; tab.T[i] = taps_host[l];
+      tab.blk0[i] = blocks; tab.tile0[i] = tiles;
+      blocks += Cout_host[l];
+      tiles += ((per + 31) / 32) * ((Cout_host[l] + 31) / 32);
+    }
+    tab.blk0[cnt] = blocks; tab.tile0[cnt] = tiles;
+    weight_pack_multi_kernel<<<unsigned(blocks), 256, 0, st>>>(tab, one_bits(fmt));
+    int rc = check_launch("weight_pack_multi_kernel");
+    if (rc) return rc;
+    weight_wt_multi_kernel<<<unsigned(tiles), dim3(32, 8), 0, st>>>(tab, one_bits(fmt));
+    rc = check_launch("weight_wt_multi_kernel");
+    if (rc) return rc;
+  }
+  return BDBNN_OK;
 }
 
 extern "C" int bdbnn_grad_pack(const float* gy, const float* gscale, int64_t n_pix, int32_t Cout,

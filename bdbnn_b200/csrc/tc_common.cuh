@@ -414,6 +414,10 @@ struct TcConvLaunch {
   // (sum y, sum y^2 as doubles [2*Nout]; max|y| bits [Nout]); NULL = off.  Zeroed by the caller.
   double* bn_sums;
   uint32_t* bn_ymax;
+  // dgrad only (persistent kernel, stride 1): bn_sums / bn_ymax receive the BACKWARD statistics of the BatchNorm
+  // unit that produced this conv's input — sum gz, sum gz*yhat, max|gz| with gz = this launch's result — using
+  // that unit's int16 conv result st_y [pixels][Nout] and per-channel alpha / mean / invstd
+  const int16_t* st_y; const float* st_alpha; const float* st_mean; const float* st_invstd;
   // stem conv: A is an overlapping-window view (make_window_map) instead of a dense NHWC tensor
   int win;                       // 0 = dense NHWC
   uint64_t win_stride, win_row_stride, win_img_stride;

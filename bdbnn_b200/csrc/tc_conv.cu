@@ -531,9 +531,14 @@ extern "C" int bdbnn_binconv_fwd_tc8(const uint8_t* xb_fp8, const uint8_t* wf_fp
   return rc;
 }
 
-extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
-                                      const uint16_t* wt_bf16, const uint32_t* mask_bits, const float* add,
-                                      float* gx, const bdbnn_conv_shape* s, void* stream) {
+struct DgradStats {      // backward statistics of the BatchNorm unit that produced this conv's input (see tc_common.cuh)
+  const int16_t* y_int; const float* alpha; const float* mean; const float* invstd;
+  double* sums; uint32_t* gmax;
+};
+
+static int dgrad_tc_impl(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
+                         const uint16_t* wt_bf16, const uint32_t* mask_bits, const float* add, float* gx,
+                         const bdbnn_conv_shape* s, const DgradStats* stats, void* stream) {
   int rc = validate_shape(s);
   if (rc) return rc;
   BDBNN_REQUIRE(gys_bf16 && wt_bf16 && mask_bits && gx, "binconv_dgrad_tc: NULL pointer");
@@ -574,6 +579,10 @@ extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mod
       L.fmt = grad_mode == BDBNN_GRAD_FP16S ? BDBNN_FMT_FP16 : BDBNN_FMT_BF16;
       L.amax_bits = grad_mode == BDBNN_GRAD_FP16S ? amax_bits : nullptr;
       L.add = add;
+      if (stats) {
+        L.bn_sums = stats->sums; L.bn_ymax = stats->gmax;
+        L.st_y = stats->y_int; L.st_alpha = stats->alpha; L.st_mean = stats->mean; L.st_invstd = stats->invstd;
+      }
       ++n_launch;
     }
   if (empty_phase) {
@@ -582,10 +591,38 @@ extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mod
     if (add != nullptr && add != gx) BDBNN_CUDA(cudaMemcpyAsync(gx, add, bytes, cudaMemcpyDeviceToDevice, st));
     else if (add == nullptr) BDBNN_CUDA(cudaMemsetAsync(gx, 0, bytes, st));
   }
+  if (stats) {
+    // one phase (stride 1), persistent kernel only: its epilogue owns the statistics
+    if (n_launch != 1 || empty_phase) { set_error("binconv_dgrad_tc_stats: needs stride 1"); return BDBNN_ERR_UNSUPPORTED; }
+    rc = bn_stats_zero(stats->sums, stats->gmax, s->Cin, st);
+    if (rc) return rc;
+    rc = launch_tc_conv2(Ls[0], 1, st);
+    if (rc == BDBNN_ERR_UNSUPPORTED) set_error("binconv_dgrad_tc_stats: geometry not supported by the persistent kernel");
+    return rc;
+  }
   for (int i = 0; i < n_launch; ++i) {
     rc = launch_tc_conv<1>(Ls[i], st);
     if (rc) return rc;
   }
   return BDBNN_OK;
+}
+
+extern "C" int bdbnn_binconv_dgrad_tc(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
+                                      const uint16_t* wt_bf16, const uint32_t* mask_bits, const float* add,
+                                      float* gx, const bdbnn_conv_shape* s, void* stream) {
+  return dgrad_tc_impl(gys_bf16, grad_mode, amax_bits, wt_bf16, mask_bits, add, gx, s, nullptr, stream);
+}
+
+extern "C" int bdbnn_binconv_dgrad_tc_stats(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
+                                            const uint16_t* wt_bf16, const uint32_t* mask_bits, const float* add,
+                                            float* gx, const bdbnn_conv_shape* s, const int16_t* prod_y_int,
+                                            const float* prod_alpha, const float* prod_mean,
+                                            const float* prod_invstd, double* prod_sums, uint32_t* prod_gmax,
+                                            void* stream) {
+  BDBNN_REQUIRE(prod_y_int && prod_alpha && prod_mean && prod_invstd && prod_sums && prod_gmax,
+                "binconv_dgrad_tc_stats: NULL statistics pointer");
+  BDBNN_REQUIRE(s && s->stride == 1 && s->Cin <= 512, "binconv_dgrad_tc_stats: needs stride 1 and Cin <= 512");
+  const DgradStats stats = {prod_y_int, prod_alpha, prod_mean, prod_invstd, prod_sums, prod_gmax};
+  return dgrad_tc_impl(gys_bf16, grad_mode, amax_bits, wt_bf16, mask_bits, add, gx, s, &stats, stream);
 }
 

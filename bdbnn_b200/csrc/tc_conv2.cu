@@ -58,6 +58,13 @@ struct TcConv2Params {
   int16_t* out_i16;          // MODE 0: write the exact integer accumulator as int16 (y = alpha * int, |int| <= taps*Kc)
   double* bn_sums;           // MODE 0: per-channel sum / sum of squares of the result [2*Nout] (or NULL)
   uint32_t* bn_ymax;         // MODE 0: per-channel max|result| bits [Nout]
+  // MODE 1 (dgrad whose result gx IS the gradient gz of the BatchNorm unit that produced this conv's input):
+  // accumulate that unit's backward statistics here — bn_sums = [sum gz | sum gz*yhat], bn_ymax = max|gz| —
+  // with yhat = (alpha*y_int - mean)*invstd read from the producer's int16 conv result (same pixel grid, Nout ch).
+  const int16_t* st_y;
+  const float* st_alpha;
+  const float* st_mean;
+  const float* st_invstd;
   long long* trace;          // optional clock64 trace of CTA 0 (bdbnn_debug_trace), else NULL
 };
 
@@ -106,7 +113,8 @@ __device__ __forceinline__ SuperGeom super_geom(const TcConv2Params& p, int sup)
 // per unit of work every SM fetches half the B bytes from shared memory — the measured limiter of the SS-mode
 // MMAs (DESIGN.md §5 finding 3).  Barriers the MMA thread waits on live in the leader; the peer's TMA loads
 // complete_tx on them (cta_group::2 TMA form) and its epilogue warps arrive on them through shared::cluster.
-template <int MODE, int CG>
+// BST (MODE 1 only): accumulate the producing unit's BatchNorm backward statistics in the epilogue (see params).
+template <int MODE, int CG, bool BST = false>
 __global__ void __launch_bounds__(kTc2Threads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const TcConv2Params p) {
@@ -117,9 +125,10 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t tap_shift_rows[kMaxTaps];   // halo: row offset of tap i inside the patch
   // BatchNorm statistics of this CTA's output rows (MODE 0 with p.bn_sums): fp32 partials, flushed once
-  __shared__ float stat_sum[MODE == 0 ? kMaxStatCh : 1], stat_sq[MODE == 0 ? kMaxStatCh : 1];
-  __shared__ uint32_t stat_max[MODE == 0 ? kMaxStatCh : 1];
-  const bool do_stats = MODE == 0 && p.bn_sums != nullptr;
+  constexpr bool kStats = MODE == 0 || BST;
+  __shared__ float stat_sum[kStats ? kMaxStatCh : 1], stat_sq[kStats ? kMaxStatCh : 1];
+  __shared__ uint32_t stat_max[kStats ? kMaxStatCh : 1];
+  const bool do_stats = kStats && p.bn_sums != nullptr;   // MODE 0: statistics of y; MODE 1 (BST): backward statistics of gz
   if (do_stats)
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { stat_sum[i] = 0.f; stat_sq[i] = 0.f; stat_max[i] = 0u; }
 
@@ -155,13 +164,18 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
+  if (CG == 2) {
+    // both CTAs of the pair are running and their barriers initialised before the pair-wide TMEM allocation and
+    // before anything signals a peer barrier
+    __syncthreads();
+    cluster_sync_all();
+  }
   if (warp == kEpiWarps + 1) {
     if (CG == 2) tmem_alloc_cg2(smem_u32(&tmem_slot), 512);
     else tmem_alloc(smem_u32(&tmem_slot), 512);
   }
   tc_fence_before();
   __syncthreads();
-  if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
@@ -313,7 +327,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // every 32-column block of the N tile, across tiles and work items, and flushes them to shared memory
     // only when the N tile changes or the CTA is done (per-block shuffles + atomics cost 25-35 % of the
     // forward kernels when done per 32x32 block).
-    constexpr int kAcc = MODE == 0 ? 4 : 1;          // this group's 32-column blocks of the widest N tile (256)
+    constexpr int kAcc = kStats ? 4 : 1;             // this group's 32-column blocks of the widest N tile (256)
     float4 acc_s[kAcc], acc_q[kAcc], acc_m[kAcc];
 #pragma unroll
     for (int cb = 0; cb < kAcc; ++cb) acc_s[cb] = acc_q[cb] = acc_m[cb] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -439,12 +453,27 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           float4 a16 = make_float4(1.f, 1.f, 1.f, 1.f);
           if (MODE == 0 && p.out_i16 != nullptr)
             a16 = __ldg(reinterpret_cast<const float4*>(p.alpha + nn0 + c0 + cq * 4));
+          float4 st_a = make_float4(0.f, 0.f, 0.f, 0.f), st_b = st_a;      // yhat = y_int * st_a - st_b
+          if (BST && do_stats) {
+            const int ch = nn0 + c0 + cq * 4;
+            const float4 al = __ldg(reinterpret_cast<const float4*>(p.st_alpha + ch));
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(p.st_mean + ch));
+            const float4 is = __ldg(reinterpret_cast<const float4*>(p.st_invstd + ch));
+            st_a = make_float4(al.x * is.x, al.y * is.y, al.z * is.z, al.w * is.w);
+            st_b = make_float4(mu.x * is.x, mu.y * is.y, mu.z * is.z, mu.w * is.w);
+          }
           float4 addv[8];
           if (MODE == 1 && p.add != nullptr) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               addv[i] = offs[i] >= 0 ? *reinterpret_cast<const float4*>(p.add + offs[i] + c0 + cq * 4)   // may alias out
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          uint2 yv[BST ? 8 : 1];        // producer's y_int for the 8 row groups: all loads in flight before the stores
+          if (BST && do_stats) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              yv[i] = offs[i] >= 0 ? __ldg(reinterpret_cast<const uint2*>(p.st_y + offs[i] + c0 + cq * 4)) : make_uint2(0u, 0u);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -465,10 +494,18 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 *reinterpret_cast<float4*>(p.out + offs[i] + c0 + cq * 4) = o;
               }
               if (do_stats) {
-                float4& ss = acc_s[MODE == 0 ? ca : 0]; float4& sq = acc_q[MODE == 0 ? ca : 0];
-                float4& mx = acc_m[MODE == 0 ? ca : 0];
+                float4& ss = acc_s[kStats ? ca : 0]; float4& sq = acc_q[kStats ? ca : 0];
+                float4& mx = acc_m[kStats ? ca : 0];
                 ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
+                if (BST) {            // sum gz * yhat of the producing BatchNorm unit
+                  const uint2 yr = yv[BST ? i : 0];
+                  sq.x += o.x * fmaf(float(int16_t(yr.x & 0xffffu)), st_a.x, -st_b.x);
+                  sq.y += o.y * fmaf(float(int16_t(yr.x >> 16)), st_a.y, -st_b.y);
+                  sq.z += o.z * fmaf(float(int16_t(yr.y & 0xffffu)), st_a.z, -st_b.z);
+                  sq.w += o.w * fmaf(float(int16_t(yr.y >> 16)), st_a.w, -st_b.w);
+                } else {
                 sq.x += o.x * o.x; sq.y += o.y * o.y; sq.z += o.z * o.z; sq.w += o.w * o.w;
+                }
                 mx.x = fmaxf(mx.x, fabsf(o.x)); mx.y = fmaxf(mx.y, fabsf(o.y));
                 mx.z = fmaxf(mx.z, fabsf(o.z)); mx.w = fmaxf(mx.w, fabsf(o.w));
               }
@@ -544,7 +581,9 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   // forward: the fp8 layers with Cout >= 256 (bit 1 of the knob)
   // CTA pairs (cta_group::2): each CTA stages half of the N tile, so the widest tile (256) costs a CTA what a
   // 128-wide one costs alone — use it whenever the channel count allows.  BDBNN_TC_CG2=0: single-CTA MMAs.
-  static const int cg2_env = [] { const char* e = getenv("BDBNN_TC_CG2"); return e ? atoi(e) : 1; }();
+  // Measured on B200 (profiles/r2_cg2_ablation.txt): correct, but a pair MMA costs more than two independent ones
+  // on these shapes (layer1 N=64: MMA pipeline 193 us vs 150 us; layer3 dgrad N=256: 82 vs 68 us) -> default off.
+  static const int cg2_env = [] { const char* e = getenv("BDBNN_TC_CG2"); return e ? atoi(e) : 0; }();
   p.cg = cg2_env ? 2 : 1;
   const bool wide = L.Nout % 256 == 0 && (p.cg == 2 || (mode == 1 && !f8 && (bn256 & 1)) || (mode == 0 && f8 && (bn256 & 2)));
   p.BN = wide ? 256 : (L.Nout >= 128 ? 128 : 64);
@@ -562,9 +601,12 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   p.out_i16 = mode == 0 ? L.out_i16 : nullptr;
   if (L.out_i16 && (mode != 0 || L.n_taps * L.Kc * L.a_halves > 32767)) return BDBNN_ERR_UNSUPPORTED;
   p.fmt = L.fmt; p.amax_bits = L.amax_bits; p.add = L.add;
-  p.bn_sums = (mode == 0 && L.Nout <= kMaxStatCh) ? L.bn_sums : nullptr;
+  p.bn_sums = L.Nout <= kMaxStatCh ? L.bn_sums : nullptr;
   p.bn_ymax = L.bn_ymax;
   if (L.bn_sums && !p.bn_sums) return BDBNN_ERR_UNSUPPORTED;
+  p.st_y = L.st_y; p.st_alpha = L.st_alpha; p.st_mean = L.st_mean; p.st_invstd = L.st_invstd;
+  if (mode == 1 && L.bn_sums && !(L.st_y && L.st_alpha && L.st_mean && L.st_invstd && L.out_step == 1))
+    return BDBNN_ERR_UNSUPPORTED;
   p.b_bytes = uint32_t(p.BN / p.cg) * row_bytes;       // rows of the weight tile THIS CTA stages
 
   int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
@@ -573,7 +615,11 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
     dw0 = min(dw0, int(p.tap_dw[i])); dw1 = max(dw1, int(p.tap_dw[i]));
   }
   const int dh_span = dh1 - dh0, dw_span = dw1 - dw0;
-  const int PW = L.OW + dw_span;
+  // BDBNN_TC_PW8=1 (experiment): pad the patch width to a multiple of 8 pixel rows so that the dh row shifts of
+  // the tap views stay aligned to the 8-row swizzle atoms
+  static const int pw8_env = [] { const char* e = getenv("BDBNN_TC_PW8"); return e ? atoi(e) : 0; }();
+  int PW = L.OW + dw_span;
+  if (pw8_env && !L.win) PW = (PW + 7) & ~7;
   const int super_rows = p.TS * kTileM;  // padded rows per super tile
   CUtensorMap tmA, tmB;
   int rc;
@@ -640,7 +686,8 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   const uint32_t kStaging = uint32_t(kEpiWarps) * 4096u;   // epilogue transpose tiles
   const uint32_t fixed = (p.halo ? 2u * p.patch_bytes : 0u) + kStaging;
   // 227 KB per CTA minus static shared memory (barriers; MODE 0 also holds 6 KB of BN statistics)
-  const uint32_t budget = 224u * 1024u - 1024u - (mode == 0 ? 3u * kMaxStatCh * 4u : 0u);
+  const bool bst = mode == 1 && p.bn_sums != nullptr;
+  const uint32_t budget = 224u * 1024u - 1024u - ((mode == 0 || bst) ? 3u * kMaxStatCh * 4u : 0u);
   if (fixed + 2u * p.stage_bytes > budget) return BDBNN_ERR_UNSUPPORTED;
   int stages = int((budget - fixed) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -672,6 +719,7 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
     return BDBNN_OK;
   };
   if (mode == 0) rc = p.cg == 2 ? launch(tc_conv2_kernel<0, 2>) : launch(tc_conv2_kernel<0, 1>);
+  else if (bst)  rc = p.cg == 2 ? launch(tc_conv2_kernel<1, 2, true>) : launch(tc_conv2_kernel<1, 1, true>);
   else           rc = p.cg == 2 ? launch(tc_conv2_kernel<1, 2>) : launch(tc_conv2_kernel<1, 1>);
   if (rc) return rc;
   return check_launch("tc_conv2_kernel");

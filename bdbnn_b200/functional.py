@@ -598,8 +598,63 @@ def y_i16_enabled():
     return os.environ.get("BDBNN_Y_I16", "1") != "0"
 
 
+def bwd_stats_enabled():
+    """BDBNN_BWD_STATS (default 1): the data-gradient kernel of the NEXT unit accumulates this unit's BatchNorm
+    backward sums (its result is this unit's gz), so the separate reduction pass over gz and y is skipped."""
+    return os.environ.get("BDBNN_BWD_STATS", "1") != "0"
+
+
 def fuse_enabled():
     return os.environ.get(_FUSE_ENV, "1") != "0"
+
+
+def prepack_enabled():
+    """BDBNN_PREPACK (default 1): the network shells pack the weights of all their binary convs in two launches at
+    the start of the forward (bdbnn_weight_pack_multi) instead of two small launches inside every unit."""
+    return os.environ.get("BDBNN_PREPACK", "1") != "0"
+
+
+def prepack_weights(items):
+    """items: list of (weight [Cout,Cin,kh,kw] CUDA fp32, use8) for the binary convs of one forward pass.
+    Returns {weight.data_ptr(): (version, fmt, use8, w, alpha, wsign, wmask, wf, wf8, wt, gscale, inv_gscale)} — the
+    tensors `_ConvBNAddUnit` would otherwise produce itself with one bdbnn_weight_pack call per layer."""
+    if not items:
+        return {}
+    L = _lib.lib()
+    fmt = grad_mode()[3]
+    dev = items[0][0].device
+    n = len(items)
+    ws, packs = [], []
+    for weight, use8 in items:
+        _require_cuda(weight, "prepack_weights")
+        w = weight.detach().contiguous()
+        cout, cin, kh, kw = w.shape
+        T, cw = kh * kw, (cin + 31) // 32
+        if (cin * T) % 32:
+            raise RuntimeError("prepack_weights: Cin*kh*kw must be a multiple of 32")
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        alpha, gscale, inv_gscale = torch.empty((cout,), **f32), torch.empty((cout,), **f32), torch.empty((cout,), **f32)
+        wsign = torch.empty((cout, T, cw), **i32)
+        wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
+        wf = torch.empty((cout, T, cin), dtype=torch.int16, device=dev) if not use8 else None
+        wf8 = torch.empty((cout, T, cin), dtype=torch.uint8, device=dev) if use8 else None
+        wt = torch.empty((cin, T, cout), dtype=torch.int16, device=dev)
+        ws.append(w)
+        packs.append((alpha, wsign, wmask, wf, wf8, wt, gscale, inv_gscale))
+    P = ctypes.c_void_p * n
+    I = ctypes.c_int32 * n
+    ptrs = lambda k: P(*[(p[k].data_ptr() if p[k] is not None else 0) for p in packs])
+    _lib.check(L.bdbnn_weight_pack_multi(
+        n, P(*[w.data_ptr() for w in ws]), I(*[w.shape[0] for w in ws]), I(*[w.shape[1] for w in ws]),
+        I(*[w.shape[2] * w.shape[3] for w in ws]), ptrs(0), ptrs(1), ptrs(2), ptrs(3), ptrs(5), ptrs(4), ptrs(6), ptrs(7),
+        fmt, _stream()), "weight_pack_multi")
+    _lib.count(2 * ((n + 31) // 32))
+    return {weight.data_ptr(): (weight._version, fmt, bool(use8), w) + pk
+            for (weight, use8), w, pk in zip(items, ws, packs)}
+
+
+_PREPACKED = {}     # filled by the network shells for the duration of one forward pass (same thread)
 
 
 def unit_supported(x_shape, w_shape, stride, padding):
@@ -630,6 +685,13 @@ class _ConvBNAddUnit(torch.autograd.Function):
         ctx.set_materialize_grads(False)     # no zero tensors for the (integer) pack outputs in backward
         L = _lib.lib()
         sh = conv_shape(x.shape, weight.shape, stride, padding)
+        # x produced by another fused unit (identity shortcut: this unit's dgrad result + gz IS that unit's gz):
+        # its int16 conv result and BN constants let this unit's dgrad epilogue accumulate its backward sums
+        prod = getattr(x, "_bdbnn_bnctx", None)
+        ctx.prod_bn = None
+        if (prod is not None and res_is_x and int(stride) == 1 and bwd_stats_enabled() and
+                getattr(x, "_bdbnn_pack_version", None) == x._version and x.shape[1] <= 512):
+            ctx.prod_bn = prod
         dev = x.device
         n, cin, h, wd = x.shape
         cout, _, kh, kw = weight.shape
@@ -653,17 +715,24 @@ class _ConvBNAddUnit(torch.autograd.Function):
             xb8 = torch.empty((n, h, wd, cin), dtype=torch.uint8, device=dev)
             _lib.check(L.bdbnn_bits_to_fp8(_p(xs), n * h * wd, cin, _p(xb8), st), "bits_to_fp8")
             _lib.count(1)
-        w = weight.detach().contiguous()
-        alpha = torch.empty((cout,), dtype=torch.float32, device=dev)
-        wsign = torch.empty((cout, T, cw), **i32)
-        wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
-        wf = torch.empty((cout, T, cin), dtype=torch.int16, device=dev) if not use8 else None
-        wf8 = torch.empty((cout, T, cin), dtype=torch.uint8, device=dev) if use8 else None
-        wt = torch.empty((cin, T, cout), dtype=torch.int16, device=dev)
-        gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
-        inv_gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
-        _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask), _p(wf), _p(wt),
-                                       _p(wf8), _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
+        pre = _PREPACKED.get(weight.data_ptr())
+        if pre is not None and pre[0] == weight._version and pre[1] == fmt and pre[2] == use8:
+            # packed with every other binary conv of the network at the start of this forward (prepack_weights)
+            w, alpha, wsign, wmask, wf, wf8, wt, gscale, inv_gscale = pre[3:]
+            n_wpack = 0
+        else:
+            w = weight.detach().contiguous()
+            alpha = torch.empty((cout,), dtype=torch.float32, device=dev)
+            wsign = torch.empty((cout, T, cw), **i32)
+            wmask = torch.empty(((cout * cin * T + 31) // 32,), **i32)
+            wf = torch.empty((cout, T, cin), dtype=torch.int16, device=dev) if not use8 else None
+            wf8 = torch.empty((cout, T, cin), dtype=torch.uint8, device=dev) if use8 else None
+            wt = torch.empty((cin, T, cout), dtype=torch.int16, device=dev)
+            gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
+            inv_gscale = torch.empty((cout,), dtype=torch.float32, device=dev)
+            _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask), _p(wf), _p(wt),
+                                           _p(wf8), _p(gscale), _p(inv_gscale), fmt, st), "weight_pack")
+            n_wpack = 2
         # BN batch statistics of y are accumulated by the conv kernel's epilogue (BDBNN_CONV_STATS=0: separate pass)
         sums = torch.empty((2 * cout,), dtype=torch.float64, device=dev)
         ymax = torch.empty((cout,), **i32)
@@ -688,7 +757,7 @@ class _ConvBNAddUnit(torch.autograd.Function):
                 with _timed("binconv_fwd_tc", key, algorithmic_bytes("fwd_tc", sh)):
                     _lib.check(L.bdbnn_binconv_fwd_tc(_p(xb), _p(wf), fmt, _p(alpha), _p(y), ctypes.byref(sh), s_ptr,
                                                       m_ptr, st), "binconv_fwd_tc")
-        _lib.count(3)
+        _lib.count(1 + n_wpack)
         n_pix = n * sh.Ho * sh.Wo
         if res_is_x:            # identity shortcut: the residual IS the conv input (one autograd edge)
             rc = _nhwc(x.detach())
@@ -718,12 +787,14 @@ class _ConvBNAddUnit(torch.autograd.Function):
                                           1 if in_conv else 0, st), "bn_fwd")
         _lib.count(2 if in_conv else 3)
         ctx.y_i16 = i16
+        ctx.bnctx_out = (y, alpha, mean, invstd) if i16 else None
         ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
         ctx.shapes = (tuple(x.shape), tuple(weight.shape))
         ctx.has_res = residual is not None and sc_weight is None
         ctx.res_is_x = bool(res_is_x)
         ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale, alpha,
                               *sc_saved)
+        _ConvBNAddUnit._last_bnctx = ctx.bnctx_out       # picked up by conv_bn_add right after apply() (same thread)
         if pack:
             if zb8 is not None:
                 ctx.mark_non_differentiable(zs, zm, zb, zb8)
@@ -756,26 +827,50 @@ class _ConvBNAddUnit(torch.autograd.Function):
         amax = torch.empty((1,), **i32)
         gys = torch.empty((sh.N, sh.Ho, sh.Wo, gh * cout), dtype=torch.int16, device=dev)
         ybytes = 2 if ctx.y_i16 else 4
-        with _timed("bn_bwd_pack", key, (8 + 2 * ybytes + 2 * gh) * n_pix * cout):
+        # backward sums already accumulated by the dgrad kernel that produced gz?  (attached to the gradient tensor
+        # by the next unit's backward; identity of y guards against a foreign tensor)
+        ready = 0
+        stt = getattr(gz, "_bdbnn_bwdstats", None)
+        if ctx.y_i16 and stt is not None and stt[2].data_ptr() == y.data_ptr() and stt[3] == gz._version:
+            sums, gmax, ready = stt[0], stt[1], 1
+        with _timed("bn_bwd_pack", key, ((0 if ready else 4 + ybytes) + 4 + ybytes + 2 * gh) * n_pix * cout):
             if ctx.y_i16:
                 _lib.check(L.bdbnn_bn_bwd_pack_i16(_p(g), _p(y), _p(alpha), _p(mean), _p(invstd), _p(gamma), _p(gscale),
                                                    _p(ymax), n_pix, cout, gcode, _p(sums), _p(gmax), _p(consts),
-                                                   _p(dgamma), _p(dbeta), _p(amax), _p(gys), st), "bn_bwd_pack_i16")
+                                                   _p(dgamma), _p(dbeta), _p(amax), _p(gys), ready, st),
+                           "bn_bwd_pack_i16")
             else:
                 _lib.check(L.bdbnn_bn_bwd_pack(_p(g), _p(y), _p(mean), _p(invstd), _p(gamma), _p(gscale), _p(ymax),
                                                n_pix, cout, gcode, _p(sums), _p(gmax), _p(consts), _p(dgamma),
                                                _p(dbeta), _p(amax), _p(gys), st), "bn_bwd_pack")
-        _lib.count(3)
+        _lib.count(2 if ready else 3)
         x_shape, w_shape = ctx.shapes
         gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty(x_shape, dtype=torch.float32, device=dev, memory_format=torch.channels_last)
-            with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh)):
-                # identity shortcut: d/dx = dgrad + gz, summed in the dgrad epilogue (no separate add kernel)
-                _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(xm),
-                                                    _p(g) if ctx.res_is_x else _p(None), _p(gx),
-                                                    ctypes.byref(sh), st), "binconv_dgrad_tc")
-            _lib.count(_dgrad_launches(sh))
+            done = False
+            if ctx.prod_bn is not None and ctx.res_is_x:
+                # gx = dgrad + gz is the producing unit's gz: accumulate ITS BatchNorm backward sums in this epilogue
+                py, palpha, pmean, pinvstd = ctx.prod_bn
+                psums = torch.empty((2 * sh.Cin,), dtype=torch.float64, device=dev)
+                pgmax = torch.empty((sh.Cin,), **i32)
+                with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh) + 2 * gx.numel()):
+                    rc = L.bdbnn_binconv_dgrad_tc_stats(_p(gys), gcode, _p(amax), _p(wt), _p(xm), _p(g), _p(gx),
+                                                        ctypes.byref(sh), _p(py), _p(palpha), _p(pmean), _p(pinvstd),
+                                                        _p(psums), _p(pgmax), st)
+                if rc == 0:
+                    done = True
+                    gx._bdbnn_bwdstats = (psums, pgmax, py, gx._version)
+                    _lib.count(1)
+                elif rc != -3:           # BDBNN_ERR_UNSUPPORTED: plain dgrad below
+                    _lib.check(rc, "binconv_dgrad_tc_stats")
+            if not done:
+                with _timed("binconv_dgrad_tc", key, algorithmic_bytes("dgrad_tc", sh, gh)):
+                    # identity shortcut: d/dx = dgrad + gz, summed in the dgrad epilogue (no separate add kernel)
+                    _lib.check(L.bdbnn_binconv_dgrad_tc(_p(gys), gcode, _p(amax), _p(wt), _p(xm),
+                                                        _p(g) if ctx.res_is_x else _p(None), _p(gx),
+                                                        ctypes.byref(sh), st), "binconv_dgrad_tc")
+                _lib.count(_dgrad_launches(sh))
         if ctx.needs_input_grad[1]:
             gw = torch.empty(w_shape, dtype=torch.float32, device=dev)
             nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
@@ -825,6 +920,8 @@ def conv_bn_add(x, weight, gamma, beta, residual, running_mean, running_var, mom
     if zs is not None:
         z._bdbnn_pack = (zs, zm, zb, fmt, zb8)
         z._bdbnn_pack_version = z._version
+        z._bdbnn_bnctx = _ConvBNAddUnit._last_bnctx      # (y_int, alpha, mean, invstd) of this unit, or None
+    _ConvBNAddUnit._last_bnctx = None
     return z
 
 

@@ -33,6 +33,26 @@ def _fused_unit(x, conv, bn, residual, shortcut=None):
     return z
 
 
+def _prepack(model, x):
+    """Pack the weights of every binary conv that will run as a fused unit in this forward, in two launches
+    (functional.prepack_weights).  Returns True if functional._PREPACKED was filled (caller clears it)."""
+    if not (x.is_cuda and model.training and F_.fuse_enabled() and F_.prepack_enabled() and x.dtype == torch.float32):
+        return False
+    items = []
+    for m in model.modules():
+        if isinstance(m, BinarizeConv2d) and m.impl != "xnor" and not m.ede_active and m.weight.is_cuda:
+            cout, cin, kh, kw = m.weight.shape
+            if (cin * kh * kw) % 32 == 0 and cin % 64 == 0 and cout % 32 == 0:
+                # the fp8 forward is used where the shape allows (same rule as _ConvBNAddUnit)
+                use8 = F_.fwd8_enabled() and cin % 128 == 0 and (cout == 64 or cout % 128 == 0)
+                items.append((m.weight, use8))
+    if not items:
+        return False
+    F_._PREPACKED.clear()
+    F_._PREPACKED.update(F_.prepack_weights(items))
+    return True
+
+
 def _shortcut_args(x, ds):
     """Arguments for the tcgen05 `downsample` path — Sequential(fp32 1x1 Conv2d, BatchNorm2d) in training
     mode on a supported geometry — or None."""
@@ -135,8 +155,13 @@ class ResNetImageNet(nn.Module):
         return mp(bn(y))
 
     def forward(self, x):
-        x = self._stem(x)
-        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        packed = _prepack(self, x)
+        try:
+            x = self._stem(x)
+            x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        finally:
+            if packed:
+                F_._PREPACKED.clear()
         return self.fc(torch.flatten(self.avgpool(x), 1))
 
 
@@ -193,8 +218,13 @@ class ResNetCifar(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        x = self.bn1(self.conv1(x))
-        x = self.layer3(self.layer2(self.layer1(x)))
+        packed = _prepack(self, x)
+        try:
+            x = self.bn1(self.conv1(x))
+            x = self.layer3(self.layer2(self.layer1(x)))
+        finally:
+            if packed:
+                F_._PREPACKED.clear()
         return self.fc(torch.flatten(self.avgpool(x), 1))
 
 

@@ -94,6 +94,15 @@ BDBNN_API int bdbnn_weight_pack(const float* W, int32_t Cout, int32_t Cin, int32
                       float* alpha, uint32_t* wsign_bits, uint32_t* wmask_bits,
                       uint16_t* wf_bf16, uint16_t* wt_bf16, uint8_t* wf_fp8, float* gscale,
                       float* inv_gscale, int32_t fmt, void* stream);
+/* The same packing for ALL binary convs of a network in two launches (one grid of sum(Cout) filter blocks, one
+ * of transpose tiles) instead of two small launches per layer; host tables of `count` entries, per-layer pointers
+ * exactly as bdbnn_weight_pack takes them (wf / wf8 entries may be NULL).  Every layer needs Cin*kh*kw % 32 == 0
+ * (3x3 convs on multiples of 32 channels); taps = kh*kw. */
+BDBNN_API int bdbnn_weight_pack_multi(int32_t count, const float* const* W_host, const int32_t* Cout_host,
+                            const int32_t* Cin_host, const int32_t* taps_host, float* const* alpha_host,
+                            uint32_t* const* wsign_host, uint32_t* const* wmask_host, uint16_t* const* wf_host,
+                            uint16_t* const* wt_host, uint8_t* const* wf8_host, float* const* gscale_host,
+                            float* const* inv_gscale_host, int32_t fmt, void* stream);
 /* sign bits -> fp8 e4m3 +-1 bytes [n_pix][C] (0x38 = +1, 0xB8 = -1), C % 32 == 0: operand of fwd_tc8. */
 BDBNN_API int bdbnn_bits_to_fp8(const uint32_t* sign_bits, int64_t n_pix, int32_t C, uint8_t* xb_fp8, void* stream);
 
@@ -260,7 +269,18 @@ BDBNN_API int bdbnn_bn_bwd_pack_i16(const float* gz, const int16_t* y_int, const
                           const float* invstd, const float* gamma, const float* gscale, const uint32_t* ymax_bits,
                           int64_t n_pix, int32_t C, int32_t grad_mode, double* sums_ws, uint32_t* gmax_bits,
                           float* consts_ws, float* dgamma, float* dbeta, uint32_t* amax_bits, uint16_t* gys,
-                          void* stream);
+                          int32_t stats_ready, void* stream);
+/* bdbnn_bn_bwd_pack_i16(stats_ready = 1): sums_ws (sum gz | sum gz*yhat) and gmax_bits were already accumulated by
+ * the kernel that PRODUCED gz — bdbnn_binconv_dgrad_tc_stats, the data-gradient kernel of the next unit, whose
+ * result (dgrad + shortcut gradient) is this unit's gz: the separate reduction pass over gz and y is skipped.
+ * dgrad_tc_stats = bdbnn_binconv_dgrad_tc (stride 1, persistent kernel, Cin <= 512) + those statistics of the
+ * producing unit: prod_y_int int16 [N,H,W,Cin], prod_alpha / prod_mean / prod_invstd float[Cin];
+ * prod_sums double[2*Cin] and prod_gmax u32[Cin] are zeroed here. */
+BDBNN_API int bdbnn_binconv_dgrad_tc_stats(const uint16_t* gys_bf16, int32_t grad_mode, const uint32_t* amax_bits,
+                                 const uint16_t* wt_bf16, const uint32_t* mask_bits, const float* add, float* gx,
+                                 const bdbnn_conv_shape* s, const int16_t* prod_y_int, const float* prod_alpha,
+                                 const float* prod_mean, const float* prod_invstd, double* prod_sums,
+                                 uint32_t* prod_gmax, void* stream);
 
 /* ---- stem: BatchNorm(train) + MaxPool fused (the BN output is never written) -----------------------
  * bn_pool_fwd: y fp32 NHWC [N,H,W,C] (stem conv output) -> z = maxpool_k,s,p(gamma*(y-mean)*invstd+beta)

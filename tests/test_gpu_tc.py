@@ -488,3 +488,92 @@ def test_backward_tc_full_size_vs_fp64_conv_on_gpu(geom, mode, monkeypatch):
         assert e_max <= tol_max, (name, "max", e_max)
         assert e_l2 <= tol_l2, (name, "l2", e_l2)
     assert (xd.grad[x.abs() > 1] == 0).all() and (wd.grad[w.abs() > 1] == 0).all()
+
+
+@pytest.mark.parametrize("mode", ["fp16s", "bf16x2"])
+@pytest.mark.parametrize("geom", [(3, 64, 20, 20), (2, 128, 14, 14), (4, 256, 7, 7)])
+def test_bn_backward_sums_from_next_units_dgrad_epilogue(geom, mode, monkeypatch):
+    """Two chained identity units (z1 = BN(conv(x)) + x; z2 = BN(conv(z1)) + z1): with BDBNN_BWD_STATS=1 the dgrad
+    kernel of unit 2 accumulates unit 1's BatchNorm backward sums (sum gz1, sum gz1*yhat1, max|gz1|) in its epilogue
+    and unit 1 skips its reduction pass — one launch fewer — with the same gradients as the separate pass."""
+    from bdbnn_b200 import _lib
+    from bdbnn_b200.functional import conv_bn_add
+    monkeypatch.setenv("BDBNN_GRAD_MODE", mode)
+    n, c, h, w = geom
+    g = torch.Generator().manual_seed(7 + sum(geom))
+    x0 = (torch.randn(n, c, h, w, generator=g) * 1.1).cuda().contiguous(memory_format=torch.channels_last)
+    ws = [(torch.randn(c, c, 3, 3, generator=g) * 0.6).cuda() for _ in range(2)]
+    gam = [(torch.rand(c, generator=g) + 0.5).cuda() for _ in range(2)]
+    bet = [(torch.randn(c, generator=g) * 0.2).cuda() for _ in range(2)]
+    gz = torch.randn(n, c, h, w, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    results, launches = {}, {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BDBNN_BWD_STATS", flag)
+        x = x0.clone().requires_grad_(True)
+        wp = [t.clone().requires_grad_(True) for t in ws]
+        gp = [t.clone().requires_grad_(True) for t in gam]
+        bp = [t.clone().requires_grad_(True) for t in bet]
+        rm = [torch.zeros(c, device="cuda") for _ in range(2)]
+        rv = [torch.ones(c, device="cuda") for _ in range(2)]
+        z1 = conv_bn_add(x, wp[0], gp[0], bp[0], x, rm[0], rv[0], 0.1, 1e-5, 1, 1)
+        z2 = conv_bn_add(z1, wp[1], gp[1], bp[1], z1, rm[1], rv[1], 0.1, 1e-5, 1, 1)
+        n0 = _lib.launch_count()
+        z2.backward(gz)
+        torch.cuda.synchronize()
+        launches[flag] = _lib.launch_count() - n0
+        results[flag] = [x.grad] + [t.grad for t in wp + gp + bp]
+    assert launches["1"] == launches["0"] - 1            # unit 1's bn_reduce<bwd> pass is gone
+    for a, b in zip(results["1"], results["0"]):
+        scale = b.abs().max().item() + 1e-30
+        # fp16s: the power-of-two scale of the gradient operand comes from a bound built on these sums, so a last-bit
+        # difference in them may move it by one binade (different fp16 rounding of gys)
+        assert (a - b).abs().max().item() <= (2e-3 if mode == "fp16s" else 2e-5) * scale
+
+
+def test_prepacked_weights_equal_per_layer_packing(monkeypatch):
+    """bdbnn_weight_pack_multi (all binary convs of the network in two launches at the start of the forward) must
+    give exactly the tensors the per-layer bdbnn_weight_pack gives (bit for bit), and the network must use them."""
+    import ctypes
+    from bdbnn_b200 import _lib
+    from bdbnn_b200.functional import _p, _stream, grad_mode, prepack_weights
+    from bdbnn_b200.resnet import ResNetImageNet
+    L = _lib.lib()
+    fmt = grad_mode()[3]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(64, 64, 3, 3, False), (128, 64, 3, 3, False), (128, 128, 3, 3, True), (512, 256, 3, 3, True),
+              (96, 32, 1, 1, False)]
+    ws = [torch.randn(s[:4], device="cuda", generator=g) * 0.7 for s in shapes]
+    ws[1][3].zero_()                                             # alpha == 0 filter
+    packs = prepack_weights([(w, s[4]) for w, s in zip(ws, shapes)])
+    for w, s in zip(ws, shapes):
+        cout, cin, kh, kw, use8 = s
+        T, cw = kh * kw, (cin + 31) // 32
+        i32 = dict(dtype=torch.int32, device="cuda")
+        alpha, gs, igs = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
+        wsign, wmask = torch.empty((cout, T, cw), **i32), torch.empty(((w.numel() + 31) // 32,), **i32)
+        wf = torch.empty((cout, T, cin), dtype=torch.int16, device="cuda") if not use8 else None
+        wf8 = torch.empty((cout, T, cin), dtype=torch.uint8, device="cuda") if use8 else None
+        wt = torch.empty((cin, T, cout), dtype=torch.int16, device="cuda")
+        _lib.check(L.bdbnn_weight_pack(_p(w), cout, cin, kh, kw, _p(alpha), _p(wsign), _p(wmask), _p(wf), _p(wt), _p(wf8),
+                                       _p(gs), _p(igs), fmt, _stream()), "weight_pack")
+        ver, pfmt, p8, _, palpha, pwsign, pwmask, pwf, pwf8, pwt, pgs, pigs = packs[w.data_ptr()]
+        assert pfmt == fmt and p8 == use8
+        for got, ref in ((palpha, alpha), (pwsign, wsign), (pwmask, wmask), (pwf, wf), (pwf8, wf8), (pwt, wt), (pgs, gs),
+                         (pigs, igs)):
+            assert (got is None) == (ref is None)
+            if ref is not None:
+                assert torch.equal(got, ref)
+    torch.manual_seed(0)
+    net = ResNetImageNet([1, 1, 1, 1], num_classes=10).cuda()
+    x = torch.randn(4, 3, 64, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BDBNN_PREPACK", flag)
+        net.zero_grad(set_to_none=True)
+        n0 = _lib.launch_count()
+        y = net(x)
+        y.square().mean().backward()
+        torch.cuda.synchronize()
+        outs[flag] = (y.detach().clone(), _lib.launch_count() - n0)
+    assert outs["1"][1] == outs["0"][1] - 2 * 8 + 2          # 8 binary convs: 2 launches instead of 2 each
+    torch.testing.assert_close(outs["1"][0], outs["0"][0], rtol=1e-3, atol=1e-4)
