@@ -154,14 +154,10 @@ bn_apply_add_pack_kernel(const void* __restrict__ y, const float4* __restrict__ 
   const int c4 = int(i % C4);                                     // constant per thread
   const float4 av = *reinterpret_cast<const float4*>(a + c4 * 4);
   const float4 bv = *reinterpret_cast<const float4*>(b + c4 * 4);
-  for (; i < n4; i += nthreads) {
-    const float4 v = load_y4<I16>(y, i);         // I16: `a` already carries alpha (a = gamma*invstd*alpha)
+  auto emit = [&](int64_t i, const float4 v, const float4 r) {
     float4 o = make_float4(fmaf(v.x, av.x, bv.x), fmaf(v.y, av.y, bv.y), fmaf(v.z, av.z, bv.z),
                            fmaf(v.w, av.w, bv.w));
-    if (res != nullptr) {
-      const float4 r = __ldg(res + i);
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-    }
+    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     z[i] = o;
     if (PACK) {
       const uint32_t s0 = o.x >= 0.0f, s1 = o.y >= 0.0f, s2 = o.z >= 0.0f, s3 = o.w >= 0.0f;
@@ -180,7 +176,18 @@ bn_apply_add_pack_kernel(const void* __restrict__ y, const float4* __restrict__ 
       if (xb8 != nullptr)   // e4m3 +-1 bytes for the fp8 forward of the next conv
         xb8[i] = 0x38383838u | ((s0 ? 0u : 0x80u) | (s1 ? 0u : 0x8000u) | (s2 ? 0u : 0x800000u) | (s3 ? 0u : 0x80000000u));
     }
+  };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // two elements per thread and iteration: all four loads are issued before the first dependent instruction
+  // (whole 8-lane pack groups take the same branch: n4 and nthreads are multiples of 8)
+  for (; i + nthreads < n4; i += 2 * nthreads) {
+    const float4 v0 = load_y4<I16>(y, i), v1 = load_y4<I16>(y, i + nthreads);   // I16: `a` already carries alpha
+    const float4 r0 = res != nullptr ? __ldg(res + i) : zero4;
+    const float4 r1 = res != nullptr ? __ldg(res + i + nthreads) : zero4;
+    emit(i, v0, r0);
+    emit(i + nthreads, v1, r1);
   }
+  if (i < n4) emit(i, load_y4<I16>(y, i), res != nullptr ? __ldg(res + i) : zero4);
 }
 
 // [C] math of the backward.  consts[c] = {m1, m2*invstd, mean, a*gscale}; gy*gscale = (gz - m1 -
@@ -240,9 +247,7 @@ bn_bwd_pack_kernel(const float4* __restrict__ gz, const void* __restrict__ y, co
   const int C = C4 * 4;
   int64_t pix = i / C4;
   const int64_t pix_step = nthreads / C4;
-  for (; i < n4; i += nthreads, pix += pix_step) {
-    const float4 g = __ldcs(gz + i);
-    const float4 v = load_y4<I16>(y, i);
+  auto emit = [&](int64_t pix, const float4 g, const float4 v) {
     const float a0 = (g.x - k0.x - (v.x - k0.z) * k0.y) * k0.w * up;
     const float a1 = (g.y - k1.x - (v.y - k1.z) * k1.y) * k1.w * up;
     const float a2 = (g.z - k2.x - (v.z - k2.z) * k2.y) * k2.w * up;
@@ -263,7 +268,15 @@ bn_bwd_pack_kernel(const float4* __restrict__ gz, const void* __restrict__ y, co
       l.y = bn_pack_bf16x2(a2 - bn_bf16_round(a2), a3 - bn_bf16_round(a3));
       *reinterpret_cast<uint2*>(dst + C) = l;
     }
+  };
+  // two elements per thread and iteration, loads first
+  for (; i + nthreads < n4; i += 2 * nthreads, pix += 2 * pix_step) {
+    const float4 g0 = __ldcs(gz + i), g1 = __ldcs(gz + i + nthreads);
+    const float4 v0 = load_y4<I16>(y, i), v1 = load_y4<I16>(y, i + nthreads);
+    emit(pix, g0, v0);
+    emit(pix + pix_step, g1, v1);
   }
+  if (i < n4) emit(pix, __ldcs(gz + i), load_y4<I16>(y, i));
 }
 
 static int bn_grid(int64_t work, int C4, int per_sm = 8) {

@@ -21,7 +21,7 @@ class GradAllReduce:
     NCCL transfer of the big late-layer buckets runs under the backward of the early layers.  `__call__`
     (after backward) issues whatever is left, waits, and applies 1/world."""
 
-    def __init__(self, model, process_group=None, broadcast_params=True, n_buckets=4, overlap=True, scale=True):
+    def __init__(self, model, process_group=None, broadcast_params=True, n_buckets=2, overlap=True, scale=True):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.params = [p for p in model.parameters() if p.requires_grad]

@@ -299,6 +299,16 @@ def eager_gpu_run(args, steps, warmup, batch, dev):
     return batch / (ms / 1e3), ms
 
 
+def finish(world):
+    """Leave without tearing NCCL down: with captured graphs holding collectives alive,
+    dist.destroy_process_group() / interpreter teardown can block forever (seen at N=2: the JSON line was printed and
+    the processes never exited).  Everything is flushed; a hard exit is the documented-safe way out of a benchmark."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -381,7 +391,10 @@ def main():
         fold = hasattr(opt, "grad_scale")       # FusedAdam / FusedSGD apply 1/world inside the update kernel
         if fold:
             opt.grad_scale = 1.0 / world
-        reducer = GradAllReduce(model, scale=not fold)
+        # BDBNN_DDP_BUCKETS=k: k reverse-order buckets all-reduced from post-accumulate hooks while the backward
+        # runs (overlap); 0: ONE all-reduce of the flat buffer after the backward
+        nb = int(os.environ.get("BDBNN_DDP_BUCKETS", "2"))
+        reducer = GradAllReduce(model, scale=not fold, n_buckets=max(1, nb), overlap=nb > 0)
         opt = FlatGradOptimizerShim(opt, reducer)
     step_eager = TrainStep(model, opt, cfg, teacher=teacher, grad_sync=reducer)
     use_graph = not args.no_graph and not args.profile_mode
@@ -549,9 +562,10 @@ def main():
             os.environ["BDBNN_GRAD_MODE"] = "fp16s"
             step2 = None
 
+    if world > 1:
+        barrier()                     # every rank has finished its timed regions before anyone leaves
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     # ---- same-box GPU comparator: stock eager PyTorch on the oracle modules (N=1 only) ----------------------
@@ -614,7 +628,8 @@ def main():
             "dtype": dtype_str,
             "data": "synthetic",
             "config": {"workload": workload, "global_batch": batch * world,
-                       "parallelism": f"dp{world}", "optimizer": "Adam (train.py:323-336)" if dataset == "imagenet"
+                       "parallelism": f"dp{world}", "ddp_buckets": os.environ.get("BDBNN_DDP_BUCKETS", "2") if world > 1 else None,
+                       "optimizer": "Adam (train.py:323-336)" if dataset == "imagenet"
                        else "SGD (train.py:319-321)", "conv_impl": args.conv_impl or "auto", "grad_mode": gname,
                        "launch": "CUDA graph replay (whole step captured once)" if use_graph else
                                  (graph_note or "eager (Python/ctypes per kernel)"),
@@ -622,8 +637,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "kernels": kernels, "cpu_baseline": cpu, "eager_gpu": eager, "secondary": secondary}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 if __name__ == "__main__":
