@@ -138,7 +138,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n_pi
 }
 
 // z = y*a + b (+ residual); optionally the sign / STE-mask bits and the +-1 16-bit copy of z.
-template <bool PACK, bool I16 = false>
+template <bool PACK, bool I16 = false, int U = 4>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_add_pack_kernel(const void* __restrict__ y, const float4* __restrict__ res,
                          const float* __restrict__ a, const float* __restrict__ b, int64_t n4, int C4,
@@ -158,7 +158,9 @@ bn_apply_add_pack_kernel(const void* __restrict__ y, const float4* __restrict__ 
     float4 o = make_float4(fmaf(v.x, av.x, bv.x), fmaf(v.y, av.y, bv.y), fmaf(v.z, av.z, bv.z),
                            fmaf(v.w, av.w, bv.w));
     o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-    z[i] = o;
+    // z (4 B/element, re-read only after the next conv has run) is stored evict-first so that the next conv's
+    // operands written below (xb / xb8, 1-2 B/element) have a chance to stay in the 126 MB L2
+    __stcs(z + i, o);
     if (PACK) {
       const uint32_t s0 = o.x >= 0.0f, s1 = o.y >= 0.0f, s2 = o.z >= 0.0f, s3 = o.w >= 0.0f;
       const uint32_t m0 = fabsf(o.x) <= 1.0f, m1 = fabsf(o.y) <= 1.0f, m2 = fabsf(o.z) <= 1.0f,
@@ -180,14 +182,16 @@ bn_apply_add_pack_kernel(const void* __restrict__ y, const float4* __restrict__ 
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   // two elements per thread and iteration: all four loads are issued before the first dependent instruction
   // (whole 8-lane pack groups take the same branch: n4 and nthreads are multiples of 8)
-  for (; i + nthreads < n4; i += 2 * nthreads) {
-    const float4 v0 = load_y4<I16>(y, i), v1 = load_y4<I16>(y, i + nthreads);   // I16: `a` already carries alpha
-    const float4 r0 = res != nullptr ? __ldg(res + i) : zero4;
-    const float4 r1 = res != nullptr ? __ldg(res + i + nthreads) : zero4;
-    emit(i, v0, r0);
-    emit(i + nthreads, v1, r1);
+  for (; i + (U - 1) * nthreads < n4; i += U * nthreads) {
+    float4 v[U], r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = load_y4<I16>(y, i + u * nthreads);       // I16: `a` already carries alpha
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = res != nullptr ? __ldcs(res + i + u * nthreads) : zero4;
+#pragma unroll
+    for (int u = 0; u < U; ++u) emit(i + u * nthreads, v[u], r[u]);
   }
-  if (i < n4) emit(i, load_y4<I16>(y, i), res != nullptr ? __ldg(res + i) : zero4);
+  for (; i < n4; i += nthreads) emit(i, load_y4<I16>(y, i), res != nullptr ? __ldcs(res + i) : zero4);
 }
 
 // [C] math of the backward.  consts[c] = {m1, m2*invstd, mean, a*gscale}; gy*gscale = (gz - m1 -
@@ -234,7 +238,7 @@ __global__ void bn_bwd_bound_kernel(const double* __restrict__ sums, const uint3
 }
 
 // gys = 16-bit operand of the conv backward, straight from gz and y.
-template <int MODE, bool I16 = false>
+template <int MODE, bool I16 = false, int U = 4>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_pack_kernel(const float4* __restrict__ gz, const void* __restrict__ y, const float4* __restrict__ consts,
                    const uint32_t* __restrict__ amax_bits, int64_t n4, int C4, uint16_t* __restrict__ out) {
@@ -269,14 +273,17 @@ bn_bwd_pack_kernel(const float4* __restrict__ gz, const void* __restrict__ y, co
       *reinterpret_cast<uint2*>(dst + C) = l;
     }
   };
-  // two elements per thread and iteration, loads first
-  for (; i + nthreads < n4; i += 2 * nthreads, pix += 2 * pix_step) {
-    const float4 g0 = __ldcs(gz + i), g1 = __ldcs(gz + i + nthreads);
-    const float4 v0 = load_y4<I16>(y, i), v1 = load_y4<I16>(y, i + nthreads);
-    emit(pix, g0, v0);
-    emit(pix + pix_step, g1, v1);
+  // U elements per thread and iteration, loads first
+  for (; i + (U - 1) * nthreads < n4; i += U * nthreads, pix += U * pix_step) {
+    float4 g[U], v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) g[u] = __ldcs(gz + i + u * nthreads);
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = load_y4<I16>(y, i + u * nthreads);
+#pragma unroll
+    for (int u = 0; u < U; ++u) emit(pix + u * pix_step, g[u], v[u]);
   }
-  if (i < n4) emit(pix, __ldcs(gz + i), load_y4<I16>(y, i));
+  for (; i < n4; i += nthreads, pix += pix_step) emit(pix, __ldcs(gz + i), load_y4<I16>(y, i));
 }
 
 static int bn_grid(int64_t work, int C4, int per_sm = 8) {
@@ -345,7 +352,12 @@ static int bn_fwd_impl(const void* y, const float* alpha_i16, const float* resid
     const uint32_t one16 = fmt == BDBNN_FMT_FP16 ? 0x3C00u : 0x3F80u;
     uint2* xb2 = reinterpret_cast<uint2*>(xb);
     uint32_t* xb8 = reinterpret_cast<uint32_t*>(xb_fp8);
-    if (i16)
+    // four float4 per thread and iteration (measured: bn_fwd 1.13 -> 1.04 ms per ResNet-18 step vs two); BDBNN_BN_UNROLL=2
+    static const int unroll2 = [] { const char* e = getenv("BDBNN_BN_UNROLL"); return e ? atoi(e) == 2 : 0; }();
+    if (i16 && unroll2)
+      bn_apply_add_pack_kernel<true, true, 2><<<grid, kBnThreads, 0, st>>>(y, r4, a, b, n4, C4, z4, sign_bits, mask_bits,
+                                                                            xb2, xb8, one16);
+    else if (i16)
       bn_apply_add_pack_kernel<true, true><<<grid, kBnThreads, 0, st>>>(y, r4, a, b, n4, C4, z4, sign_bits, mask_bits,
                                                                          xb2, xb8, one16);
     else

@@ -19,6 +19,11 @@ timeout 1500 ncu --set full --clock-control none --profile-from-start off \
    -k regex:"tc_conv2_kernel|tc_wgrad_kernel|bn_reduce_kernel|bn_apply_add_pack_kernel|bn_bwd_pack_kernel|weight_pack_multi|weight_wt_multi|bn_pool" -c 160 \
    -o /tmp/${TAG}_prof -f python bench.py --steps 1 --profile-mode > gpurun_out/${TAG}_ncu_full.log 2>&1
 ncu -i /tmp/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
+# source-level capture of ONE layer1 forward launch (the N = 64 MMA pipeline question)
+timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"tc_conv2_kernel" \
+   --launch-skip 1 --launch-count 1 -o /tmp/${TAG}_l1fwd -f python bench.py --steps 1 --profile-mode > gpurun_out/${TAG}_ncu_l1fwd.log 2>&1
+ncu -i /tmp/${TAG}_l1fwd.ncu-rep --page source --csv > gpurun_out/${TAG}_l1fwd_source.csv 2>/dev/null
+ncu -i /tmp/${TAG}_l1fwd.ncu-rep --page raw --csv > gpurun_out/${TAG}_l1fwd_raw.csv 2>/dev/null
 # loss kernels (config 3)
 timeout 600 ncu --set full --clock-control none --profile-from-start off -k regex:"kurt|kd_" -c 40 -o /tmp/${TAG}_loss -f \
    python bench.py --workload kurt_kd --steps 1 --profile-mode > gpurun_out/${TAG}_ncu_loss.log 2>&1

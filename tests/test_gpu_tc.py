@@ -347,9 +347,10 @@ def test_stem_fused_conv_bn_pool(geom):
 
     zf, gwf, ggf, gbf, rmf, rvf, gz = run(True)
     zu, gwu, ggu, gbu, rmu, rvu, _ = run(False)
-    # same kernels; the BN statistics are summed with fp64 atomics, so the last bits may differ run to run
+    # same kernels; the BN statistics are summed with atomics (fp32 per CTA, then fp64), so the last bits of mean /
+    # invstd differ run to run and dgamma / dbeta (sums over 1e5 terms) move by a few 1e-5 relative
     for a, b in ((zf, zu), (rmf, rmu), (rvf, rvu), (ggf, ggu), (gbf, gbu)):
-        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
     assert (gwf - gwu).abs().max().item() <= 2e-3 * gwu.abs().max().item()
     assert hasattr(zf, "shape") and zf.shape == (n, 64, ((h - 1) // 2) // 2 + 1, ((w - 1) // 2) // 2 + 1)
     # fp64 torch BN + max-pool + conv weight gradient, evaluated on the GPU conv's own output y (pooling

@@ -119,7 +119,7 @@ def test_cpu_oracle_step_runs_and_learns():
     assert all(p.grad is not None for p in m.parameters())          # DDP needs every param to get a grad
 
 
-def _ddp_worker(rank, world, port, outdir):
+def _ddp_worker(rank, world, port, outdir, use_shim=True):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -129,31 +129,53 @@ def _ddp_worker(rank, world, port, outdir):
     torch.manual_seed(100 + rank)                     # different init per rank: broadcast must fix it
     m = resnet20_ref()
     red = GradAllReduce(m)
-    opt = FlatGradOptimizerShim(make_optimizer(m, "cifar10", lr=0.1), red)
-    step = TrainStep(m, opt, StepConfig(w_kurtosis=True), ops=RefOps, grad_sync=red)
     g = torch.Generator().manual_seed(5)
     x = torch.randn(8, 3, 32, 32, generator=g)
     y = torch.randint(0, 10, (8,), generator=g)
     xs, ys = x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4]
-    step(xs, ys)
+    if use_shim:
+        opt = FlatGradOptimizerShim(make_optimizer(m, "cifar10", lr=0.1), red)
+        step = TrainStep(m, opt, StepConfig(w_kurtosis=True), ops=RefOps, grad_sync=red)
+        for _ in range(2):
+            step(xs, ys)
+    else:
+        # a caller that wraps nothing: torch's own zero_grad() (set_to_none=True drops the flat-buffer views), plain
+        # backward, the reducer, the optimizer — must give the same result (no silent stale all-reduce)
+        opt = make_optimizer(m, "cifar10", lr=0.1)
+        step = TrainStep(m, opt, StepConfig(w_kurtosis=True), ops=RefOps)      # no grad_sync: drives nothing itself
+        hooked = list(step.hooked.values())
+        for _ in range(2):
+            opt.zero_grad()
+            loss = torch.nn.functional.cross_entropy(m(xs), ys) + RefOps.kurtosis(hooked, [1.8] * len(hooked), "avg",
+                                                                                 len(hooked), 1.0)
+            loss.backward()
+            red()
+            opt.step()
     torch.save((red.flat.clone(), torch.cat([p.detach().reshape(-1) for p in m.parameters()])),
-               os.path.join(outdir, f"r{rank}.pt"))
+               os.path.join(outdir, f"r{rank}_{int(use_shim)}.pt"))
     dist.destroy_process_group()
 
 
 def test_gloo_world2_gradient_allreduce(tmp_path):
+    """Two gloo ranks, two steps: averaged gradients and updated parameters are bit-identical across ranks, with the
+    flat-buffer shim AND for a caller that uses torch's own optimizer.zero_grad() (views dropped, re-bound by the
+    reducer) — and both ways give the same parameters."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(300)
-        assert p.exitcode == 0
-    (g0, p0), (g1, p1) = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2)]
-    assert torch.equal(g0, g1) and torch.equal(p0, p1)     # averaged grads and updated params identical
-    assert g0.abs().sum() > 0
+    res = {}
+    for use_shim in (True, False):
+        port = 29500 + os.getpid() % 2000 + int(use_shim)
+        procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, str(tmp_path), use_shim)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+            assert p.exitcode == 0
+        (g0, p0), (g1, p1) = [torch.load(os.path.join(tmp_path, f"r{r}_{int(use_shim)}.pt")) for r in range(2)]
+        assert torch.equal(g0, g1) and torch.equal(p0, p1)     # averaged grads and updated params identical
+        assert g0.abs().sum() > 0
+        res[use_shim] = p0
+    torch.testing.assert_close(res[True], res[False], rtol=1e-6, atol=1e-7)
 
 
 def test_ede_attributes_and_activation_rule():
