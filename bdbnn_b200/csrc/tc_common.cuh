@@ -459,6 +459,10 @@ int launch_stem_wgrad(const uint16_t* gys, const uint16_t* xw, float* ws, size_t
 // Persistent multi-accumulator kernel (tc_conv2.cu). Returns BDBNN_ERR_UNSUPPORTED if the geometry
 // does not qualify (caller falls back to the one-tile-per-CTA kernel in tc_conv.cu).
 int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st);
+// Pixel-N kernel for the 64-channel layers (tc_conv64.cu): forward and stride-1 dgrad with Kc = Nout = 64 on images
+// of more than 256 pixels; BDBNN_ERR_UNSUPPORTED otherwise (callers then use launch_tc_conv2).
+int launch_tc_conv64(const TcConvLaunch& L, int mode, cudaStream_t st);
+bool tc_conv64_eligible(const TcConvLaunch& L);
 void set_tc_trace(long long* buf);
 void set_conv_plan_sink(int32_t* sink);   // host-only planning probe, see tc_conv2.cu
 long long* get_tc_trace();

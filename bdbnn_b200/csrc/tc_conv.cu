@@ -247,6 +247,8 @@ static int launch_tc_conv(const TcConvLaunch& L, cudaStream_t st) {
   // Persistent multi-accumulator kernel first (tc_conv2.cu); BDBNN_TC_V2=0 forces the simple kernel.
   static const int v2_env = [] { const char* e = getenv("BDBNN_TC_V2"); return e ? atoi(e) : 1; }();
   if (v2_env) {
+    const int rc64 = launch_tc_conv64(L, MODE, st);        // 64-channel layers: pixels as the N = 256 dimension
+    if (rc64 != BDBNN_ERR_UNSUPPORTED) return rc64;
     const int rc2 = launch_tc_conv2(L, MODE, st);
     if (rc2 != BDBNN_ERR_UNSUPPORTED) return rc2;
   }
@@ -464,7 +466,8 @@ extern "C" int bdbnn_binconv_fwd_tc_i16(const void* xb, const void* wf, int32_t 
   L.bn_sums = bn_sums; L.bn_ymax = bn_ymax;
   rc = bn_stats_zero(bn_sums, bn_ymax, s->Cout, cudaStream_t(stream));
   if (rc) return rc;
-  rc = launch_tc_conv2(L, 0, cudaStream_t(stream));
+  rc = launch_tc_conv64(L, 0, cudaStream_t(stream));
+  if (rc == BDBNN_ERR_UNSUPPORTED) rc = launch_tc_conv2(L, 0, cudaStream_t(stream));
   if (rc == BDBNN_ERR_UNSUPPORTED) set_error("binconv_fwd_tc_i16: geometry not supported by the persistent kernel");
   return rc;
 }
@@ -594,9 +597,16 @@ static int dgrad_tc_impl(const uint16_t* gys_bf16, int32_t grad_mode, const uint
   if (stats) {
     // one phase (stride 1), persistent kernel only: its epilogue owns the statistics
     if (n_launch != 1 || empty_phase) { set_error("binconv_dgrad_tc_stats: needs stride 1"); return BDBNN_ERR_UNSUPPORTED; }
+    static const int c64_env = [] { const char* e = getenv("BDBNN_TC_C64"); return e ? atoi(e) : 1; }();
+    if (c64_env < 2 && tc_conv64_eligible(Ls[0])) {
+      // 64-channel layers: the plain pixel-N dgrad + the separate reduction pass is faster (see tc_conv64.cu)
+      set_error("binconv_dgrad_tc_stats: declined for this shape (pixel-N kernel without statistics is faster)");
+      return BDBNN_ERR_UNSUPPORTED;
+    }
     rc = bn_stats_zero(stats->sums, stats->gmax, s->Cin, st);
     if (rc) return rc;
-    rc = launch_tc_conv2(Ls[0], 1, st);
+    rc = launch_tc_conv64(Ls[0], 1, st);
+    if (rc == BDBNN_ERR_UNSUPPORTED) rc = launch_tc_conv2(Ls[0], 1, st);
     if (rc == BDBNN_ERR_UNSUPPORTED) set_error("binconv_dgrad_tc_stats: geometry not supported by the persistent kernel");
     return rc;
   }
