@@ -463,6 +463,7 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st);
 // of more than 256 pixels; BDBNN_ERR_UNSUPPORTED otherwise (callers then use launch_tc_conv2).
 int launch_tc_conv64(const TcConvLaunch& L, int mode, cudaStream_t st);
 bool tc_conv64_eligible(const TcConvLaunch& L);
+int launch_tc_conv64_stem(const TcConvLaunch& L, cudaStream_t st);
 void set_tc_trace(long long* buf);
 void set_conv_plan_sink(int32_t* sink);   // host-only planning probe, see tc_conv2.cu
 long long* get_tc_trace();

@@ -356,6 +356,8 @@ int launch_stem_fwd(const uint16_t* xw, const uint16_t* wf, const float* alpha, 
   L.bn_sums = bn_sums; L.bn_ymax = bn_ymax;
   int rc = bn_stats_zero(bn_sums, bn_ymax, kStemCout, st);
   if (rc) return rc;
+  rc = launch_tc_conv64_stem(L, st);            // pixel-N kernel (tc_conv64.cu); falls back to the pixel-M kernels
+  if (rc != BDBNN_ERR_UNSUPPORTED) return rc;
   return launch_tc_conv<0>(L, st);
 }
 

@@ -29,7 +29,7 @@ namespace bdbnn {
 constexpr int kC64Threads = 448;    // 14 warps: see the role list above
 constexpr int kC64N = 256;          // pixels (MMA N) per unit
 constexpr int kC64MaxTaps = 9;
-constexpr uint32_t kC64TapBytes = 64u * 128u;   // one tap's weights: 64 rows x 128 B
+constexpr uint32_t kC64TapBytes = 64u * 128u;   // one tap's weights: 64 rows x 128 B (64-byte rows in the stem variant)
 
 struct TcConv64Params {
   int32_t OW, OH, NIMG;
@@ -38,6 +38,11 @@ struct TcConv64Params {
   int32_t n_taps;
   int8_t tap_dh[kC64MaxTaps], tap_dw[kC64MaxTaps];
   uint8_t tap_b[kC64MaxTaps];
+  // STEM variant (7x7/2 stem conv over the packed window image, stem.cu): K = 32 halves per tap (64-byte rows), the
+  // unit is UH = 2 output rows x 128 windows, and the patch has two row-parity planes (even / odd window rows) so that
+  // tap r is plane r&1 viewed from row (r>>1)*PW
+  int32_t plane_rows;        // window rows per plane box
+  uint32_t plane_bytes;      // smem bytes of one plane
   int32_t a_halves;          // K blocks of the activation operand (2 = bf16 hi|lo gradient)
   int32_t fmt;
   int32_t dbg;               // BDBNN_TC_DBG experiment bits: 1 = no global stores / loads in the epilogue, 2 = no TMEM loads, 4 = no MMAs
@@ -75,10 +80,13 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       : "memory");
 }
 
-template <int MODE, bool BST, bool I16>
+template <int MODE, bool BST, bool I16, bool STEM = false>
 __global__ void __launch_bounds__(kC64Threads, 1)
 tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const TcConv64Params p) {
+  constexpr uint32_t RB = STEM ? 64u : 128u;          // bytes per operand row of one K block
+  constexpr uint32_t kTapBytes = 64u * RB;            // one tap's weights: 64 rows
+  constexpr int kKSteps = int(RB / 32u);              // K = 16 MMAs per tap and K block
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_bar;
   __shared__ __align__(8) uint64_t pfull_bar[2], pempty_bar[2];
@@ -89,10 +97,16 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base;                                              // (n_taps + 1) tap tiles
-  const uint32_t patch_base = smem_base + uint32_t(p.n_taps + 1) * kC64TapBytes;  // two patch buffers
-  if (threadIdx.x < p.n_taps)
-    tap_shift_rows[threadIdx.x] = uint32_t((p.tap_dh[threadIdx.x] - p.dh_min) * p.PW +
-                                           (p.tap_dw[threadIdx.x] - p.dw_min));
+  const uint32_t patch_base = smem_base + ((uint32_t(p.n_taps + 1) * kTapBytes + 1023u) & ~1023u);  // two patch buffers
+  if (threadIdx.x < p.n_taps) {
+    // offset of tap t's view inside a patch buffer, in 16-byte descriptor units
+    if (STEM)      // tap r = window row 2*oh + r: plane r & 1, row shift (r >> 1) * PW
+      tap_shift_rows[threadIdx.x] = (uint32_t(threadIdx.x & 1) * p.plane_bytes +
+                                     uint32_t(threadIdx.x >> 1) * uint32_t(p.PW) * RB) >> 4;
+    else
+      tap_shift_rows[threadIdx.x] = uint32_t((p.tap_dh[threadIdx.x] - p.dh_min) * p.PW +
+                                             (p.tap_dw[threadIdx.x] - p.dw_min)) * (RB >> 4);
+  }
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&w_bar), 1);
     for (int s = 0; s < 2; ++s) {
@@ -105,8 +119,8 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
   // the tile behind the last tap is read by that tap's M = 128 descriptor (rows 64..127, results ignored): keep it finite
   {
-    uint8_t* tail = smem_raw + (w_base - smem_u32(smem_raw)) + size_t(p.n_taps) * kC64TapBytes;
-    for (int i = threadIdx.x; i < int(kC64TapBytes / 16); i += blockDim.x)
+    uint8_t* tail = smem_raw + (w_base - smem_u32(smem_raw)) + size_t(p.n_taps) * kTapBytes;
+    for (int i = threadIdx.x; i < int(kTapBytes / 16); i += blockDim.x)
       reinterpret_cast<uint4*>(tail)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
   }
@@ -126,11 +140,11 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (lane == 0) {
       // all tap weights, once
       const uint32_t wb = smem_u32(&w_bar);
-      mbar_expect_tx(wb, uint32_t(p.n_taps) * kC64TapBytes);
+      mbar_expect_tx(wb, uint32_t(p.n_taps) * kTapBytes);
       for (int t = 0; t < p.n_taps; ++t)
-        tma_load_2d(w_base + uint32_t(t) * kC64TapBytes, &tmW, wb, int(p.tap_b[t]) * 64, 0);
+        tma_load_2d(w_base + uint32_t(t) * kTapBytes, &tmW, wb, int(p.tap_b[t]) * int(RB / 2u), 0);
       uint32_t pcount = 0;
-      const uint32_t patch_tx = uint32_t(p.PW * p.PH) * 128u;
+      const uint32_t patch_tx = STEM ? 2u * uint32_t(p.PW * p.plane_rows) * RB : uint32_t(p.PW * p.PH) * RB;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const int n0 = u / p.units_per_img, h0 = (u - n0 * p.units_per_img) * p.SH;
         for (int kb = 0; kb < kb_total; ++kb, ++pcount) {
@@ -138,14 +152,20 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(smem_u32(&pempty_bar[pa]), ((pcount >> 1) & 1u) ^ 1u);
           const uint32_t pb = smem_u32(&pfull_bar[pa]);
           mbar_expect_tx(pb, patch_tx);
-          tma_load_4d(patch_base + pa * p.patch_bytes, &tmX, pb, kb * 64, p.dw_min, h0 + p.dh_min, n0);
+          const uint32_t dst = patch_base + pa * p.patch_bytes;
+          if (STEM) {     // even and odd window rows of the unit (the map steps two rows per box row)
+            tma_load_4d(dst, &tmX, pb, 0, 0, 2 * h0, n0);
+            tma_load_4d(dst + p.plane_bytes, &tmX, pb, 0, 0, 2 * h0 + 1, n0);
+          } else {
+            tma_load_4d(dst, &tmX, pb, kb * 64, p.dw_min, h0 + p.dh_min, n0);
+          }
         }
       }
     }
   } else if (warp == 3) {
     // ================================ MMA issuer (converged warp) ================================
     const uint32_t idesc = make_idesc_bf16(128u, uint32_t(kC64N), uint32_t(p.fmt));
-    const uint32_t desc_hi = kmajor_hi(128u);
+    const uint32_t desc_hi = kmajor_hi(RB);
     mbar_wait(smem_u32(&w_bar), 0);
     tc_fence_after();
     uint32_t pcount = 0, ucount = 0;
@@ -161,11 +181,11 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tc_fence_after();
         const uint32_t patch_lo = kmajor_lo(patch_base + pa * p.patch_bytes);
         for (int t = 0; t < p.n_taps; ++t) {
-          const uint32_t a_lo = kmajor_lo(w_base + uint32_t(t) * kC64TapBytes);
-          const uint32_t b_lo = patch_lo + tap_shift_rows[t] * 8u;       // 128-byte rows: 8 descriptor units per row
+          const uint32_t a_lo = kmajor_lo(w_base + uint32_t(t) * kTapBytes);
+          const uint32_t b_lo = patch_lo + tap_shift_rows[t];
           if (!(p.dbg & 4)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < kKSteps; ++k) {
               umma_f16_elect(acc, a_lo + 2u * k, desc_hi, b_lo + 2u * k, desc_hi, idesc, first);
               first = 1u;
             }
@@ -241,7 +261,11 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int j = 0; j < 32; ++j) {
           const bool ok = j < nv;                                  // warp-uniform
           float o = __uint_as_float(v[j]);
-          if (MODE == 0) {
+          if (MODE == 0 && STEM) {        // real-valued result: fp32 statistics per unit, fp64 across units
+            const float yv_ = ok ? o * alpha : 0.f;
+            if (ok) p.out[off + j * 64] = yv_;
+            u_sum += yv_; u_sq = fmaf(yv_, yv_, u_sq); f_max = fmaxf(f_max, fabsf(yv_));
+          } else if (MODE == 0) {
             const int yi = ok ? int(o) : 0;
             if (ok) {
               if (I16) p.out_i16[off + j * 64] = int16_t(yi);
@@ -263,14 +287,20 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
       }
-      if (MODE == 0) { i_sum += u_isum; i_sq += u_isq; }
-      if (BST) { d_sum += double(u_sum); d_sq += double(u_sq); }
+      if (MODE == 0 && !STEM) { i_sum += u_isum; i_sq += u_isq; }
+      if (BST || STEM) { d_sum += double(u_sum); d_sq += double(u_sq); }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
     }
     if (do_stats) {
-      if (MODE == 0) {
+      if (MODE == 0 && STEM) {
+        if (f_max != 0.f) {
+          atomicAdd(p.bn_sums + ch, d_sum);
+          atomicAdd(p.bn_sums + 64 + ch, d_sq);
+          atomicMax(p.bn_ymax + ch, __float_as_uint(f_max));
+        }
+      } else if (MODE == 0) {
         if (i_max != 0) {
           const double al = double(alpha);
           atomicAdd(p.bn_sums + ch, al * double(i_sum));
@@ -355,7 +385,7 @@ int launch_tc_conv64(const TcConvLaunch& L, int mode, cudaStream_t st) {
   // the plain form (0.13 ms) plus the separate reduction pass (0.06 ms): bdbnn_binconv_dgrad_tc_stats declines
   // these shapes (the caller then runs the plain dgrad here + bn_reduce) unless BDBNN_TC_C64=2.
   if (bst && enabled < 2) return BDBNN_ERR_UNSUPPORTED;
-  const size_t smem = size_t(L.n_taps + 1) * kC64TapBytes + 2 * size_t(p.patch_bytes) + 1024;
+  const size_t smem = ((size_t(L.n_taps + 1) * kC64TapBytes + 1023) & ~size_t(1023)) + 2 * size_t(p.patch_bytes) + 1024;
   if (smem > 226u * 1024u) return BDBNN_ERR_UNSUPPORTED;
   CUtensorMap tmX, tmW;
   int rc = make_act_map(&tmX, L.A, L.NIMG, L.IH, L.IW, L.Kc * L.a_halves, 64, p.PW, p.PH, 1, 1, 2);
@@ -371,6 +401,49 @@ int launch_tc_conv64(const TcConvLaunch& L, int mode, cudaStream_t st) {
   };
   if (mode == 0) return p.out_i16 ? launch(tc_conv64_kernel<0, false, true>) : launch(tc_conv64_kernel<0, false, false>);
   return bst ? launch(tc_conv64_kernel<1, true, false>) : launch(tc_conv64_kernel<1, false, false>);
+}
+
+// Stem conv forward (7 vertical taps of K = 32 over the packed window image) on the pixel-N kernel.
+// L is the launch launch_stem_fwd builds (win = 1, Kc = 32, in_step = 2, Nout = 64).
+int launch_tc_conv64_stem(const TcConvLaunch& L, cudaStream_t st) {
+  static const int enabled = [] { const char* e = getenv("BDBNN_TC_C64_STEM"); return e ? atoi(e) : 1; }();
+  if (!enabled || !c64_enabled() || !L.win || L.Kc != 32 || L.Nout != 64 || L.in_step != 2 || L.n_taps != 7 ||
+      L.fmt < 0 || L.a_halves != 1)
+    return BDBNN_ERR_UNSUPPORTED;
+  for (int r = 0; r < 7; ++r)
+    if (L.dh[r] != r || L.dw[r] != 0 || L.tb[r] != r) return BDBNN_ERR_UNSUPPORTED;
+  if (L.OW > 128 || L.OW <= 32 || L.OH < 2) return BDBNN_ERR_UNSUPPORTED;
+  if (int64_t(L.NIMG) * L.OH * L.OW * 64 >= (int64_t(1) << 31)) return BDBNN_ERR_UNSUPPORTED;
+  TcConv64Params p;
+  memset(&p, 0, sizeof(p));
+  p.OW = L.OW; p.OH = L.OH; p.NIMG = L.NIMG;
+  p.PW = 128;                                   // windows per unit row (zero-filled beyond OW)
+  p.SH = kC64N / p.PW;                          // 2 output rows per unit
+  p.plane_rows = p.SH + 3;                      // window rows oh0+k, k = 0 .. SH-1+3, of one parity
+  p.plane_bytes = uint32_t(p.plane_rows * p.PW) * 64u;          // 40 KB: also covers every 256-row view (k <= 3)
+  p.patch_bytes = 2u * p.plane_bytes;
+  p.units_per_img = (L.OH + p.SH - 1) / p.SH;
+  p.n_units = L.NIMG * p.units_per_img;
+  p.n_taps = 7; p.a_halves = 1; p.fmt = L.fmt;
+  for (int r = 0; r < 7; ++r) p.tap_b[r] = uint8_t(r);
+  p.alpha = L.alpha; p.out = L.out; p.bn_sums = L.bn_sums; p.bn_ymax = L.bn_ymax;
+  static const int dbg_env = [] { const char* e = getenv("BDBNN_TC_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg_env;
+  const size_t smem = ((size_t(7 + 1) * 64 * 64 + 1023) & ~size_t(1023)) + 2 * size_t(p.patch_bytes) + 1024;
+  if (smem > 226u * 1024u) return BDBNN_ERR_UNSUPPORTED;
+  CUtensorMap tmX, tmW;
+  // window image: box = [1 image][plane_rows rows, every 2nd window row][128 windows][32 halves]
+  int rc = make_window_map(&tmX, L.A, L.NIMG, L.IH, L.IW, 32, L.win_stride, L.win_row_stride, L.win_img_stride, p.PW,
+                           p.plane_rows, 1, 2);
+  if (rc) return rc;
+  rc = make_weight_map(&tmW, L.B, L.Nout, L.b_taps * L.Kc, 32, 64, 2);
+  if (rc) return rc;
+  int grid = num_sms();
+  if (grid > p.n_units) grid = p.n_units;
+  auto kern = tc_conv64_kernel<0, false, false, true>;
+  BDBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<grid, kC64Threads, smem, st>>>(tmX, tmW, p);
+  return check_launch("tc_conv64_kernel(stem)");
 }
 
 }  // namespace bdbnn

@@ -368,6 +368,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner (and NCCL_DEBUG output) on stdout: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True            # train.py:368
     torch.manual_seed(0)
@@ -531,9 +533,10 @@ def main():
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         e2e = {"value": round(batch * world * args.steps / (ms_e2e / 1e3), 2), "unit": "images/sec",
                "ms_per_step": round(ms_e2e / args.steps, 3),
-               "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
-               "d2h_bytes_per_step": 4,
-               "note": "pinned fp32 batch, H2D double-buffered on a copy stream, loss read back every step"}
+               "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8) * world,
+               "d2h_bytes_per_step": 4 * world,
+               "note": "whole job (all ranks): pinned fp32 batch, H2D double-buffered on a copy stream, "
+                       "loss read back every step"}
 
     # ---- secondary value: the fp32-class gradient operand mode (bf16 hi+lo pair, two MMAs per K step) -------
     from bdbnn_b200.functional import grad_mode

@@ -1,14 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-run() { # name, bench args..., env via VAR=..
+NG=$(nvidia-smi -L | wc -l); echo "gpus: $NG"
+run() { # name, bench args...
   name=$1; shift
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $((29520 + RANDOM % 200)) bench.py --gpus 8 "$@" > gpurun_out/n8_$name.json 2> gpurun_out/n8_$name.err
+  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((29520 + RANDOM % 200)) bench.py --gpus $NG "$@" > gpurun_out/n${NG}_$name.json 2> gpurun_out/n${NG}_$name.err
   echo "$name rc=$?"; python -c "
 import json,sys
-t=[l for l in open('gpurun_out/n8_$name.json') if l.startswith('{')]
+t=[l for l in open('gpurun_out/n${NG}_$name.json') if l.startswith('{')]
 d=json.loads(t[-1]); print('$name', d['value'], d['ms_per_step'], (d.get('e2e') or {}).get('value'), d['config']['launch'][:40])"
 }
-BDBNN_DDP_BUCKETS=2 run overlap2 --steps 20 --warmup 5 --no-secondary
+run overlap2 --steps 20 --warmup 5 --no-secondary
 BDBNN_DDP_BUCKETS=0 run single --steps 10 --warmup 3 --no-secondary --no-e2e
-BDBNN_DDP_BUCKETS=2 run r34_b512 --model resnet34 --batch 512 --steps 10 --warmup 3 --no-secondary
+run r34_b512 --model resnet34 --batch 512 --steps 10 --warmup 3 --no-secondary

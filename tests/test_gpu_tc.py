@@ -272,7 +272,7 @@ def test_stem_bn_pool_fused_vs_torch(geom):
 
 
 @pytest.mark.parametrize("geom,layout", [((2, 32, 32), "nchw"), ((3, 33, 47), "nhwc"), ((5, 16, 16), "nchw"),
-                                         ((2, 224, 224), "nhwc"), ((1, 64, 255), "nchw")])
+                                         ((2, 224, 224), "nhwc"), ((1, 64, 255), "nchw"), ((3, 150, 130), "nhwc")])
 def test_stem_conv_tc_vs_fp64_conv(geom, layout):
     """7x7/2 stem conv on tcgen05 (fp16 operands with power-of-two scales = TF32-class significands, fp32
     accumulate) vs an fp64 convolution: forward and weight gradient within 2e-3 of max|ref|
