@@ -405,6 +405,15 @@ static WgradPlan plan_wgrad(const bdbnn_conv_shape* s, int halves) {
   p.kboxes_per_cta = (p.n_kboxes + ks - 1) / ks;
   pl.ksplit = (p.n_kboxes + p.kboxes_per_cta - 1) / p.kboxes_per_cta;
   const size_t stage_bytes = size_t(p.n_a_boxes) * p.a_box_bytes + size_t(p.BN / 64 * halves) * p.b_box_bytes;
+  // Box-mode stages are small (32-64 K rows) and the loop is bound by the TMA round trip, not by bytes: use every
+  // stage the shared memory holds (BDBNN_WG_STAGES=2 restores the two-stage ring for A/B runs).
+  static const int stages_env = [] { const char* e = getenv("BDBNN_WG_STAGES"); return e ? atoi(e) : 0; }();
+  int stages = stages_env > 0 ? stages_env : int(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > p.kboxes_per_cta) stages = p.kboxes_per_cta;
+  if (stages < 2) stages = 2;
+  if (size_t(stages) * stage_bytes > budget) stages = 2;
+  p.stages = stages;
   pl.smem = size_t(p.stages) * stage_bytes + 1024;
   pl.ok = pl.smem <= 227u * 1024u;
   return pl;

@@ -19,7 +19,16 @@ class GradAllReduce:
     into `n_buckets` contiguous buckets.  A post-accumulate hook on every parameter counts its bucket
     down; the bucket's `all_reduce(SUM, async)` is issued the moment its last gradient is written, so the
     NCCL transfer of the big late-layer buckets runs under the backward of the early layers.  `__call__`
-    (after backward) issues whatever is left, waits, and applies 1/world."""
+    (after backward) issues whatever is left, waits, and applies 1/world.
+
+    A bucket is issued one event AFTER its last gradient was accounted for (the next hook / side-stream launch, or
+    `__call__`): autograd runs a node's AccumulateGrad hooks right after the node, so by then every accumulation
+    into the bucket is enqueued.  That matters for the side-stream weight gradients (functional.wgrad_side): there
+    a conv weight's gradient is written by a GEMM on the second stream into `wflat` (a second flat buffer of the
+    same layout) and the parameter is accounted for when that GEMM is launched; a kurtosis term's AccumulateGrad
+    on the same weight follows immediately on the main stream.  The bucket is then issued FROM the side stream
+    after it has waited for the main stream: flat[bucket] += wflat[bucket], all_reduce(flat[bucket]).  A gradient
+    that arrives after its bucket was issued raises."""
 
     def __init__(self, model, process_group=None, broadcast_params=True, n_buckets=2, overlap=True, scale=True):
         self.group = process_group
@@ -52,6 +61,13 @@ class GradAllReduce:
             self.buckets.append([b_start, off, b_count])
         self._pending = [b[2] for b in self.buckets]
         self._works = [None] * len(self.buckets)
+        self._done = set()                     # id(p) accounted for in this step
+        self._armed = []                       # complete buckets, issued at the next event
+        self.wflat = None                      # side-stream weight gradients (same layout as flat)
+        self._wview = {}
+        self._side_stream = None
+        self._side_now = set()                 # id(p) whose wgrad ran on the side stream in this step
+        self._side_ever = {}                   # id(p) -> p: wflat entries that hold (possibly stale) values
         if self.overlap:
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._hook)
@@ -62,7 +78,57 @@ class GradAllReduce:
 
     def _launch(self, b):
         a, e, _ = self.buckets[b]
+        if self._side_now or self._side_ever:
+            side = self._side_stream
+            side.wait_stream(torch.cuda.current_stream())     # every accumulation enqueued on the main stream so far
+            with torch.cuda.stream(side):
+                for i, q in self._side_ever.items():          # entries not rewritten in this step are stale
+                    if i not in self._side_now and self._bucket_of[i] == b:
+                        self._wview[i].zero_()
+                self.flat[a:e].add_(self.wflat[a:e])
+                self._works[b] = dist.all_reduce(self.flat[a:e], op=dist.ReduceOp.SUM, group=self.group,
+                                                 async_op=True)
+            return
         self._works[b] = dist.all_reduce(self.flat[a:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _flush_armed(self):
+        for b in self._armed:
+            if self._works[b] is None:
+                self._launch(b)
+        self._armed = []
+
+    def _check_open(self, p):
+        if self._works[self._bucket_of[id(p)]] is not None:
+            raise RuntimeError("GradAllReduce: a gradient was written after its bucket's all-reduce was issued "
+                               "(unexpected backward order; set BDBNN_WGRAD_SIDE=0 or overlap=False)")
+
+    def _account(self, p):
+        b = self._bucket_of[id(p)]
+        if id(p) in self._done:       # second event of a weight with a side-stream wgrad AND an autograd term
+            return
+        self._done.add(id(p))
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._armed.append(b)
+
+    # ---- functional.wgrad_side sink ----------------------------------------------------------------------
+    def side_target(self, p, stream):
+        """Buffer the side-stream wgrad of `p` writes (its view into `wflat`), or None: keep it on autograd's path."""
+        if not self.overlap or id(p) not in self._bucket_of or not p.is_contiguous():
+            return None
+        if self.wflat is None:
+            self.wflat = torch.zeros_like(self.flat)
+            off = 0
+            for q in reversed(self.params):
+                self._wview[id(q)] = torch.as_strided(self.wflat, q.size(), q.stride(), storage_offset=off)
+                off += q.numel()
+        self._side_stream = stream
+        self._check_open(p)
+        self._flush_armed()
+        self._side_now.add(id(p))
+        self._side_ever[id(p)] = p
+        self._account(p)          # the launch follows immediately; the bucket is issued at the NEXT event
+        return self._wview[id(p)]
 
     def _rebind(self, p):
         """Fail-safe: `optimizer.zero_grad()` (torch's default set_to_none=True) or user code dropped /
@@ -79,11 +145,10 @@ class GradAllReduce:
         p.grad = v
 
     def _hook(self, p):
+        self._check_open(p)           # (this gradient's accumulation is already enqueued: a flush below covers it)
+        self._flush_armed()
         self._rebind(p)
-        b = self._bucket_of[id(p)]
-        self._pending[b] -= 1
-        if self._pending[b] == 0 and self._works[b] is None:
-            self._launch(b)
+        self._account(p)
 
     def zero(self):
         self.flat.zero_()
@@ -91,14 +156,19 @@ class GradAllReduce:
             v = self._view[id(p)]
             if p.grad is not v:
                 p.grad = v
+        self._reset()
+
+    def _reset(self):
         self._pending = [b[2] for b in self.buckets]
         self._works = [None] * len(self.buckets)
+        self._done, self._armed, self._side_now = set(), [], set()
 
     def __call__(self):
         if not self.overlap:
             for p in self.params:              # no hooks registered: verify the views here
                 self._rebind(p)
         if self.world > 1:
+            self._armed = []
             for b in range(len(self.buckets)):
                 if self._works[b] is None:
                     self._launch(b)
@@ -106,8 +176,7 @@ class GradAllReduce:
                 w.wait()
             if self.scale:
                 self.flat.mul_(1.0 / self.world)
-            self._pending = [b[2] for b in self.buckets]
-            self._works = [None] * len(self.buckets)
+        self._reset()
 
 
 class FlatGradOptimizerShim:

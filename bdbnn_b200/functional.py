@@ -242,6 +242,7 @@ class _BinConv2d(torch.autograd.Function):
         ctx.gmode = (gname, gcode, ghalves)
         ctx.x_shape = tuple(x.shape)
         ctx.w_shape = tuple(weight.shape)
+        ctx.w_param = weight if (weight.is_leaf and weight.requires_grad) else None
         ctx.ede = ede_k is not None
         if ctx.ede:
             # EDE backward (train.py:409-415): soft-sign derivative needs the real values, and the
@@ -302,13 +303,22 @@ class _BinConv2d(torch.autograd.Function):
                                                      ctypes.byref(sh), st), "binconv_wgrad")
                 _lib.count(1)
             elif need_w:
-                gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
                 nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
-                ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
-                with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh, gh)):
-                    _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gcode, _p(amax), _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
-                                                        ctypes.byref(sh), _p(ws), nbytes, st),
-                               "binconv_wgrad_tc")
+                sbuf, sstream = (None, None) if ctx.ede else _side_launch(getattr(ctx, "w_param", None),
+                                                                          (gys, amax, xb, wmask, inv_gscale))
+                if sbuf is not None:      # wgrad_side scope: second stream, gw stays None
+                    with torch.cuda.stream(sstream):
+                        ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+                        _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gcode, _p(amax), _p(xb), _p(wmask), _p(inv_gscale),
+                                                            _p(sbuf), ctypes.byref(sh), _p(ws), nbytes, _stream()),
+                                   "binconv_wgrad_tc")
+                else:
+                    gw = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
+                    ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+                    with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh, gh)):
+                        _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gcode, _p(amax), _p(xb), _p(wmask), _p(inv_gscale),
+                                                            _p(gw), ctypes.byref(sh), _p(ws), nbytes, st),
+                                   "binconv_wgrad_tc")
                 _lib.count(2)
         else:
             if need_x:
@@ -657,6 +667,101 @@ def prepack_weights(items):
 _PREPACKED = {}     # filled by the network shells for the duration of one forward pass (same thread)
 
 
+def wgrad_side_enabled():
+    """BDBNN_WGRAD_SIDE (default 1): inside TrainStep's backward the weight-gradient GEMMs run on a second stream."""
+    return os.environ.get("BDBNN_WGRAD_SIDE", "1") != "0"
+
+
+class _WgradSide:
+    """State of the `wgrad_side` scope (one per process; the scope is entered by one thread at a time)."""
+
+    def __init__(self):
+        self.active = False
+        self.stream = None
+        self.bufs = {}       # id(param) -> persistent fp32 buffer the side-stream wgrad writes (param's shape, contiguous)
+        self.used = []       # (param, buffer) written in this scope
+        self.keep = []       # operands the side stream still reads: referenced until the join
+        self.sink = None     # ddp.GradAllReduce: owns the buffers and folds them into its flat gradient buffer
+
+    def target(self, param):
+        """Persistent gradient buffer for `param` if its wgrad may run on the side stream, else None.
+        Orders the side stream after everything enqueued on the current stream so far."""
+        if not self.active or param is None or not param.is_leaf or not param.requires_grad:
+            return None
+        if self.sink is not None:
+            buf = self.sink.side_target(param, self.stream)
+            if buf is None:
+                return None
+        else:
+            buf = self.bufs.get(id(param))
+            if buf is None or buf.shape != param.shape or buf.device != param.device:
+                buf = torch.empty(param.shape, dtype=torch.float32, device=param.device)
+                self.bufs[id(param)] = buf
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self.used.append((param, buf))
+        return buf
+
+
+_WSIDE = _WgradSide()
+
+
+class wgrad_side:
+    """Scope (bdbnn_b200.step.TrainStep wraps `loss.backward()` in it) in which the weight gradients of the binary
+    convs, the 1x1 shortcuts and the stem are computed on a SECOND stream: nothing in the backward chain consumes
+    them (dgrad -> BN backward -> dgrad ... is the critical path), so the split-K GEMMs fill the SMs that the
+    memory-bound BatchNorm kernels and the kernel boundaries of the main chain leave idle.  Inside the scope the
+    autograd nodes return no weight gradient; each wgrad writes a persistent per-parameter buffer on the side
+    stream, and the scope's exit joins the streams and adds the buffers into `.grad` (or binds them as `.grad`
+    where autograd produced none).  With `sink` = a ddp.GradAllReduce the buffers are views of its second flat
+    buffer and it folds them in bucket by bucket ahead of each all-reduce (see there).  Operands are kept referenced until the join, so the caching allocator cannot
+    hand their memory to main-stream kernels early; the same code is captured by GraphedTrainStep (fork / join
+    become graph dependencies).  Results are bit-identical to the single-stream order: the kernels are the same
+    and their summation order does not depend on the stream."""
+
+    def __init__(self, enable=True, sink=None):
+        self.enable = bool(enable) and wgrad_side_enabled() and not KernelTimer.enabled and torch.cuda.is_available()
+        self.sink = sink          # object with side_target(param, stream) (ddp.GradAllReduce) or None
+
+    def __enter__(self):
+        if self.enable:
+            if _WSIDE.active:
+                raise RuntimeError("wgrad_side scopes do not nest")
+            if _WSIDE.stream is None or _WSIDE.stream.device != torch.device("cuda", torch.cuda.current_device()):
+                _WSIDE.stream = torch.cuda.Stream()
+            _WSIDE.used, _WSIDE.keep, _WSIDE.sink, _WSIDE.active = [], [], self.sink, True
+        return self
+
+    def __exit__(self, *exc):
+        if not self.enable:
+            return False
+        _WSIDE.active = False
+        try:
+            if _WSIDE.used:
+                torch.cuda.current_stream().wait_stream(_WSIDE.stream)
+                if exc[0] is None and self.sink is None:
+                    grads, bufs = [], []
+                    for prm, buf in _WSIDE.used:
+                        if prm.grad is None:
+                            prm.grad = buf            # nothing else contributed: the buffer IS the gradient
+                        elif prm.grad is not buf:
+                            grads.append(prm.grad)
+                            bufs.append(buf)
+                    if grads:
+                        torch._foreach_add_(grads, bufs)
+        finally:
+            _WSIDE.used, _WSIDE.keep, _WSIDE.sink = [], [], None
+        return False
+
+
+def _side_launch(param, keep):
+    """(gradient buffer, torch stream) for a wgrad on the side stream, or (None, None): run it in line."""
+    buf = _WSIDE.target(param) if _WSIDE.active else None
+    if buf is None:
+        return None, None
+    _WSIDE.keep.extend(t for t in keep if t is not None)
+    return buf, _WSIDE.stream
+
+
 def unit_supported(x_shape, w_shape, stride, padding):
     """The fused unit needs all three tcgen05 kernels for the conv shape."""
     sh = conv_shape(x_shape, w_shape, stride, padding)
@@ -790,6 +895,8 @@ class _ConvBNAddUnit(torch.autograd.Function):
         ctx.bnctx_out = (y, alpha, mean, invstd) if i16 else None
         ctx.sh, ctx.gmode = sh, (gname, gcode, ghalves)
         ctx.shapes = (tuple(x.shape), tuple(weight.shape))
+        ctx.w_param = weight if (weight.is_leaf and weight.requires_grad) else None
+        ctx.sc_w_param = sc_weight if (sc_weight is not None and sc_weight.is_leaf and sc_weight.requires_grad) else None
         ctx.has_res = residual is not None and sc_weight is None
         ctx.res_is_x = bool(res_is_x)
         ctx.save_for_backward(y, mean, invstd, gamma.detach(), ymax, xm, xb, wt, wmask, gscale, inv_gscale, alpha,
@@ -846,6 +953,23 @@ class _ConvBNAddUnit(torch.autograd.Function):
         _lib.count(2 if ready else 3)
         x_shape, w_shape = ctx.shapes
         gx = gw = None
+        # the weight gradient first: in a wgrad_side scope it forks off here and overlaps this unit's dgrad as well
+        if ctx.needs_input_grad[1]:
+            nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
+            sbuf, sstream = _side_launch(ctx.w_param, (gys, amax, xb, wmask, inv_gscale))
+            if sbuf is not None:          # wgrad_side scope: second stream, persistent gradient buffer, gw stays None
+                with torch.cuda.stream(sstream):
+                    ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+                    _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gcode, _p(amax), _p(xb), _p(wmask), _p(inv_gscale),
+                                                        _p(sbuf), ctypes.byref(sh), _p(ws), nbytes, _stream()),
+                               "binconv_wgrad_tc")
+            else:
+                gw = torch.empty(w_shape, dtype=torch.float32, device=dev)
+                ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+                with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh, gh)):
+                    _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gcode, _p(amax), _p(xb), _p(wmask), _p(inv_gscale),
+                                                        _p(gw), ctypes.byref(sh), _p(ws), nbytes, st), "binconv_wgrad_tc")
+            _lib.count(2)
         if ctx.needs_input_grad[0]:
             gx = torch.empty(x_shape, dtype=torch.float32, device=dev, memory_format=torch.channels_last)
             done = False
@@ -871,20 +995,13 @@ class _ConvBNAddUnit(torch.autograd.Function):
                                                         _p(g) if ctx.res_is_x else _p(None), _p(gx),
                                                         ctypes.byref(sh), st), "binconv_dgrad_tc")
                 _lib.count(_dgrad_launches(sh))
-        if ctx.needs_input_grad[1]:
-            gw = torch.empty(w_shape, dtype=torch.float32, device=dev)
-            nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh)))
-            ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
-            with _timed("binconv_wgrad_tc", key, algorithmic_bytes("wgrad_tc", sh, gh)):
-                _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), gcode, _p(amax), _p(xb), _p(wmask), _p(inv_gscale), _p(gw),
-                                                    ctypes.byref(sh), _p(ws), nbytes, st), "binconv_wgrad_tc")
-            _lib.count(2)
         gres = gz if (ctx.has_res and ctx.needs_input_grad[4]) else None
         sc_gw = sc_dg = sc_db = None
         if ctx.n_sc:
             # shortcut branch: residual gradient = gz; its dgrad accumulates into gx in place
             sgx, sc_gw, sc_dg, sc_db = _shortcut_bwd_impl(gz, ctx.saved_tensors[12:], ctx.sc_geom,
-                                                          ctx.needs_input_grad[0], ctx.needs_input_grad[16], acc=gx)
+                                                          ctx.needs_input_grad[0], ctx.needs_input_grad[16], acc=gx,
+                                                          w_param=ctx.sc_w_param)
             gx = sgx if sgx is not None else gx
             sc_dg = sc_dg if ctx.needs_input_grad[17] else None
             sc_db = sc_db if ctx.needs_input_grad[18] else None
@@ -987,7 +1104,7 @@ def _shortcut_fwd_impl(x, weight, gamma, beta, running_mean, running_var, moment
     return z, saved, (sh1, shs, tuple(x.shape), tuple(weight.shape))
 
 
-def _shortcut_bwd_impl(gz, saved, geom, need_x, need_w, acc=None):
+def _shortcut_bwd_impl(gz, saved, geom, need_x, need_w, acc=None, w_param=None):
     """bn_bwd_pack -> dgrad_tc (scatter to the sampled positions) , wgrad_tc.
     acc: an fp32 NHWC gradient of x already holding the main branch's part — the shortcut's part is added
     in place (no zero fill, no separate add); otherwise a fresh tensor (zeros off the samples).
@@ -1022,12 +1139,20 @@ def _shortcut_bwd_impl(gz, saved, geom, need_x, need_w, acc=None):
         _lib.count(_dgrad_launches(shs))
     if need_w:
         wones = torch.full(((cout * cin + 31) // 32,), -1, **i32)
-        gw = torch.empty(w_shape, **f32)
         nbytes = int(L.bdbnn_wgrad_tc_workspace_bytes(ctypes.byref(sh1)))
-        ws = torch.empty((max(nbytes, 4) // 4,), **f32)
-        with _timed("shortcut_wgrad_tc", key, 2 * gys.numel() + 2 * xh.numel()):
-            _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), 3, _p(amax), _p(xh), _p(wones), _p(inv_gscale), _p(gw),
-                                                ctypes.byref(sh1), _p(ws), nbytes, st), "binconv_wgrad_tc(shortcut)")
+        sbuf, sstream = _side_launch(w_param, (gys, amax, xh, wones, inv_gscale))
+        if sbuf is not None:              # wgrad_side scope: second stream, gw stays None
+            with torch.cuda.stream(sstream):
+                ws = torch.empty((max(nbytes, 4) // 4,), **f32)
+                _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), 3, _p(amax), _p(xh), _p(wones), _p(inv_gscale), _p(sbuf),
+                                                    ctypes.byref(sh1), _p(ws), nbytes, _stream()),
+                           "binconv_wgrad_tc(shortcut)")
+        else:
+            gw = torch.empty(w_shape, **f32)
+            ws = torch.empty((max(nbytes, 4) // 4,), **f32)
+            with _timed("shortcut_wgrad_tc", key, 2 * gys.numel() + 2 * xh.numel()):
+                _lib.check(L.bdbnn_binconv_wgrad_tc(_p(gys), 3, _p(amax), _p(xh), _p(wones), _p(inv_gscale), _p(gw),
+                                                    ctypes.byref(sh1), _p(ws), nbytes, st), "binconv_wgrad_tc(shortcut)")
         _lib.count(2)
     return gx, gw, dgamma, dbeta
 
@@ -1202,11 +1327,19 @@ def _stem_conv_fwd_impl(x, weight, want_stats=False):
     return y, xw, x_amax
 
 
-def _stem_wgrad_impl(gys, g_amax, xw, x_amax, n, h, w):
+def _stem_wgrad_impl(gys, g_amax, xw, x_amax, n, h, w, w_param=None):
     L = _lib.lib()
     dev = gys.device
-    gw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dev)
     nbytes = int(L.bdbnn_stem_wgrad_workspace_bytes(n, h, w))
+    sbuf, sstream = _side_launch(w_param, (gys, g_amax, xw, x_amax))
+    if sbuf is not None:                  # wgrad_side scope: second stream, the caller returns no gradient
+        with torch.cuda.stream(sstream):
+            ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
+            _lib.check(L.bdbnn_stem_conv_wgrad(_p(gys), _p(g_amax), _p(xw), _p(x_amax), _p(sbuf), n, h, w,
+                                               _p(ws), nbytes, _stream()), "stem_conv_wgrad")
+        _lib.count(2)
+        return None
+    gw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dev)
     ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=dev)
     with _timed("stem_conv_wgrad", f"stem_N{n}_{h}x{w}", 2 * gys.numel() + xw.numel() * 2):
         _lib.check(L.bdbnn_stem_conv_wgrad(_p(gys), _p(g_amax), _p(xw), _p(x_amax), _p(gw), n, h, w,
@@ -1224,6 +1357,7 @@ class _StemConv(torch.autograd.Function):
     @_on_device
     def forward(ctx, x, weight):
         y, xw, x_amax = _stem_conv_fwd_impl(x, weight)
+        ctx.w_param = weight if (weight.is_leaf and weight.requires_grad) else None
         ctx.geom = (x.shape[0], x.shape[2], x.shape[3], y.shape[2], y.shape[3])
         ctx.save_for_backward(xw, x_amax)
         return y
@@ -1245,7 +1379,7 @@ class _StemConv(torch.autograd.Function):
             _lib.check(L.bdbnn_grad_pack(_p(g), _p(ones), n * ho * wo, 64, 3, _p(g_amax), _p(gys), _stream()),
                        "grad_pack")
         _lib.count(2)
-        return None, _stem_wgrad_impl(gys, g_amax, xw, x_amax, n, h, w)
+        return None, _stem_wgrad_impl(gys, g_amax, xw, x_amax, n, h, w, ctx.w_param)
 
 
 class _StemFused(torch.autograd.Function):
@@ -1260,6 +1394,7 @@ class _StemFused(torch.autograd.Function):
         outs, saved, ctx.geom = _bn_pool_fwd_impl(y, gamma, beta, running_mean, running_var, momentum, eps, k,
                                                   stride, pad, stats)
         ctx.xgeom = (x.shape[0], x.shape[2], x.shape[3])
+        ctx.w_param = weight if (weight.is_leaf and weight.requires_grad) else None
         ctx.save_for_backward(xw, x_amax, *saved)
         nd = [t for t in outs[1:] if t is not None]
         if nd:
@@ -1273,7 +1408,7 @@ class _StemFused(torch.autograd.Function):
             return (None,) * 11
         xw, x_amax = ctx.saved_tensors[:2]
         (gys, g_amax), dgamma, dbeta = _bn_pool_bwd_impl(gz, ctx.saved_tensors[2:], ctx.geom, half=True)
-        gw = _stem_wgrad_impl(gys, g_amax, xw, x_amax, *ctx.xgeom) if ctx.needs_input_grad[1] else None
+        gw = _stem_wgrad_impl(gys, g_amax, xw, x_amax, *ctx.xgeom, w_param=ctx.w_param) if ctx.needs_input_grad[1] else None
         return (None, gw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
                 None, None, None, None, None, None, None)
 

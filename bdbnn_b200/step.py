@@ -16,6 +16,8 @@ Nothing here calls .item(): the five host syncs per step of train.py:519-524 are
 from dataclasses import dataclass, field
 from typing import Optional, Sequence, Union
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -142,6 +144,7 @@ class TrainStep:
         self.criterion = criterion or nn.CrossEntropyLoss()
         self.meters = None          # device float64 {ce*N, acc1*N, acc5*N, N} (fused CE path)
         self._loss_sum = None       # device float64 sum of total loss*N (train.py:519 / 638 `losses` meter)
+        self._t_stream = None       # second stream of the teacher forward
         self.hooked = select_hooked_weights(model, self.cfg)
         if self.cfg.teacher_student and teacher is None:
             raise ValueError("teacher_student step needs a teacher model")
@@ -181,13 +184,32 @@ class TrainStep:
 
     def __call__(self, images, target, epoch=0):
         cfg = self.cfg
+        output_teacher = None
+        t_stream = None
+        if cfg.teacher_student and images.is_cuda and os.environ.get("BDBNN_TEACHER_SIDE", "1") != "0":
+            from .functional import KernelTimer
+            if not KernelTimer.enabled:
+                # the frozen teacher's forward (train.py:603) depends on nothing the student computes: run it on a
+                # second stream under the student's forward; the streams join before the KD losses read its logits
+                # (the layer-wise KD term reads weights only).  Everything it allocates belongs to that stream's
+                # pool and is only recycled by the next teacher forward, which the wait below orders after all
+                # main-stream work enqueued so far — so the logits cannot be overwritten while the losses read them.
+                if self._t_stream is None:
+                    self._t_stream = torch.cuda.Stream()
+                t_stream = self._t_stream
+                t_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(t_stream), torch.no_grad():
+                    output_teacher = self.teacher(images)                         # train.py:603
         output = self.model(images)                                               # train.py:492 / 602
         ce, acc1, acc5 = self._ce(output, target)                                 # train.py:493/614, :518
         loss_kl = loss_kl_c = 0
         if cfg.teacher_student:
             from .functional import _timed
-            with torch.no_grad(), _timed("teacher_forward(cuDNN fp32)", "teacher", 0):
-                output_teacher = self.teacher(images)                             # train.py:603
+            if t_stream is not None:
+                torch.cuda.current_stream().wait_stream(t_stream)
+            else:
+                with torch.no_grad(), _timed("teacher_forward(cuDNN fp32)", "teacher", 0):
+                    output_teacher = self.teacher(images)                         # train.py:603
             alpha, beta, lam_ce = cfg.alpha, cfg.beta, cfg.w_lambda_ce
             if cfg.react:                                                         # train.py:605-609
                 beta, lam_ce = 0, 0
@@ -214,7 +236,12 @@ class TrainStep:
             self.grad_sync.zero()             # flat-buffer .grad views stay bound (GradAllReduce); train.py:527
         else:
             self.optimizer.zero_grad()                                            # train.py:527
-        loss.backward()                                                           # train.py:528
+        # weight-gradient GEMMs on a second stream (functional.wgrad_side); a GradAllReduce owns their buffers and
+        # folds them into its buckets, any other grad_sync callable keeps the gradients on autograd's path
+        from .functional import wgrad_side
+        sink = self.grad_sync if hasattr(self.grad_sync, "side_target") else None
+        with wgrad_side(loss.is_cuda and (self.grad_sync is None or sink is not None), sink=sink):
+            loss.backward()                                                       # train.py:528
         if self.grad_sync is not None:
             self.grad_sync()
         self.optimizer.step()                                                     # train.py:529
