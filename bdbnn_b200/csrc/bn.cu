@@ -426,7 +426,10 @@ static int bn_bwd_pack_impl(const float* gz, const void* y, const float* alpha_i
   rc = check_launch("bn_bwd_bound_kernel");
   if (rc) return rc;
   const int64_t n4 = n_pix * C4;
-  const int grid = bn_grid(n4, C4);
+  // BDBNN_BN_BWD_PER_SM: resident blocks per SM of the backward apply kernel (64 registers x 256 threads: 4 fill the
+  // register file; 3 leave room for a side-stream wgrad CTA next to them)
+  static const int bwd_per_sm = [] { const char* e = getenv("BDBNN_BN_BWD_PER_SM"); return e ? atoi(e) : 8; }();
+  const int grid = bn_grid(n4, C4, bwd_per_sm);
   const float4* g4 = reinterpret_cast<const float4*>(gz);
   const float4* k4 = reinterpret_cast<const float4*>(consts_ws);
   if (i16) {

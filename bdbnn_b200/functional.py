@@ -727,7 +727,8 @@ class wgrad_side:
             if _WSIDE.active:
                 raise RuntimeError("wgrad_side scopes do not nest")
             if _WSIDE.stream is None or _WSIDE.stream.device != torch.device("cuda", torch.cuda.current_device()):
-                _WSIDE.stream = torch.cuda.Stream()
+                # BDBNN_SIDE_PRIO: CUDA priority of the second stream (0 = lowest = default, -1 = above the default)
+                _WSIDE.stream = torch.cuda.Stream(priority=int(os.environ.get("BDBNN_SIDE_PRIO", "0")))
             _WSIDE.used, _WSIDE.keep, _WSIDE.sink, _WSIDE.active = [], [], self.sink, True
         return self
 
@@ -750,6 +751,40 @@ class wgrad_side:
                         torch._foreach_add_(grads, bufs)
         finally:
             _WSIDE.used, _WSIDE.keep, _WSIDE.sink = [], [], None
+        return False
+
+
+class _FwdSide:
+    """Forward-pass use of the second stream (shortcut branches), switched on by TrainStep for its model forward."""
+
+    def __init__(self):
+        self.active = False
+
+    def stream(self):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if _WSIDE.stream is None or _WSIDE.stream.device != dev:
+            _WSIDE.stream = torch.cuda.Stream(priority=int(os.environ.get("BDBNN_SIDE_PRIO", "0")))
+        return _WSIDE.stream
+
+
+_FWD_SIDE = _FwdSide()
+
+
+class forward_side:
+    """Scope for the model forward inside TrainStep: independent branches may use the second stream (BDBNN_FWD_SIDE=0
+    switches it off)."""
+
+    def __init__(self, enable=True):
+        self.enable = (bool(enable) and wgrad_side_enabled() and os.environ.get("BDBNN_FWD_SIDE", "1") != "0" and
+                       torch.cuda.is_available())
+
+    def __enter__(self):
+        self.prev = _FWD_SIDE.active
+        _FWD_SIDE.active = self.enable
+        return self
+
+    def __exit__(self, *exc):
+        _FWD_SIDE.active = self.prev
         return False
 
 
@@ -783,9 +818,20 @@ class _ConvBNAddUnit(torch.autograd.Function):
         # and its input gradient is added in place to this conv's (see backward)
         ctx.n_sc = 0
         sc_saved = ()
+        sc_join = None
         if sc_weight is not None:
-            residual, sc_saved, ctx.sc_geom = _shortcut_fwd_impl(x, sc_weight, sc_gamma, sc_beta, sc_rm, sc_rv,
-                                                                sc_momentum, sc_eps, sc_stride)
+            if _FWD_SIDE.active and not KernelTimer.enabled:
+                # step scope (TrainStep): the shortcut branch depends only on x — run it on the second stream under the
+                # main conv; the streams join before bn_fwd reads the residual.  (Every side section starts by waiting
+                # for the main stream, which is what makes recycling of side-pool blocks safe.)
+                sc_join = _FWD_SIDE.stream()
+                sc_join.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(sc_join):
+                    residual, sc_saved, ctx.sc_geom = _shortcut_fwd_impl(x, sc_weight, sc_gamma, sc_beta, sc_rm, sc_rv,
+                                                                        sc_momentum, sc_eps, sc_stride)
+            else:
+                residual, sc_saved, ctx.sc_geom = _shortcut_fwd_impl(x, sc_weight, sc_gamma, sc_beta, sc_rm, sc_rv,
+                                                                    sc_momentum, sc_eps, sc_stride)
             ctx.n_sc = len(sc_saved)
         ctx.set_materialize_grads(False)     # no zero tensors for the (integer) pack outputs in backward
         L = _lib.lib()
@@ -878,6 +924,8 @@ class _ConvBNAddUnit(torch.autograd.Function):
         zb = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.int16, device=dev) if pack else None
         zb8 = torch.empty((n, sh.Ho, sh.Wo, cout), dtype=torch.uint8, device=dev) if (pack and fwd8_enabled()) else None
         ybytes = 2 if i16 else 4
+        if sc_join is not None:
+            torch.cuda.current_stream().wait_stream(sc_join)
         with _timed("bn_fwd", key, ((0 if in_conv else 4) + ybytes + 8 + (2.25 if pack else 0) +
                                     (1 if zb8 is not None else 0)) * n_pix * cout):
             if i16:
