@@ -506,11 +506,17 @@ def main():
                 bufs[b][1].copy_(y_host, non_blocking=True)
                 ready[b].record(copy_stream)
 
+        loss_pin = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+
         def e2e_loop(n):
+            # every step: H2D of its batch (prefetched one step ahead on the copy stream) and a D2H read of its loss
+            # (train.py:519 `loss.item()`).  The read is asynchronous — copied to pinned memory right behind the step
+            # and consumed by the host after the NEXT step has been launched — so the host never leaves the GPU idle.
             for b in range(2):
                 consumed[b].record()
             prefetch(0)
-            last = None
+            last, pending = None, None
             for i in range(n):
                 b = i % 2
                 if i + 1 < n:
@@ -518,7 +524,14 @@ def main():
                 torch.cuda.current_stream().wait_event(ready[b])
                 out = step(bufs[b][0], bufs[b][1])
                 consumed[b].record()
-                last = float(out["loss"])       # D2H read of the step's result (train.py:519)
+                loss_pin[b].copy_(out["loss"], non_blocking=True)
+                loss_evt[b].record()
+                if pending is not None:
+                    loss_evt[pending].synchronize()
+                    last = float(loss_pin[pending])
+                pending = b
+            loss_evt[pending].synchronize()
+            last = float(loss_pin[pending])
             return last
 
         e2e_loop(2)
@@ -535,8 +548,8 @@ def main():
                "ms_per_step": round(ms_e2e / args.steps, 3),
                "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8) * world,
                "d2h_bytes_per_step": 4 * world,
-               "note": "whole job (all ranks): pinned fp32 batch, H2D double-buffered on a copy stream, "
-                       "loss read back every step"}
+               "note": "whole job (all ranks): pinned fp32 batch, H2D double-buffered on a copy stream; every "
+                       "step's loss is copied to pinned host memory and read by the host one launch later"}
 
     # ---- secondary value: the fp32-class gradient operand mode (bf16 hi+lo pair, two MMAs per K step) -------
     from bdbnn_b200.functional import grad_mode

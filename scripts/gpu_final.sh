@@ -16,11 +16,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --profile-mode > gpurun_out/${TAG}_ncu_bench.log 2>&1
 # ncu --set full of the main kernels over one step
 timeout 1500 ncu --set full --clock-control none --profile-from-start off \
-   -k regex:"tc_conv2_kernel|tc_wgrad_kernel|bn_reduce_kernel|bn_apply_add_pack_kernel|bn_bwd_pack_kernel|weight_pack_multi|weight_wt_multi|bn_pool" -c 160 \
+   -k regex:"tc_conv2_kernel|tc_conv64_kernel|tc_wgrad_kernel|bn_reduce_kernel|bn_apply_add_pack_kernel|bn_bwd_pack_kernel|weight_pack_multi|weight_wt_multi|bn_pool" -c 180 \
    -o /tmp/${TAG}_prof -f python bench.py --steps 1 --profile-mode > gpurun_out/${TAG}_ncu_full.log 2>&1
 ncu -i /tmp/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
-# source-level capture of ONE layer1 forward launch (the N = 64 MMA pipeline question)
-timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"tc_conv2_kernel" \
+# source-level capture of ONE layer1 forward launch of the pixel-N kernel (launch 0 is the stem variant)
+timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"tc_conv64_kernel" \
    --launch-skip 1 --launch-count 1 -o /tmp/${TAG}_l1fwd -f python bench.py --steps 1 --profile-mode > gpurun_out/${TAG}_ncu_l1fwd.log 2>&1
 ncu -i /tmp/${TAG}_l1fwd.ncu-rep --page source --csv > gpurun_out/${TAG}_l1fwd_source.csv 2>/dev/null
 ncu -i /tmp/${TAG}_l1fwd.ncu-rep --page raw --csv > gpurun_out/${TAG}_l1fwd_raw.csv 2>/dev/null
