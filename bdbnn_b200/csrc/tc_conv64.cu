@@ -232,57 +232,68 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int cbi = 0; cbi < kC64N / 128; ++cbi) {
         if (p.dbg & 2) break;
         const int c0 = (4 * cbi + grp) * 32;                       // first pixel column of this block
-        uint32_t v[32];
-        tmem_ld32(tbase + uint32_t(c0), v);
         // The padded width PW is a multiple of 32, so a block of 32 raster columns lies inside ONE unit row:
         // image row h0 + hi, image columns wi0 .. wi0 + 31, of which the first nv are outputs.
         const int hi = c0 / p.PW, wi0 = c0 - hi * p.PW;
         const int nv = hi < rows_ok ? min(32, max(0, p.OW - wi0)) : 0;
-        if (nv == 0) { tmem_ld_wait(); continue; }
+        if (nv == 0) continue;
         // element offset (32-bit, checked on the host) of pixel 0 of the block for this lane's channel
         const int off = ((n0 * p.OH + h0 + hi) * p.OW + wi0) * 64 + ch;
         uint32_t mword = 0;
-        float addv[32];
-        uint32_t yv[BST ? 32 : 1];
-        if (MODE == 1) {
-          // lane j fetches the STE-mask word of pixel j (this warp's 32 channels); broadcast by shuffle below
+        if (MODE == 1)   // lane j fetches the STE-mask word of pixel j (this warp's 32 channels); broadcast by shuffle below
           mword = lane < nv ? __ldg(p.mask + int64_t((off - ch) >> 6) * 2 + lane * 2 + quad) : 0u;
-          if (p.add != nullptr) {
+        // pixels per pass: 32, or 16 with the BatchNorm backward sums (v + add + y of 32 pixels would not fit the
+        // register budget of 448 threads: the first version spilled and ran at 0.4 ms per launch)
+        constexpr int NPB = BST ? 16 : 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) addv[j] = j < nv ? p.add[off + j * 64] : 0.f;       // may alias out
-          }
-          if (BST) {
+        for (int hb = 0; hb < 32 / NPB; ++hb) {
+          const int p0 = hb * NPB;                                 // first pixel of this pass inside the block
+          if (p0 >= nv) break;                                     // warp-uniform
+          uint32_t v[NPB];
+          if constexpr (NPB == 32) tmem_ld32(tbase + uint32_t(c0), v);
+          else tmem_ld16(tbase + uint32_t(c0 + p0), v);
+          float addv[NPB];
+          uint32_t yv[BST ? NPB : 1];
+          if (MODE == 1) {
+            if (p.add != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) yv[j] = j < nv ? uint32_t(uint16_t(__ldg(p.st_y + off + j * 64))) : 0u;
-          }
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = j < nv;                                  // warp-uniform
-          float o = __uint_as_float(v[j]);
-          if (MODE == 0 && STEM) {        // real-valued result: fp32 statistics per unit, fp64 across units
-            const float yv_ = ok ? o * alpha : 0.f;
-            if (ok) p.out[off + j * 64] = yv_;
-            u_sum += yv_; u_sq = fmaf(yv_, yv_, u_sq); f_max = fmaxf(f_max, fabsf(yv_));
-          } else if (MODE == 0) {
-            const int yi = ok ? int(o) : 0;
-            if (ok) {
-              if (I16) p.out_i16[off + j * 64] = int16_t(yi);
-              else p.out[off + j * 64] = o * alpha;
+              for (int j = 0; j < NPB; ++j) addv[j] = p0 + j < nv ? p.add[off + (p0 + j) * 64] : 0.f;   // may alias out
             }
-            u_isum += yi;
-            u_isq += uint32_t(yi * yi);
-            i_max = max(i_max, abs(yi));
-          } else {
-            const uint32_t wordj = __shfl_sync(0xffffffffu, mword, j);
-            o = ((wordj >> lane) & 1u) ? o * post : 0.f;
-            if (p.add != nullptr) o += addv[j];
-            if (ok) p.out[off + j * 64] = o;
             if (BST) {
-              const float g = ok ? o : 0.f;
-              const float yh = fmaf(float(int16_t(yv[j])), st_a, -st_b);
-              u_sum += g; u_sq = fmaf(g, yh, u_sq); f_max = fmaxf(f_max, fabsf(g));
+#pragma unroll
+              for (int j = 0; j < NPB; ++j)
+                yv[j] = p0 + j < nv ? uint32_t(uint16_t(__ldg(p.st_y + off + (p0 + j) * 64))) : 0u;
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < NPB; ++jj) {
+            const int j = p0 + jj;
+            const bool ok = j < nv;                                  // warp-uniform
+            float o = __uint_as_float(v[jj]);
+            if (MODE == 0 && STEM) {        // real-valued result: fp32 statistics per unit, fp64 across units
+              const float yv_ = ok ? o * alpha : 0.f;
+              if (ok) p.out[off + j * 64] = yv_;
+              u_sum += yv_; u_sq = fmaf(yv_, yv_, u_sq); f_max = fmaxf(f_max, fabsf(yv_));
+            } else if (MODE == 0) {
+              const int yi = ok ? int(o) : 0;
+              if (ok) {
+                if (I16) p.out_i16[off + j * 64] = int16_t(yi);
+                else p.out[off + j * 64] = o * alpha;
+              }
+              u_isum += yi;
+              u_isq += uint32_t(yi * yi);
+              i_max = max(i_max, abs(yi));
+            } else {
+              const uint32_t wordj = __shfl_sync(0xffffffffu, mword, j);
+              o = ((wordj >> lane) & 1u) ? o * post : 0.f;
+              if (p.add != nullptr) o += addv[jj];
+              if (ok) p.out[off + j * 64] = o;
+              if (BST) {
+                const float g = ok ? o : 0.f;
+                const float yh = fmaf(float(int16_t(yv[jj])), st_a, -st_b);
+                u_sum += g; u_sq = fmaf(g, yh, u_sq); f_max = fmaxf(f_max, fabsf(g));
+              }
             }
           }
         }

@@ -59,25 +59,30 @@ def parse():
     return ap.parse_args()
 
 
-TRAFFIC_KERNEL = {  # KernelTimer family -> kernel name in profiles/*_dram_traffic.json (ncu --set full)
-    "binconv_dgrad_tc": "tc_conv2_kernel<1>", "binconv_fwd_tc": "tc_conv2_kernel<0>",
-    "binconv_fwd_tc8": "tc_conv2_kernel<0>", "binconv_wgrad_tc": "tc_wgrad_kernel",
-    "bn_fwd": "bn_apply_add_pack_kernel<1>", "bn_bwd_pack": "bn_bwd_pack_kernel<3>",
+TRAFFIC_KERNEL = {  # KernelTimer family -> kernel-name prefixes in profiles/*_dram_traffic.json (ncu --set full)
+    "binconv_dgrad_tc": ("tc_conv2_kernel<1", "tc_conv64_kernel<1"),
+    "binconv_fwd_tc": ("tc_conv2_kernel<0", "tc_conv64_kernel<0, 0, 1, 0"),
+    "binconv_fwd_tc8": ("tc_conv2_kernel<0",), "binconv_wgrad_tc": ("tc_wgrad_kernel",),
+    "bn_fwd": ("bn_apply_add_pack_kernel<1",), "bn_bwd_pack": ("bn_bwd_pack_kernel<3",),
 }
 
 
-def ncu_traffic(family):
-    """dram__bytes_read+write per launch of the family's main kernel, from the newest committed ncu capture."""
+def ncu_traffic(family, calls_per_step):
+    """dram__bytes_read+write of the family's kernels over ONE step of the newest committed ncu capture, divided by
+    the family's API calls per step (a stride-2 dgrad is four phase launches; the three 1x1 shortcut dgrads run the
+    same kernel and are included, so the figure is an upper bound for the family)."""
     import glob
     import re
     nat = lambda f: [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", os.path.basename(f))]
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")), key=nat)   # r1_step10 > r1_step9
-    if not files or family not in TRAFFIC_KERNEL:
+    files = sorted((f for f in glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")) if "losses" not in f),
+                   key=nat)                                                     # r1_step9 < r1_step10 < r2_final
+    if not files or family not in TRAFFIC_KERNEL or not calls_per_step:
         return None, None
     with open(files[-1]) as fh:
         d = json.load(fh)
-    e = d.get(TRAFFIC_KERNEL[family])
-    return (round(e["dram_bytes_per_launch"]), os.path.basename(files[-1])) if e else (None, None)
+    tot = sum(e["launches"] * e["dram_bytes_per_launch"] for k, e in d.items()
+              if any(k.startswith(pre) for pre in TRAFFIC_KERNEL[family]))
+    return (round(tot / calls_per_step), os.path.basename(files[-1])) if tot else (None, None)
 
 
 def peaks():
@@ -498,12 +503,15 @@ def main():
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+        diag = os.environ.get("BDBNN_E2E_DIAG", "")      # attribution runs only (scripts/): "noh2d", "nod2d"
+
         def prefetch(i):
             b = i % 2
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[b])
-                bufs[b][0].copy_(x_host, non_blocking=True)
-                bufs[b][1].copy_(y_host, non_blocking=True)
+                if diag != "noh2d":
+                    bufs[b][0].copy_(x_host, non_blocking=True)
+                    bufs[b][1].copy_(y_host, non_blocking=True)
                 ready[b].record(copy_stream)
 
         loss_pin = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -522,7 +530,10 @@ def main():
                 if i + 1 < n:
                     prefetch(i + 1)
                 torch.cuda.current_stream().wait_event(ready[b])
-                out = step(bufs[b][0], bufs[b][1])
+                if diag == "nod2d" and getattr(step, "static_images", None) is not None:
+                    out = step(step.static_images, step.static_target)
+                else:
+                    out = step(bufs[b][0], bufs[b][1])
                 consumed[b].record()
                 loss_pin[b].copy_(out["loss"], non_blocking=True)
                 loss_evt[b].record()
@@ -615,7 +626,7 @@ def main():
     timed = [k for k in kernels if k["achieved_gbs"]]       # families with algorithmic bytes (not the cuDNN teacher)
     if timed:
         top = timed[0]
-        traffic, traffic_src = ncu_traffic(top["kernel"])
+        traffic, traffic_src = ncu_traffic(top["kernel"], top["launches_per_step"])
         roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": round(top["achieved_gbs"] / peak, 4), "traffic": traffic,
                     "traffic_source": traffic_src,
