@@ -260,9 +260,16 @@ tc_conv64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               for (int j = 0; j < NPB; ++j) addv[j] = p0 + j < nv ? p.add[off + (p0 + j) * 64] : 0.f;   // may alias out
             }
             if (BST) {
+              // plain ld.global, NOT ld.global.nc / __ldg: a non-coherent load may be moved past the stores below, and
+              // ptxas sank each one next to its use — one exposed DRAM latency per pixel, 0.38 ms per launch.  An
+              // ordinary load may alias the stores, so all NPB of them are issued here, ahead of the TMEM wait.
 #pragma unroll
-              for (int j = 0; j < NPB; ++j)
-                yv[j] = p0 + j < nv ? uint32_t(uint16_t(__ldg(p.st_y + off + (p0 + j) * 64))) : 0u;
+              for (int j = 0; j < NPB; ++j) {
+                uint16_t t = 0;
+                if (p0 + j < nv)
+                  asm volatile("ld.global.u16 %0, [%1];" : "=h"(t) : "l"(p.st_y + off + (p0 + j) * 64) : "memory");
+                yv[j] = t;
+              }
             }
           }
           tmem_ld_wait();
