@@ -183,7 +183,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t it = 0, pcount = 0;
-      int tr_n = 0;
+      uint32_t stage = 0, phase = 0;          // ring position, advanced incrementally (this is one thread: no divisions
+      int tr_n = 0;                           // by run-time values inside the loops)
       const uint32_t patch_tx = uint32_t(p.PW * p.PH * p.HBNI) * uint32_t(p.row_bytes);
       for (int w = cta_w; w < n_work; w += n_ctas_w) {
         const int nt = w % p.n_ntiles;
@@ -191,6 +192,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const SuperGeom g = super_geom(p, sup);
         const int ntl_peer = CG == 2 ? super_geom(p, sup_of(w, rank ^ 1u)).ntl : 0;
         const int nn0 = nt * p.BN + int(rank) * (p.BN / CG);        // this CTA's rows of the weight tile
+        const int t0_n = p.halo ? 0 : (sup * p.TS) / p.tiles_h, t0_h = p.halo ? 0 : sup * p.TS - t0_n * p.tiles_h;
         for (int kb = 0; kb < kb_total; ++kb) {
           const int kbb = kb >= p.n_kb ? kb - p.n_kb : kb;
           if (p.halo) {
@@ -209,9 +211,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             ++pcount;
           }
-          for (int ti = 0; ti < p.n_taps; ++ti, ++it) {
-            const uint32_t stage = it % uint32_t(p.stages);
-            const uint32_t phase = (it / uint32_t(p.stages)) & 1u;
+          for (int ti = 0; ti < p.n_taps; ++ti, ++it, stage = stage + 1 == uint32_t(p.stages) ? (phase ^= 1u, 0u) : stage + 1) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
             const uint32_t fb_local = smem_u32(&full_bar[stage]);
             const uint32_t fb = CG == 2 ? mapa_shared(fb_local, 0) : fb_local;
@@ -223,9 +223,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               mbar_expect_tx(fb_local, tx);
             }
             if (!p.halo) {
-              for (int j = 0; j < g.ntl; ++j) {
-                const int t = sup * p.TS + j;
-                const int tile_n = t / p.tiles_h, tile_h = t - tile_n * p.tiles_h;
+              int tile_n = t0_n, tile_h = t0_h;              // tile sup * TS + j, advanced without dividing
+              for (int j = 0; j < g.ntl; ++j, tile_h + 1 == p.tiles_h ? (tile_h = 0, ++tile_n) : ++tile_h) {
                 const uint32_t d = dst + p.b_bytes + uint32_t(j) * (kTileM * uint32_t(p.row_bytes));
                 if (CG == 2)
                   tma_load_4d_cg2(d, &tmA, fb, kb * p.kb_elems, p.tap_dw[ti], tile_h * p.BH * p.in_step + p.tap_dh[ti],
@@ -252,6 +251,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t row16 = uint32_t(p.row_bytes) >> 4;          // descriptor-address units per pixel row
       const int k_steps = p.row_bytes / 32;
       uint32_t it = 0, pcount = 0, wcount = 0;
+      uint32_t stage = 0, phase = 0;
       int tr_n = 0;
       auto commit = [&](uint32_t bar) { if (CG == 2) umma_commit_cg2(bar); else umma_commit(bar); };
       for (int w = cta_w; w < n_work; w += n_ctas_w, ++wcount) {
@@ -274,9 +274,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ++pcount;
             BDBNN_TR(1, 2);
           }
-          for (int ti = 0; ti < p.n_taps; ++ti, ++it) {
-            const uint32_t stage = it % uint32_t(p.stages);
-            const uint32_t phase = (it / uint32_t(p.stages)) & 1u;
+          for (int ti = 0; ti < p.n_taps; ++ti, ++it, stage = stage + 1 == uint32_t(p.stages) ? (phase ^= 1u, 0u) : stage + 1) {
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             tc_fence_after();
             if (ti == 0) BDBNN_TR(1, 3);

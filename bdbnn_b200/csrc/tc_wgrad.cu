@@ -81,6 +81,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t unit_off[kMaxUnits];   // byte offset of unit i's operand view inside a stage
+  __shared__ int32_t unit_c[kMaxUnits], unit_dw[kMaxUnits], unit_dh[kMaxUnits];   // box mode: TMA coordinates of unit i
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -115,6 +116,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       off = threadIdx.x * p.a_box_bytes;
     }
     unit_off[threadIdx.x] = off;
+    // the producer is ONE thread: everything per unit that needs a division is computed here, once (ncu of the
+    // layer4 launch showed the per-stage address arithmetic of 8 loads — ~750 dependent instructions — at 4.4 K
+    // cycles per stage, four times the MMA time)
+    const int r = t / p.kw, sx = t - r * p.kw;
+    unit_c[threadIdx.x] = j * 64;
+    unit_dw[threadIdx.x] = sx - p.pad;
+    unit_dh[threadIdx.x] = r - p.pad;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -166,34 +174,33 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int n_a_loads = p.halo ? p.n_a_boxes : g_cta * upt;
       const uint32_t tx = uint32_t(n_a_loads) * uint32_t(p.rows_a) * a_row +
                           uint32_t(nb_boxes) * uint32_t(p.rows_b) * b_row;
-      int it = 0, tr_n = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-        const int stage = it % p.stages;
-        const uint32_t phase = uint32_t(it / p.stages) & 1u;
+      int tr_n = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      int tile_n = kb_begin / p.tiles_h, tile_h = kb_begin - tile_n * p.tiles_h;   // advanced incrementally
+      const int n_units_cta = g_cta * upt;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         BDBNN_WTR(0, 0);
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
         BDBNN_WTR(0, 1);
         const uint32_t fb = smem_u32(&full_bar[stage]);
         mbar_expect_tx(fb, tx);
-        const int tile_n = kb / p.tiles_h, tile_h = kb - tile_n * p.tiles_h;
         const int n0 = tile_n * p.BNI, h0 = tile_h * p.BH;
         const uint32_t dst0 = tiles_base + stage * stage_bytes;
         if (p.halo) {
           for (int j = 0; j < p.n_a_boxes; ++j)
             tma_load_4d(dst0 + j * p.a_box_bytes, &tmX, fb, j * 64, p.dw_min, h0 + p.dh_min, n0);
         } else {
-          for (int i = 0; i < g_cta * upt; ++i) {
-            int u = mt0 * upt + i;
-            if (u >= p.n_units) u = p.n_units - 1;
-            const int t = u / p.chunks_per_tap, j = u - t * p.chunks_per_tap;
-            const int r = t / p.kw, s = t - r * p.kw;
-            tma_load_4d(dst0 + i * p.a_box_bytes, &tmX, fb, j * 64, s - p.pad, h0 * p.stride + r - p.pad, n0);
-          }
+          const int hs = h0 * p.stride;
+          for (int i = 0; i < n_units_cta; ++i)
+            tma_load_4d(dst0 + i * p.a_box_bytes, &tmX, fb, unit_c[i], unit_dw[i], hs + unit_dh[i], n0);
         }
+        uint32_t bdst = dst0 + a_bytes;
         for (int hf = 0; hf < p.g_halves; ++hf)
-          for (int jb = 0; jb < nb_chunks; ++jb)
-            tma_load_4d(dst0 + a_bytes + (hf * nb_chunks + jb) * p.b_box_bytes, &tmG, fb,
-                        hf * p.Cout + nn0 + jb * 64, 0, h0, n0);
+          for (int jb = 0; jb < nb_chunks; ++jb, bdst += p.b_box_bytes)
+            tma_load_4d(bdst, &tmG, fb, hf * p.Cout + nn0 + jb * 64, 0, h0, n0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        if (++tile_h == p.tiles_h) { tile_h = 0; ++tile_n; }
       }
     }
   } else if (warp == 5) {
@@ -202,9 +209,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.BN), uint32_t(p.fmt)) | (1u << 15) | (1u << 16);
       const int k_steps = p.k_stage / 16;
       int it = 0, tr_n = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-        const int stage = it % p.stages;
-        const uint32_t phase = uint32_t(it / p.stages) & 1u;
         BDBNN_WTR(1, 0);
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
@@ -230,6 +237,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         umma_commit(smem_u32(&empty_bar[stage]));
         BDBNN_WTR(1, 4);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(smem_u32(&accum_bar));
     }
