@@ -593,7 +593,13 @@ int launch_tc_conv2(const TcConvLaunch& L, int mode, cudaStream_t st) {
   // layer2 fwd 0.109 -> 0.097 ms, stride-2 fwd 0.081 -> 0.058), TS=4 wins for K >= 256 (layers 3, 4).
   static const int ts128 = [] { const char* e = getenv("BDBNN_TC_TS128"); return e ? atoi(e) : 0; }();
   const int ts_auto = (L.Kc * L.a_halves <= 128) ? 2 : 4;
-  p.TS = p.BN == 256 ? 2 : (p.BN == 64 ? 4 : (ts128 == 4 ? 4 : (ts128 == 2 ? 2 : ts_auto)));
+  // 256-wide N tiles: ONE M tile per work item and two accumulator buffers (BDBNN_TC_TS256=2: two tiles, one buffer).
+  // The 14x14 / 7x7 layers have 128-196 two-tile items for 148 CTAs — one item per CTA, nothing to overlap its
+  // epilogue with (ncu: epilogue warps 59 % of the samples waiting for the accumulator, producer / MMA warps done
+  // early); with one-tile items a CTA's second item runs under the first one's epilogue: dgrad 2.08 -> 2.00 ms per
+  // step at twice the weight traffic per pixel (forward unchanged).
+  static const int ts256 = [] { const char* e = getenv("BDBNN_TC_TS256"); return e ? atoi(e) : 1; }();
+  p.TS = p.BN == 256 ? (ts256 == 1 ? 1 : 2) : (p.BN == 64 ? 4 : (ts128 == 4 ? 4 : (ts128 == 2 ? 2 : ts_auto)));
   p.NB = 512 / (p.TS * p.BN);
   p.alpha = L.alpha; p.mask = L.mask; p.out = L.out;
   p.out_i16 = mode == 0 ? L.out_i16 : nullptr;
