@@ -678,8 +678,8 @@ class _WgradSide:
     def __init__(self):
         self.active = False
         self.stream = None
-        self.bufs = {}       # id(param) -> persistent fp32 buffer the side-stream wgrad writes (param's shape, contiguous)
-        self.used = []       # (param, buffer) written in this scope
+        self.used = []       # (param, buffer) written in this scope; the persistent fp32 buffer (param's shape,
+                             # contiguous) lives on the parameter as `_bdbnn_wgrad_buf`, so it dies with it
         self.keep = []       # operands the side stream still reads: referenced until the join
         self.sink = None     # ddp.GradAllReduce: owns the buffers and folds them into its flat gradient buffer
 
@@ -688,15 +688,17 @@ class _WgradSide:
         Orders the side stream after everything enqueued on the current stream so far."""
         if not self.active or param is None or not param.is_leaf or not param.requires_grad:
             return None
+        if param.device != self.stream.device:       # a parameter of another device: keep it on autograd's path
+            return None
         if self.sink is not None:
             buf = self.sink.side_target(param, self.stream)
             if buf is None:
                 return None
         else:
-            buf = self.bufs.get(id(param))
+            buf = getattr(param, "_bdbnn_wgrad_buf", None)
             if buf is None or buf.shape != param.shape or buf.device != param.device:
                 buf = torch.empty(param.shape, dtype=torch.float32, device=param.device)
-                self.bufs[id(param)] = buf
+                param._bdbnn_wgrad_buf = buf
         self.stream.wait_stream(torch.cuda.current_stream())
         self.used.append((param, buf))
         return buf

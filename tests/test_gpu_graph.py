@@ -154,7 +154,7 @@ def test_wgrad_side_stream_equals_single_stream(net, kurt, monkeypatch):
     assert not F_._WSIDE.used and not F_._WSIDE.keep
     for graphed in (False, True):
         l1, g1 = grads(True, graphed)
-        assert F_._WSIDE.bufs and not F_._WSIDE.active and not F_._WSIDE.keep
+        assert not F_._WSIDE.active and not F_._WSIDE.keep and F_._WSIDE.stream is not None
         assert l1 == pytest.approx(l0, rel=1e-6)
         for n in g0:
             err = (g0[n].double() - g1[n].double()).norm().item()
