@@ -178,6 +178,58 @@ def test_gloo_world2_gradient_allreduce(tmp_path):
     torch.testing.assert_close(res[True], res[False], rtol=1e-6, atol=1e-7)
 
 
+def test_allreduce_bucket_accounting_with_side_stream_gradients():
+    """Host logic of GradAllReduce's bucket scheduling (no process group, `_launch` recorded instead of issued): a
+    bucket is issued one event AFTER its last parameter was accounted for; a conv weight whose gradient is written by
+    a side-stream GEMM (`side_target`) and ALSO receives an autograd term (kurtosis) is counted once; the lagged
+    issue therefore still happens after that term's accumulation hook; a gradient arriving after its bucket was
+    issued raises; `__call__`-time reset re-arms everything."""
+    import torch.nn as nn
+    from bdbnn_b200.ddp import GradAllReduce
+    m = nn.Sequential(nn.Conv2d(4, 4, 3, bias=False), nn.BatchNorm2d(4), nn.Conv2d(4, 4, 3, bias=False), nn.BatchNorm2d(4))
+    red = GradAllReduce(m, broadcast_params=False, n_buckets=2)           # world 1: no hooks registered, no NCCL
+    assert len(red.buckets) == 2
+    red.overlap = True                                                     # drive the scheduling by hand
+    issued = []
+    red._launch = lambda b: (issued.append(b), red._works.__setitem__(b, "work"))
+    w1, g1, b1, w2, g2, b2 = list(m.parameters())
+    order = list(reversed(red.params))                                     # flat layout = reverse registration
+    assert [id(p) for p in order] == [id(p) for p in (b2, g2, w2, b1, g1, w1)]
+    assert [red._bucket_of[id(p)] for p in order] == [0, 0, 0, 1, 1, 1]    # 152 + 152 elements
+    # --- backward of the last unit: side-stream wgrad of w2, then the autograd hooks of its BN parameters
+    buf = red.side_target(w2, stream=None)
+    assert buf is not None and buf.shape == w2.shape and buf.data_ptr() != red._view[id(w2)].data_ptr()
+    assert red.wflat is not None and float(red.wflat.abs().sum()) == 0.0
+    for p in (g2, b2):
+        p.grad = red._view[id(p)]
+        red._hook(p)
+    assert issued == [] and red._armed == [0]                              # complete, but not issued yet
+    # w2's kurtosis term: its post-accumulate hook is the next event — the accumulation is already enqueued, so the
+    # flush inside this hook covers it; w2 itself is counted once
+    red._hook(w2)
+    assert issued == [0] and red._pending == [0, 3]
+    # --- next unit
+    red.side_target(w1, stream=None)
+    for p in (g1, b1):
+        red._hook(p)
+    assert issued == [0] and red._armed == [1] and red._pending == [0, 0]
+    # a gradient for an already-issued bucket is an error, not a silent stale reduce
+    try:
+        red._hook(b2)
+        raise AssertionError("late gradient accepted")
+    except RuntimeError as e:
+        assert "after its bucket" in str(e)
+    # the remaining bucket goes out in __call__ (world 1: nothing to reduce) and the state is re-armed
+    red.world = 2
+    red.scale = False
+    red._works = [type("W", (), {"wait": lambda self: None})() if w is not None else None for w in red._works]
+    red._launch = lambda b: (issued.append(b), red._works.__setitem__(b, type("W", (), {"wait": lambda self: None})()))
+    red()
+    assert sorted(issued) == [0, 1]
+    assert red._pending == [b[2] for b in red.buckets] and not red._done and not red._armed and not red._side_now
+    assert set(red._side_ever) == {id(w1), id(w2)}
+
+
 def test_ede_attributes_and_activation_rule():
     """train.py:412-415 assigns .k/.t onto every nn.Conv2d; only the cifar class reacts, and only
     after both were assigned."""
