@@ -373,8 +373,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner (and NCCL_DEBUG output) on stdout: keep stdout to the one JSON line
+        # NCCL prints its version banner (and NCCL_DEBUG output) on stdout: keep stdout to the one JSON line.
+        # NCCL_DEBUG_FILE is only honoured above the VERSION level, so a bare VERSION setting becomes WARN.
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True            # train.py:368
     torch.manual_seed(0)
